@@ -1,0 +1,165 @@
+/*
+ * rsb200.h -- C ABI of librsb200.so: the B200 (sm_100a) kernels behind RoboSat's segmentation hot path.
+ *
+ * The reference (mapbox/robosat @ cbb1c73) has no FFI of its own: its "operator interface" for this
+ * path is a handful of PyTorch call sites. Every entry point below names the reference call site it
+ * replaces (file:line under /root/reference). Host code (robosat_b200/*.py) binds these with ctypes.
+ *
+ * Conventions
+ *   - plain C types only; every pointer is a DEVICE pointer unless the name ends in _host
+ *   - the library never allocates or frees user tensors and never synchronises: all work is enqueued
+ *     on the `stream` argument (a cudaStream_t passed as void*)
+ *   - return value: 0 on success, negative RSB_E_* on failure; rsb_last_error() gives the message
+ *     (thread local). There is NO CPU fallback: without a usable sm_100 device every compute entry fails.
+ *   - activations are NHWC fp16 ("channels last"), accumulators fp32; weights are pre-packed fp16
+ */
+#ifndef RSB200_H
+#define RSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSB_OK 0
+#define RSB_E_INVALID -1   /* bad argument / unsupported shape */
+#define RSB_E_CUDA -2      /* CUDA runtime or driver error */
+#define RSB_E_NODEVICE -3  /* no sm_100 device / driver entry point missing */
+
+#define RSB_MAX_SEGS 12
+#define RSB_MAX_SRCS 4
+
+int rsb_version(void);
+const char* rsb_last_error(void);
+/* 0 if a compute-capability-10.x device is current and the TMA driver entry point resolves */
+int rsb_device_ok(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution on tcgen05 tensor cores (fp16 x fp16 -> fp32 in tensor memory).
+ *
+ * Replaces every nn.Conv2d (+ folded eval BatchNorm, + ReLU, + residual add, + nearest x2 upsample,
+ * + channel concat) the forward pass runs:
+ *   resnet conv1 / layer1-4 Bottleneck convs      robosat/unet.py:122-130 (torchvision resnet.py Bottleneck.forward)
+ *   ConvRelu.forward                              robosat/unet.py:44
+ *   DecoderBlock.forward (interpolate + ConvRelu) robosat/unet.py:73
+ *   torch.cat([enc, dec], dim=1)                  robosat/unet.py:134-137
+ *   final 1x1 conv + bias                         robosat/unet.py:141
+ *
+ * One output tile = 128 "tile-space" pixels (box TW x TH x TN of one source view) x BLOCK_N output
+ * channels. The contraction is a list of segments; each segment is one TMA box load per 64-channel
+ * block from source view `src` displaced by (dh, dw) pixels, multiplied by the next 64 columns of the
+ * packed weight matrix [phases*Cout][K]. Strided convs use parity views of the input, the nearest
+ * x2 upsample uses 4 output phases of 2x2 taps on the low-resolution input (pre-summed weights),
+ * channel concat uses two sources; none of them materialises an intermediate tensor.
+ */
+typedef struct rsb_conv_src {
+    const void* ptr;      /* fp16 base of the view (already offset for parity / padding) */
+    int64_t pitch_w;      /* element strides of the view */
+    int64_t pitch_h;
+    int64_t pitch_n;
+    int32_t C;            /* innermost extent (channels, or window elements for overlapped views) */
+    int32_t W, H, N;      /* extents of the view (TMA zero-fills outside) */
+} rsb_conv_src;
+
+typedef struct rsb_conv_seg {
+    int32_t src;          /* index into srcs[] */
+    int32_t dh, dw;       /* displacement in tile-space pixels, for phase (0,0) */
+    int32_t cblocks;      /* number of 64-element blocks taken from that source */
+} rsb_conv_seg;
+
+typedef struct rsb_conv_desc {
+    int32_t nsrc;
+    rsb_conv_src srcs[RSB_MAX_SRCS];
+    int32_t nseg;
+    rsb_conv_seg segs[RSB_MAX_SEGS];
+
+    const void* weights;  /* fp16 [phases * Cout][K], K = 64 * sum(cblocks), K contiguous */
+    const float* bias;    /* fp32 [Cout] (folded BatchNorm shift / conv bias) or NULL */
+    int32_t Cout;         /* multiple of block_n */
+    int32_t block_n;      /* 32, 64, 128 or 256 */
+    int32_t phases;       /* 1, or 4 for the fused nearest-x2 upsample (phase p = 2*a+b adds (a,b) to every (dh,dw)) */
+
+    int32_t Wt, Ht, Nt;   /* tile-space extents (the pixels that produce outputs) */
+    int32_t TW, TH, TN;   /* tile box, TW*TH*TN == 128 */
+
+    /* output: pixel (n, h, w) of tile space, phase (a, b) -> out + n*pitch_n + (h*sy+a)*pitch_h + (w*sx+b)*pitch_w + c */
+    void* out;            /* fp16 (mode 0) */
+    int64_t out_pitch_w, out_pitch_h, out_pitch_n;
+    int32_t out_sy, out_sx;
+    const void* residual; /* fp16, same addressing as out, added before ReLU; or NULL */
+    int32_t relu;
+
+    /* mode 1 ("head"): block_n == Cout == 32; ReLU(acc) is contracted in fp32 with head_w [classes][32] + head_b
+     * and written as fp32 NCHW logits [N][classes][Ht][Wt] to head_out (final 1x1 conv, unet.py:141) */
+    int32_t mode;
+    int32_t head_classes; /* <= 8 */
+    const float* head_w;
+    const float* head_b;
+    float* head_out;
+} rsb_conv_desc;
+
+typedef struct rsb_conv_plan rsb_conv_plan;
+
+int rsb_conv_plan_create(const rsb_conv_desc* desc, rsb_conv_plan** out_plan);
+void rsb_conv_plan_destroy(rsb_conv_plan* plan);
+/* number of CTAs / tiles the plan launches (for tests and occupancy accounting) */
+int rsb_conv_plan_info(const rsb_conv_plan* plan, int32_t* grid, int32_t* tiles, int32_t* kblocks, int32_t* smem_bytes);
+int rsb_conv_run(const rsb_conv_plan* plan, void* stream);
+/* same contraction with a plain SIMT kernel reading global memory directly (no TMA / tcgen05).
+ * Test-only checker used to bisect the tensor-core path on the device; never on the product path. */
+int rsb_conv_run_simt_check(const rsb_conv_desc* desc, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Input pre-pass. Replaces `images.to(device)` + the stem's NCHW read (predict.py:83, train.py:172) and,
+ * for uint8 input, ToTensor + Normalize (predict.py:71-73). Writes the space-to-depth view the stem
+ * convolution consumes: fp16 [N][H/2][W/2 + 4][16], pixel (hh, ww) at column ww + 2, channel
+ * (ph*2 + pw)*3 + c = x[n, c, 2*hh+ph, 2*ww+pw]; channels 12..15 and the pad columns are zero.
+ *   src_kind 0: fp32 NCHW, already normalised (the reference API)     src_kind 1: uint8 NHWC raw RGB
+ */
+int rsb_prepass_s2d(const void* src, int32_t src_kind, void* dst, int32_t N, int32_t H, int32_t W,
+                    const float* mean3_host, const float* std3_host, void* stream);
+
+/* NHWC fp16 max pooling. Replaces resnet.maxpool (unet.py:125: k3 s2 p1) and F.max_pool2d(enc4, 2, 2) (unet.py:132).
+ * Output pixel pitches are explicit so the result can land inside a padded buffer. */
+int rsb_maxpool_nhwc(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t s,
+                     int32_t p, void* stream);
+
+/* Predict head. Replaces softmax(outputs, 1) ... np.digitize(foreground, linspace(0,1,256)).astype(uint8)
+ * (predict.py:87, 93, 98-103) for the 2-class case, including the crop of the `overlap` border (datasets.py:133-136).
+ * logits fp32 [N][2][H][W] -> quant uint8 [N][H-2o][W-2o]; probs_fg (fp32, same cropped shape) optional. */
+int rsb_head_quantize(const float* logits, uint8_t* quant, float* probs_fg, int32_t N, int32_t H, int32_t W,
+                      int32_t overlap, void* stream);
+/* softmax over C for any class count: logits fp32 [N][C][H][W] -> probs fp32 same shape (predict.py:87) */
+int rsb_softmax_nchw(const float* logits, float* probs, int32_t N, int32_t C, int32_t HW, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Losses and metrics on fp32 NCHW logits + int64 targets [N][H][W].
+ */
+/* CrossEntropyLoss2d.forward (losses.py:24-25): weighted NLL of log_softmax, mean over sum of target weights.
+ * loss_out: fp32 scalar; grad (optional, fp32 NCHW) receives dLoss/dlogits. weight may be NULL (all ones).
+ * scratch: >= 2 doubles, zeroed by the call. */
+int rsb_cross_entropy(const float* logits, const int64_t* targets, const float* weight, float* loss_out, float* grad,
+                      double* scratch, int32_t N, int32_t C, int32_t HW, void* stream);
+
+/* LovaszLoss2d.forward (losses.py:96-119) and its closed-form gradient, per image:
+ * errors e = 1 - (2*onehot-1)*x over the flattened C*H*W vector, descending sort, Jaccard gradient, dot(relu(e), J).
+ * workspace: rsb_lovasz_workspace_bytes(N, C, HW) bytes. loss_out: fp32 scalar (mean over N). grad optional. */
+int64_t rsb_lovasz_workspace_bytes(int32_t N, int32_t C, int32_t HW);
+int rsb_lovasz(const float* logits, const int64_t* targets, float* loss_out, float* grad, void* workspace,
+               int64_t workspace_bytes, int32_t N, int32_t C, int32_t HW, void* stream);
+
+/* Metrics.add (metrics.py:27-41) for a whole batch: counts[4] += {tn, fn, fp, tp} with the reference's
+ * argmax / (pred/actual in {NaN, inf, 0, 1}) semantics. counts: int64[4] on the device, accumulated. */
+int rsb_metrics_count(const float* logits, const int64_t* targets, int64_t* counts, int32_t N, int32_t C, int32_t HW,
+                      void* stream);
+
+/* torch.optim.Adam.step (train.py:81,188) over one flat fp32 parameter arena:
+ * betas (b1,b2), eps, no weight decay, no amsgrad; `step` is the 1-based step count for bias correction. */
+int rsb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float b1,
+                  float b2, float eps, int32_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSB200_H */

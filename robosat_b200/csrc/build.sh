@@ -1,0 +1,13 @@
+#!/bin/sh
+# Build librsb200.so in-tree for sm_100a. Usage: sh robosat_b200/csrc/build.sh
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr"
+OBJS=""
+for f in rsb_host rsb_conv rsb_elementwise rsb_loss; do
+  $NVCC $FLAGS -c $f.cu -o $f.o 2> $f.ptxas.log || { cat $f.ptxas.log; exit 1; }
+  OBJS="$OBJS $f.o"
+done
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../librsb200.so $OBJS -cudart static
+echo "built $(cd .. && pwd)/librsb200.so"

@@ -1,0 +1,545 @@
+// Implicit-GEMM convolution for sm_100a: TMA box loads -> 128B-swizzled shared memory ->
+// tcgen05.mma (fp16 x fp16 -> fp32 accumulators in tensor memory) -> fused epilogue.
+//
+// Persistent, warp-specialised CTA (192 threads, one CTA per SM):
+//   warp 0      TMA producer   one elected lane issues cp.async.bulk.tensor for the A box and the weight tile
+//   warp 1      MMA issuer     one elected lane issues 4 x tcgen05.mma (K=16) per 64-wide K block; owns TMEM alloc
+//   warps 2..5  epilogue       tcgen05.ld 32 rows x 32 columns per warp, bias / residual / ReLU, fp16 NHWC stores
+// Pipelines: smem ring (full/empty mbarriers, TMA <-> MMA) and a 2-deep TMEM accumulator ring
+// (tmem_full / tmem_empty, MMA <-> epilogue) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// A-operand addressing (what makes this a convolution rather than a GEMM) is entirely in the TMA
+// coordinates: a tile is a TW x TH x TN box of pixels of one source *view*; every filter tap is the same
+// box displaced by (dh, dw), zero-filled by TMA outside the view (= the conv's zero padding). Strided
+// convs read parity views, the nearest x2 upsample runs as 4 output phases with 2x2 taps on the low-res
+// input, channel concat is two views. See include/rsb200.h for the reference call sites this replaces.
+
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/rsb200.h"
+#include "rsb_host.h"
+#include "rsb_ptx.cuh"
+
+namespace rsb {
+
+static constexpr int kBlockM = 128;
+static constexpr int kBlockK = 64;  // fp16 elements = 128 bytes = one swizzle row
+static constexpr int kABytes = kBlockM * kBlockK * 2;
+static constexpr int kNumThreads = 192;
+
+struct alignas(64) ConvKParams {
+    CUtensorMap tmA[RSB_MAX_SRCS];
+    CUtensorMap tmB;
+    int32_t nseg;
+    int32_t seg_src[RSB_MAX_SEGS];
+    int32_t seg_dh[RSB_MAX_SEGS];
+    int32_t seg_dw[RSB_MAX_SEGS];
+    int32_t seg_cb[RSB_MAX_SEGS];
+    int32_t kblocks;
+    int32_t tiles_w, tiles_h, tiles_n, n_blocks, phases, total_tiles;
+    int32_t TW, TH, TN;
+    int32_t Wt, Ht, Nt;
+    int32_t Cout;
+    int32_t out_sy, out_sx;
+    int64_t out_pitch_w, out_pitch_h, out_pitch_n;
+    __half* out;
+    const __half* residual;
+    const float* bias;
+    int32_t relu;
+    int32_t head_classes;
+    const float* head_w;
+    const float* head_b;
+    float* head_out;
+};
+
+template <int BLOCK_N>
+struct ConvCfg {
+    static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+    // stages + barriers (full, empty per stage; tmem_full, tmem_empty x2) + tmem ptr, plus 1 KB alignment slack
+    static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+};
+
+struct TileCoord {
+    int n_blk, pa, pb, phase, w0, h0, n0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int id) {
+    TileCoord t;
+    t.n_blk = id % p.n_blocks;
+    id /= p.n_blocks;
+    t.phase = id % p.phases;
+    id /= p.phases;
+    t.pa = t.phase >> 1;
+    t.pb = t.phase & 1;
+    t.w0 = (id % p.tiles_w) * p.TW;
+    id /= p.tiles_w;
+    t.h0 = (id % p.tiles_h) * p.TH;
+    id /= p.tiles_h;
+    t.n0 = id * p.TN;
+    return t;
+}
+
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
+    using Cfg = ConvCfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    // 128B swizzle atoms repeat every 1024 bytes: tile bases must be 1024-byte aligned
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + Cfg::kStages * kABytes;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + Cfg::kStages;
+    uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp_idx = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp_idx == 0 && lane == 0) {
+        for (int i = 0; i < RSB_MAX_SRCS; ++i) tma_prefetch_desc(&p.tmA[i]);
+        tma_prefetch_desc(&p.tmB);
+        for (int i = 0; i < Cfg::kStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full_bar[i], 1);
+            mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+        }
+        mbar_fence_init();
+    }
+    if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp_idx == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                const TileCoord t = decode_tile(p, tile);
+                const int b_row = t.phase * p.Cout + t.n_blk * BLOCK_N;
+                int kb = 0;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const CUtensorMap* tm = &p.tmA[p.seg_src[s]];
+                    const int cw = t.w0 + p.seg_dw[s] + t.pb;
+                    const int ch = t.h0 + p.seg_dh[s] + t.pa;
+                    for (int cb = 0; cb < p.seg_cb[s]; ++cb, ++kb) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                        tma_load_4d(smem_a + stage * kABytes, tm, &full_bar[stage], cb * kBlockK, cw, ch, t.n0);
+                        tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, b_row);
+                        if (++stage == Cfg::kStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp_idx == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (elect_one()) {
+            constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * kABytes));
+                    const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
+                        umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+                    if (++stage == Cfg::kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+                umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+                if (++acc == 2) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp_idx & 3;  // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const int tw = row % p.TW;
+        const int th = (row / p.TW) % p.TH;
+        const int tn = row / (p.TW * p.TH);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            const TileCoord t = decode_tile(p, tile);
+            const int w = t.w0 + tw, h = t.h0 + th, n = t.n0 + tn;
+            const bool valid = (w < p.Wt) && (h < p.Ht) && (n < p.Nt);
+            mbar_wait(&tmem_full_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+
+            if constexpr (MODE == 0) {
+                const int64_t off = static_cast<int64_t>(n) * p.out_pitch_n +
+                                    static_cast<int64_t>(h * p.out_sy + t.pa) * p.out_pitch_h +
+                                    static_cast<int64_t>(w * p.out_sx + t.pb) * p.out_pitch_w + t.n_blk * BLOCK_N;
+                __half* optr = p.out + off;
+                const __half* rptr = p.residual ? p.residual + off : nullptr;
+                const float* bptr = p.bias ? p.bias + t.n_blk * BLOCK_N : nullptr;
+#pragma unroll 1
+                for (int c = 0; c < BLOCK_N; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c, r);
+                    tmem_ld_wait();
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                    if (bptr) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bptr + c + j));
+                            v[j] += b4.x;
+                            v[j + 1] += b4.y;
+                            v[j + 2] += b4.z;
+                            v[j + 3] += b4.w;
+                        }
+                    }
+                    if (rptr && valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rptr + c + j));
+                            const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const float2 f = __half22float2(h2[u]);
+                                v[j + 2 * u] += f.x;
+                                v[j + 2 * u + 1] += f.y;
+                            }
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+                    }
+                    if (valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 o4;
+                            __half2* h2 = reinterpret_cast<__half2*>(&o4);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) h2[u] = __floats2half2_rn(v[j + 2 * u], v[j + 2 * u + 1]);
+                            *reinterpret_cast<uint4*>(optr + c + j) = o4;
+                        }
+                    }
+                }
+            } else {
+                // head: ReLU(acc) [32 ch] -> fp32 1x1 conv to `classes` logits, NCHW fp32 store
+                static_assert(MODE == 0 || BLOCK_N == 32, "head mode needs BLOCK_N == 32");
+                uint32_t r[32];
+                tmem_ld_32x32(taddr, r);
+                tmem_ld_wait();
+                float v[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float a = __uint_as_float(r[j]);
+                    if (p.bias) a += __ldg(p.bias + j);
+                    v[j] = p.relu ? fmaxf(a, 0.0f) : a;
+                }
+                for (int k = 0; k < p.head_classes; ++k) {
+                    float s = __ldg(p.head_b + k);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) s = fmaf(__ldg(p.head_w + k * 32 + j), v[j], s);
+                    if (valid) {
+                        p.head_out[((static_cast<int64_t>(n) * p.head_classes + k) * p.Ht + h) * p.Wt + w] = s;
+                    }
+                }
+            }
+
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (++acc == 2) {
+                acc = 0;
+                acc_phase ^= 1;
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp_idx == 1) {
+        tc_fence_after();
+        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SIMT checker: the same contraction read straight from global memory (tests only).
+__global__ void conv_simt_check_kernel(rsb_conv_desc d, int K) {
+    const int64_t total_px = static_cast<int64_t>(d.Nt) * d.Ht * d.Wt * d.phases;
+    const int co_per_thread = d.mode == 1 ? d.Cout : 1;
+    const int co_threads = d.Cout / co_per_thread;
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gid >= total_px * co_threads) return;
+    const int co0 = static_cast<int>(gid % co_threads) * co_per_thread;
+    int64_t px = gid / co_threads;
+    const int phase = static_cast<int>(px % d.phases);
+    px /= d.phases;
+    const int w = static_cast<int>(px % d.Wt);
+    px /= d.Wt;
+    const int h = static_cast<int>(px % d.Ht);
+    const int n = static_cast<int>(px / d.Ht);
+    const int pa = phase >> 1, pb = phase & 1;
+    const __half* wts = static_cast<const __half*>(d.weights);
+
+    float head_acc[8];
+    for (int k = 0; k < 8; ++k) head_acc[k] = (d.mode == 1 && k < d.head_classes) ? d.head_b[k] : 0.f;
+
+    for (int co = co0; co < co0 + co_per_thread; ++co) {
+        const __half* wrow = wts + (static_cast<int64_t>(phase) * d.Cout + co) * K;
+        float acc = 0.f;
+        int kidx = 0;
+        for (int s = 0; s < d.nseg; ++s) {
+            const rsb_conv_src& src = d.srcs[d.segs[s].src];
+            const int hh = h + d.segs[s].dh + pa, ww = w + d.segs[s].dw + pb;
+            const bool inb = hh >= 0 && hh < src.H && ww >= 0 && ww < src.W && n < src.N;
+            const __half* a = static_cast<const __half*>(src.ptr) + n * src.pitch_n + hh * src.pitch_h + ww * src.pitch_w;
+            for (int c = 0; c < d.segs[s].cblocks * 64; ++c, ++kidx) {
+                if (inb && c < src.C) acc += __half2float(a[c]) * __half2float(wrow[kidx]);
+            }
+        }
+        if (d.bias) acc += d.bias[co];
+        const int64_t off = n * d.out_pitch_n + static_cast<int64_t>(h * d.out_sy + pa) * d.out_pitch_h +
+                            static_cast<int64_t>(w * d.out_sx + pb) * d.out_pitch_w + co;
+        if (d.mode == 0) {
+            if (d.residual) acc += __half2float(static_cast<const __half*>(d.residual)[off]);
+            if (d.relu) acc = fmaxf(acc, 0.f);
+            static_cast<__half*>(d.out)[off] = __float2half_rn(acc);
+        } else {
+            if (d.relu) acc = fmaxf(acc, 0.f);
+            for (int k = 0; k < d.head_classes; ++k) head_acc[k] = fmaf(d.head_w[k * 32 + co], acc, head_acc[k]);
+        }
+    }
+    if (d.mode == 1) {
+        for (int k = 0; k < d.head_classes; ++k)
+            d.head_out[((static_cast<int64_t>(n) * d.head_classes + k) * d.Ht + h) * d.Wt + w] = head_acc[k];
+    }
+}
+
+}  // namespace rsb
+
+// ================================================================================================
+// host side
+// ================================================================================================
+using namespace rsb;
+
+struct rsb_conv_plan {
+    ConvKParams kp;
+    int block_n;
+    int mode;
+    int grid;
+    int smem;
+};
+
+static int validate_desc(const rsb_conv_desc* d, int* K_out) {
+    if (!d) return set_error(RSB_E_INVALID, "conv: null desc");
+    if (d->nsrc < 1 || d->nsrc > RSB_MAX_SRCS) return set_error(RSB_E_INVALID, "conv: nsrc out of range");
+    if (d->nseg < 1 || d->nseg > RSB_MAX_SEGS) return set_error(RSB_E_INVALID, "conv: nseg out of range");
+    if (!(d->block_n == 32 || d->block_n == 64 || d->block_n == 128 || d->block_n == 256))
+        return set_error(RSB_E_INVALID, "conv: block_n must be 32/64/128/256");
+    if (d->Cout <= 0 || d->Cout % d->block_n) return set_error(RSB_E_INVALID, "conv: Cout not a multiple of block_n");
+    if (!(d->phases == 1 || d->phases == 4)) return set_error(RSB_E_INVALID, "conv: phases must be 1 or 4");
+    if (d->TW * d->TH * d->TN != kBlockM) return set_error(RSB_E_INVALID, "conv: TW*TH*TN must be 128");
+    if (d->Wt <= 0 || d->Ht <= 0 || d->Nt <= 0) return set_error(RSB_E_INVALID, "conv: empty tile space");
+    if (!d->weights) return set_error(RSB_E_INVALID, "conv: null weights");
+    int kblocks = 0;
+    for (int s = 0; s < d->nseg; ++s) {
+        const rsb_conv_seg& g = d->segs[s];
+        if (g.src < 0 || g.src >= d->nsrc || g.cblocks < 1) return set_error(RSB_E_INVALID, "conv: bad segment");
+        if (g.cblocks * kBlockK > ((d->srcs[g.src].C + kBlockK - 1) / kBlockK) * kBlockK)
+            return set_error(RSB_E_INVALID, "conv: segment reads past the source's inner extent");
+        kblocks += g.cblocks;
+    }
+    for (int i = 0; i < d->nsrc; ++i) {
+        const rsb_conv_src& s = d->srcs[i];
+        if (!s.ptr || (reinterpret_cast<uintptr_t>(s.ptr) & 15)) return set_error(RSB_E_INVALID, "conv: source pointer null or not 16B aligned");
+        if ((s.pitch_w * 2) % 16 || (s.pitch_h * 2) % 16 || (s.pitch_n * 2) % 16)
+            return set_error(RSB_E_INVALID, "conv: source pitches must be multiples of 16 bytes");
+        if (s.C < 1 || s.W < 1 || s.H < 1 || s.N < 1) return set_error(RSB_E_INVALID, "conv: empty source view");
+    }
+    if (d->mode == 0) {
+        if (!d->out) return set_error(RSB_E_INVALID, "conv: null out");
+        if ((reinterpret_cast<uintptr_t>(d->out) & 15) || (d->out_pitch_w * 2) % 16 || (d->out_pitch_h * 2) % 16 ||
+            (d->out_pitch_n * 2) % 16)
+            return set_error(RSB_E_INVALID, "conv: out must be 16B aligned with 16B-multiple pitches");
+        if (d->residual && (reinterpret_cast<uintptr_t>(d->residual) & 15))
+            return set_error(RSB_E_INVALID, "conv: residual must be 16B aligned");
+    } else if (d->mode == 1) {
+        if (d->block_n != 32 || d->Cout != 32 || d->phases != 1) return set_error(RSB_E_INVALID, "conv: head mode needs Cout == block_n == 32, phases == 1");
+        if (d->head_classes < 1 || d->head_classes > 8 || !d->head_w || !d->head_b || !d->head_out)
+            return set_error(RSB_E_INVALID, "conv: bad head arguments");
+    } else {
+        return set_error(RSB_E_INVALID, "conv: unknown mode");
+    }
+    *K_out = kblocks * kBlockK;
+    return RSB_OK;
+}
+
+template <int BLOCK_N, int MODE>
+static int launch_conv(const rsb_conv_plan* plan, cudaStream_t stream) {
+    auto kern = conv_tc_kernel<BLOCK_N, MODE>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BLOCK_N>::kSmemBytes);
+        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv)");
+        attr_set = true;
+    }
+    kern<<<plan->grid, kNumThreads, ConvCfg<BLOCK_N>::kSmemBytes, stream>>>(plan->kp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "conv_tc_kernel launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_plan) {
+    if (!out_plan) return set_error(RSB_E_INVALID, "conv: null out_plan");
+    *out_plan = nullptr;
+    int K = 0;
+    int rc = validate_desc(d, &K);
+    if (rc) return rc;
+    rc = rsb_device_ok();
+    if (rc) return rc;
+
+    rsb_conv_plan* plan = new (std::nothrow) rsb_conv_plan();
+    if (!plan) return set_error(RSB_E_INVALID, "conv: out of host memory");
+    memset(&plan->kp, 0, sizeof(plan->kp));
+    ConvKParams& kp = plan->kp;
+
+    for (int i = 0; i < d->nsrc; ++i) {
+        const rsb_conv_src& s = d->srcs[i];
+        const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)s.N};
+        const uint64_t strides[3] = {(uint64_t)s.pitch_w * 2, (uint64_t)s.pitch_h * 2, (uint64_t)s.pitch_n * 2};
+        const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)d->TW, (uint32_t)d->TH, (uint32_t)d->TN};
+        rc = encode_tiled_f16(&kp.tmA[i], 4, s.ptr, dims, strides, box);
+        if (rc) {
+            delete plan;
+            return rc;
+        }
+    }
+    for (int i = d->nsrc; i < RSB_MAX_SRCS; ++i) kp.tmA[i] = kp.tmA[0];
+    {
+        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)d->phases * d->Cout};
+        const uint64_t strides[1] = {(uint64_t)K * 2};
+        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)d->block_n};
+        rc = encode_tiled_f16(&kp.tmB, 2, d->weights, dims, strides, box);
+        if (rc) {
+            delete plan;
+            return rc;
+        }
+    }
+    kp.nseg = d->nseg;
+    for (int s = 0; s < d->nseg; ++s) {
+        kp.seg_src[s] = d->segs[s].src;
+        kp.seg_dh[s] = d->segs[s].dh;
+        kp.seg_dw[s] = d->segs[s].dw;
+        kp.seg_cb[s] = d->segs[s].cblocks;
+    }
+    kp.kblocks = K / kBlockK;
+    kp.TW = d->TW;
+    kp.TH = d->TH;
+    kp.TN = d->TN;
+    kp.Wt = d->Wt;
+    kp.Ht = d->Ht;
+    kp.Nt = d->Nt;
+    kp.tiles_w = (d->Wt + d->TW - 1) / d->TW;
+    kp.tiles_h = (d->Ht + d->TH - 1) / d->TH;
+    kp.tiles_n = (d->Nt + d->TN - 1) / d->TN;
+    kp.n_blocks = d->Cout / d->block_n;
+    kp.phases = d->phases;
+    kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n * kp.n_blocks * kp.phases;
+    kp.Cout = d->Cout;
+    kp.out_sy = d->out_sy > 0 ? d->out_sy : 1;
+    kp.out_sx = d->out_sx > 0 ? d->out_sx : 1;
+    kp.out_pitch_w = d->out_pitch_w;
+    kp.out_pitch_h = d->out_pitch_h;
+    kp.out_pitch_n = d->out_pitch_n;
+    kp.out = static_cast<__half*>(d->out);
+    kp.residual = static_cast<const __half*>(d->residual);
+    kp.bias = d->bias;
+    kp.relu = d->relu;
+    kp.head_classes = d->head_classes;
+    kp.head_w = d->head_w;
+    kp.head_b = d->head_b;
+    kp.head_out = d->head_out;
+
+    plan->block_n = d->block_n;
+    plan->mode = d->mode;
+    const int sms = num_sms();
+    plan->grid = kp.total_tiles < sms ? kp.total_tiles : sms;
+    switch (d->block_n) {
+        case 32: plan->smem = ConvCfg<32>::kSmemBytes; break;
+        case 64: plan->smem = ConvCfg<64>::kSmemBytes; break;
+        case 128: plan->smem = ConvCfg<128>::kSmemBytes; break;
+        default: plan->smem = ConvCfg<256>::kSmemBytes; break;
+    }
+    *out_plan = plan;
+    return RSB_OK;
+}
+
+extern "C" void rsb_conv_plan_destroy(rsb_conv_plan* plan) { delete plan; }
+
+extern "C" int rsb_conv_plan_info(const rsb_conv_plan* plan, int32_t* grid, int32_t* tiles, int32_t* kblocks, int32_t* smem_bytes) {
+    if (!plan) return set_error(RSB_E_INVALID, "conv: null plan");
+    if (grid) *grid = plan->grid;
+    if (tiles) *tiles = plan->kp.total_tiles;
+    if (kblocks) *kblocks = plan->kp.kblocks;
+    if (smem_bytes) *smem_bytes = plan->smem;
+    return RSB_OK;
+}
+
+extern "C" int rsb_conv_run(const rsb_conv_plan* plan, void* stream_) {
+    if (!plan) return set_error(RSB_E_INVALID, "conv: null plan");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (plan->mode == 1) return launch_conv<32, 1>(plan, stream);
+    switch (plan->block_n) {
+        case 32: return launch_conv<32, 0>(plan, stream);
+        case 64: return launch_conv<64, 0>(plan, stream);
+        case 128: return launch_conv<128, 0>(plan, stream);
+        case 256: return launch_conv<256, 0>(plan, stream);
+    }
+    return set_error(RSB_E_INVALID, "conv: bad block_n");
+}
+
+extern "C" int rsb_conv_run_simt_check(const rsb_conv_desc* d, void* stream_) {
+    int K = 0;
+    int rc = validate_desc(d, &K);
+    if (rc) return rc;
+    const int64_t px = static_cast<int64_t>(d->Nt) * d->Ht * d->Wt * d->phases;
+    const int64_t threads = px * (d->mode == 1 ? 1 : d->Cout);
+    const int block = 128;
+    const int64_t grid = (threads + block - 1) / block;
+    if (grid > 0x7fffffff) return set_error(RSB_E_INVALID, "conv check: problem too large");
+    conv_simt_check_kernel<<<static_cast<unsigned>(grid), block, 0, static_cast<cudaStream_t>(stream_)>>>(*d, K);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_cuda_error(e, "conv_simt_check_kernel launch");
+    return RSB_OK;
+}

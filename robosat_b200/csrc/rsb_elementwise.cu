@@ -1,0 +1,195 @@
+// HBM-bound helper kernels around the convolution path: input pre-pass (normalise + space-to-depth),
+// NHWC max pooling, the predict head (softmax -> foreground -> quantise -> crop) and a generic softmax.
+// All are single-pass, 16-byte vectorised where the layout allows, grid sized from the element count.
+
+#include <cuda_fp16.h>
+
+#include "../../include/rsb200.h"
+#include "rsb_host.h"
+
+namespace rsb {
+
+struct Norm3 {
+    float mean[3];
+    float inv_std[3];
+    float std[3];
+};
+
+// dst fp16 [N][H2][W2 + 4][16]; one thread per (n, hh, padded column)
+template <int SRC_KIND>
+__global__ void prepass_s2d_kernel(const void* __restrict__ src, __half* __restrict__ dst, int N, int H, int W, Norm3 nm) {
+    const int H2 = H / 2, W2 = W / 2, Wp = W2 + 4;
+    const int64_t total = static_cast<int64_t>(N) * H2 * Wp;
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int wp = static_cast<int>(gid % Wp);
+    const int hh = static_cast<int>((gid / Wp) % H2);
+    const int n = static_cast<int>(gid / (static_cast<int64_t>(Wp) * H2));
+    __align__(16) __half v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __float2half_rn(0.f);
+    const int ww = wp - 2;
+    if (ww >= 0 && ww < W2) {
+#pragma unroll
+        for (int ph = 0; ph < 2; ++ph) {
+            const int h = 2 * hh + ph;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float x0, x1;
+                if (SRC_KIND == 0) {
+                    const float* s = static_cast<const float*>(src) + ((static_cast<int64_t>(n) * 3 + c) * H + h) * W + 2 * ww;
+                    const float2 f = *reinterpret_cast<const float2*>(s);
+                    x0 = f.x;
+                    x1 = f.y;
+                } else {
+                    const uint8_t* s = static_cast<const uint8_t*>(src) + ((static_cast<int64_t>(n) * H + h) * W + 2 * ww) * 3 + c;
+                    // ToTensor (u8 / 255) then Normalize ((x - mean) / std), both in fp32 like the reference
+                    x0 = (static_cast<float>(s[0]) / 255.0f - nm.mean[c]) / nm.std[c];
+                    x1 = (static_cast<float>(s[3]) / 255.0f - nm.mean[c]) / nm.std[c];
+                }
+                v[(ph * 2 + 0) * 3 + c] = __float2half_rn(x0);
+                v[(ph * 2 + 1) * 3 + c] = __float2half_rn(x1);
+            }
+        }
+    }
+    uint4* o = reinterpret_cast<uint4*>(dst + gid * 16);
+    o[0] = *reinterpret_cast<const uint4*>(&v[0]);
+    o[1] = *reinterpret_cast<const uint4*>(&v[8]);
+}
+
+// NHWC fp16 max pool, 8 channels (16 bytes) per thread
+__global__ void maxpool_nhwc_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int N, int H, int W, int C,
+                                    int k, int s, int p, int OH, int OW) {
+    const int C8 = C / 8;
+    const int64_t total = static_cast<int64_t>(N) * OH * OW * C8;
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int c8 = static_cast<int>(gid % C8);
+    int64_t r = gid / C8;
+    const int ow = static_cast<int>(r % OW);
+    r /= OW;
+    const int oh = static_cast<int>(r % OH);
+    const int n = static_cast<int>(r / OH);
+    __half2 m[4];
+    const __half2 ninf = __float2half2_rn(-65504.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) m[i] = ninf;
+    for (int dy = 0; dy < k; ++dy) {
+        const int h = oh * s - p + dy;
+        if (h < 0 || h >= H) continue;
+        for (int dx = 0; dx < k; ++dx) {
+            const int w = ow * s - p + dx;
+            if (w < 0 || w >= W) continue;
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + ((static_cast<int64_t>(n) * H + h) * W + w) * C + c8 * 8));
+            const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) m[i] = __hmax2(m[i], h2[i]);
+        }
+    }
+    *reinterpret_cast<uint4*>(dst + ((static_cast<int64_t>(n) * OH + oh) * OW + ow) * C + c8 * 8) = *reinterpret_cast<uint4*>(m);
+}
+
+// number of anchors of np.linspace(0, 1, 256) that are <= x, compared in float64 like np.digitize does
+__device__ __forceinline__ int digitize256(float xf) {
+    const double x = static_cast<double>(xf);
+    const double step = 1.0 / 255.0;
+    int k = static_cast<int>(floor(x * 255.0));
+    k = k < 0 ? 0 : (k > 255 ? 255 : k);
+    // anchor(j) = j * step for j < 255, anchor(255) = 1.0 exactly (linspace pins the endpoint)
+    auto anchor = [&](int j) { return j >= 255 ? 1.0 : static_cast<double>(j) * step; };
+    while (k < 255 && anchor(k + 1) <= x) ++k;
+    while (k >= 0 && anchor(k) > x) --k;
+    return k + 1;  // count of anchors <= x (0 when x < 0, 256 when x >= 1)
+}
+
+__global__ void head_quantize_kernel(const float* __restrict__ logits, uint8_t* __restrict__ quant, float* __restrict__ probs_fg,
+                                     int N, int H, int W, int o) {
+    const int OH = H - 2 * o, OW = W - 2 * o;
+    const int64_t total = static_cast<int64_t>(N) * OH * OW;
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int x = static_cast<int>(gid % OW);
+    const int y = static_cast<int>((gid / OW) % OH);
+    const int n = static_cast<int>(gid / (static_cast<int64_t>(OW) * OH));
+    const int64_t hw = static_cast<int64_t>(H) * W;
+    const int64_t pix = static_cast<int64_t>(y + o) * W + (x + o);
+    const float l0 = logits[(static_cast<int64_t>(n) * 2 + 0) * hw + pix];
+    const float l1 = logits[(static_cast<int64_t>(n) * 2 + 1) * hw + pix];
+    // softmax over 2 classes, max-subtracted like torch.softmax
+    const float m = fmaxf(l0, l1);
+    const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+    const float pfg = e1 / (e0 + e1);
+    if (probs_fg) probs_fg[gid] = pfg;
+    quant[gid] = static_cast<uint8_t>(digitize256(pfg));  // 256 wraps to 0 exactly like .astype(np.uint8)
+}
+
+__global__ void softmax_nchw_kernel(const float* __restrict__ logits, float* __restrict__ probs, int N, int C, int64_t HW) {
+    const int64_t total = static_cast<int64_t>(N) * HW;
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int64_t pix = gid % HW;
+    const int64_t n = gid / HW;
+    const float* l = logits + n * C * HW + pix;
+    float m = l[0];
+    for (int c = 1; c < C; ++c) m = fmaxf(m, l[c * HW]);
+    float s = 0.f;
+    for (int c = 0; c < C; ++c) s += expf(l[c * HW] - m);
+    float* o = probs + n * C * HW + pix;
+    for (int c = 0; c < C; ++c) o[c * HW] = expf(l[c * HW] - m) / s;
+}
+
+static inline unsigned grid_for(int64_t total, int block) { return static_cast<unsigned>((total + block - 1) / block); }
+
+}  // namespace rsb
+
+using namespace rsb;
+
+extern "C" int rsb_prepass_s2d(const void* src, int32_t src_kind, void* dst, int32_t N, int32_t H, int32_t W,
+                               const float* mean3_host, const float* std3_host, void* stream) {
+    if (!src || !dst || N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return set_error(RSB_E_INVALID, "prepass: bad arguments");
+    if (src_kind != 0 && src_kind != 1) return set_error(RSB_E_INVALID, "prepass: src_kind must be 0 (f32 NCHW) or 1 (u8 NHWC)");
+    Norm3 nm;
+    for (int c = 0; c < 3; ++c) {
+        nm.mean[c] = mean3_host ? mean3_host[c] : 0.f;
+        nm.std[c] = std3_host ? std3_host[c] : 1.f;
+        nm.inv_std[c] = 1.f / nm.std[c];
+    }
+    const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2 + 4);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (src_kind == 0)
+        prepass_s2d_kernel<0><<<grid_for(total, 256), 256, 0, st>>>(src, static_cast<__half*>(dst), N, H, W, nm);
+    else
+        prepass_s2d_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(src, static_cast<__half*>(dst), N, H, W, nm);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "prepass_s2d launch");
+}
+
+extern "C" int rsb_maxpool_nhwc(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t s,
+                                int32_t p, void* stream) {
+    if (!src || !dst || N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 8) || k < 1 || s < 1 || p < 0)
+        return set_error(RSB_E_INVALID, "maxpool: bad arguments (C must be a multiple of 8)");
+    const int OH = (H + 2 * p - k) / s + 1, OW = (W + 2 * p - k) / s + 1;
+    const int64_t total = static_cast<int64_t>(N) * OH * OW * (C / 8);
+    maxpool_nhwc_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(src), static_cast<__half*>(dst), N, H, W, C, k, s, p, OH, OW);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "maxpool launch");
+}
+
+extern "C" int rsb_head_quantize(const float* logits, uint8_t* quant, float* probs_fg, int32_t N, int32_t H, int32_t W,
+                                 int32_t overlap, void* stream) {
+    if (!logits || !quant || N <= 0 || overlap < 0 || H - 2 * overlap <= 0 || W - 2 * overlap <= 0)
+        return set_error(RSB_E_INVALID, "head_quantize: bad arguments");
+    const int64_t total = static_cast<int64_t>(N) * (H - 2 * overlap) * (W - 2 * overlap);
+    head_quantize_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, quant, probs_fg, N, H, W, overlap);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "head_quantize launch");
+}
+
+extern "C" int rsb_softmax_nchw(const float* logits, float* probs, int32_t N, int32_t C, int32_t HW, void* stream) {
+    if (!logits || !probs || N <= 0 || C <= 0 || HW <= 0) return set_error(RSB_E_INVALID, "softmax: bad arguments");
+    const int64_t total = static_cast<int64_t>(N) * HW;
+    softmax_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, probs, N, C, HW);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "softmax launch");
+}

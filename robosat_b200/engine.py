@@ -1,0 +1,416 @@
+"""Host-side plan of the U-Net forward pass on librsb200.so.
+
+`UNetEngine` turns a reference-format `state_dict` (robosat/unet.py:94-108 key names) into
+  * pre-packed fp16 weight matrices (eval BatchNorm folded, decoder taps pre-summed per output phase),
+  * static NHWC fp16 activation buffers in HBM,
+  * one `rsb_conv_plan` (TMA descriptors + tile schedule) per convolution,
+and replays them in order on the current CUDA stream. Python only sequences ~70 C-ABI calls; every
+arithmetic operation runs in the hand-written sm_100a kernels (no cuDNN / cuBLAS / torch ops on the path).
+
+Reference call sites covered: UNet.forward robosat/unet.py:110-141 (and the torchvision resnet50
+Bottleneck stack it calls), ConvRelu robosat/unet.py:44, DecoderBlock robosat/unet.py:73.
+"""
+
+import ctypes
+from collections import OrderedDict
+
+import torch
+
+from robosat_b200 import _lib
+from robosat_b200._lib import ConvDesc, ConvSeg, ConvSrc
+
+RESNET50_BLOCKS = (3, 4, 6, 3)
+BN_EPS = 1e-5
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+# --------------------------------------------------------------------------------------------------
+# weight packing (host, fp32 -> fp16). K index of a packed row = concatenation of the segments' 64-blocks.
+# --------------------------------------------------------------------------------------------------
+def _strip(sd):
+    if any(k.startswith("module.") for k in sd):
+        return {k[len("module."):]: v for k, v in sd.items()}
+    return dict(sd)
+
+
+def fold_bn(sd, conv_key, bn_prefix):
+    """Eval-mode BatchNorm folded into the preceding bias-free conv: w' = w*s, b' = beta - mean*s."""
+    w = sd[conv_key].float()
+    if bn_prefix is None:
+        return w, None
+    s = sd[bn_prefix + ".weight"].float() / torch.sqrt(sd[bn_prefix + ".running_var"].float() + BN_EPS)
+    b = sd[bn_prefix + ".bias"].float() - sd[bn_prefix + ".running_mean"].float() * s
+    return w * s.view(-1, 1, 1, 1), b
+
+
+def pack_conv(w):
+    """[Cout, Cin, kh, kw] -> [Cout, kh*kw*Cin] (tap-major, channel-minor)."""
+    co, ci, kh, kw = w.shape
+    return w.permute(0, 2, 3, 1).reshape(co, kh * kw * ci).contiguous()
+
+
+def pack_upsample_phases(w):
+    """3x3 conv applied after a nearest x2 upsample == four 2x2 convs on the low-res input.
+
+    Output pixel (2i+a, 2j+b) reads low-res rows {i-1+a, i+a}: row taps pre-summed as
+    a=0: [w0 | w1+w2], a=1: [w0+w1 | w2] (same for columns). Returns [4*Cout, 4*Cin], phase p=2a+b major.
+    """
+    co, ci, _, _ = w.shape
+    groups = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}
+    rows = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = []
+            for th in (0, 1):
+                for tw in (0, 1):
+                    acc = torch.zeros(co, ci, dtype=torch.float32)
+                    for kh in groups[a][th]:
+                        for kw in groups[b][tw]:
+                            acc += w[:, :, kh, kw]
+                    taps.append(acc)
+            rows.append(torch.stack(taps, dim=1).reshape(co, 4 * ci))
+    return torch.cat(rows, dim=0).contiguous()
+
+
+def pack_stem(w):
+    """7x7 stride-2 pad-3 conv on 3 channels -> 4 row-taps x (4 column-taps x 16 s2d channels) = K 256.
+
+    Input row 2*o + kh - 3 = 2*(o + t - 2) + ph with kh + 1 = 2*t + ph; the s2d channel is (ph*2+pw)*3 + c.
+    """
+    co = w.shape[0]
+    out = torch.zeros(co, 4, 4, 16, dtype=torch.float32)
+    for t in range(4):
+        for ph in range(2):
+            kh = 2 * t + ph - 1
+            if not 0 <= kh < 7:
+                continue
+            for u in range(4):
+                for pw in range(2):
+                    kw = 2 * u + pw - 1
+                    if not 0 <= kw < 7:
+                        continue
+                    out[:, t, u, (ph * 2 + pw) * 3:(ph * 2 + pw) * 3 + 3] = w[:, :, kh, kw]
+    return out.reshape(co, 256).contiguous()
+
+
+def pack_window3(w):
+    """3x3 conv on 32 channels read as 3 row-taps of a 4-pixel window (4th pixel weight zero): K = 3*128."""
+    co, ci, _, _ = w.shape
+    out = torch.zeros(co, 3, 4, ci, dtype=torch.float32)
+    out[:, :, :3, :] = w.permute(0, 2, 3, 1)
+    return out.reshape(co, 3 * 4 * ci).contiguous()
+
+
+def choose_tile(Wt, Ht, Nt):
+    """TW x TH x TN = 128 box with the least padded work; prefer single-image, wide tiles."""
+    best = None
+    for tw in (16, 8, 32, 4, 64, 2, 128, 1):
+        for th in (8, 16, 4, 32, 2, 64, 1, 128):
+            if 128 % (tw * th):
+                continue
+            tn = 128 // (tw * th)
+            if tn > 256 or tw > 256 or th > 256:
+                continue
+            tiles = -(-Wt // tw) * -(-Ht // th) * -(-Nt // tn)
+            key = (tiles, tn, abs(tw - 16) + abs(th - 8))
+            if best is None or key < best[0]:
+                best = (key, (tw, th, tn))
+    return best[1]
+
+
+def choose_block_n(cout, m_tiles, phases, sms=148):
+    """Largest N tile that still leaves about two waves of tiles for the persistent grid."""
+    cands = [bn for bn in (256, 128, 64, 32) if cout % bn == 0]
+    assert cands, "Cout must be a multiple of 32"
+    for bn in cands:
+        if m_tiles * phases * (cout // bn) >= 2 * sms:
+            return bn
+    return cands[-1] if cands[-1] >= 64 or len(cands) == 1 else cands[-2]
+
+
+# --------------------------------------------------------------------------------------------------
+class ConvOp:
+    """One convolution: the C descriptor, its plan handle and the tensors it must keep alive."""
+
+    def __init__(self, name, desc, keep, create_plan=True):
+        self.name = name
+        self.desc = desc
+        self.keep = keep
+        self.plan = ctypes.c_void_p()
+        if create_plan:
+            lib = _lib.load()
+            _lib.check(lib.rsb_conv_plan_create(ctypes.byref(desc), ctypes.byref(self.plan)), "rsb_conv_plan_create[%s]" % name)
+
+    def run(self, stream):
+        _lib.check(_lib.load().rsb_conv_run(self.plan, stream), "rsb_conv_run[%s]" % self.name)
+
+    def info(self):
+        g, t, k, s = (ctypes.c_int32() for _ in range(4))
+        _lib.check(_lib.load().rsb_conv_plan_info(self.plan, ctypes.byref(g), ctypes.byref(t), ctypes.byref(k), ctypes.byref(s)), "plan_info")
+        return {"grid": g.value, "tiles": t.value, "kblocks": k.value, "smem": s.value}
+
+    def __del__(self):
+        try:
+            if self.plan:
+                _lib.load().rsb_conv_plan_destroy(self.plan)
+                self.plan = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+def _src_dense(t, N, H, W, C):
+    return ConvSrc(t.data_ptr(), C, W * C, H * W * C, C, W, H, N)
+
+
+def _src_parity(t, N, H, W, C, ph, pw):
+    return ConvSrc(t.data_ptr() + 2 * (ph * W + pw) * C, 2 * C, 2 * W * C, H * W * C, C, W // 2, H // 2, N)
+
+
+def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out_pitches, out_scale=(1, 1),
+                   residual=None, relu=True, block_n=None, head=None, out_offset_elems=0):
+    """Fill an `rsb_conv_desc`. tile_space = (Wt, Ht, Nt); out_pitches = (pitch_w, pitch_h, pitch_n) in elements."""
+    d = ConvDesc()
+    d.nsrc = len(srcs)
+    for i, s in enumerate(srcs):
+        d.srcs[i] = s
+    d.nseg = len(segs)
+    for i, (src, dh, dw, cb) in enumerate(segs):
+        d.segs[i] = ConvSeg(src, dh, dw, cb)
+    K = 64 * sum(s[3] for s in segs)
+    assert weights.dtype == torch.float16 and weights.is_contiguous()
+    assert tuple(weights.shape) == (phases * cout, K), (tuple(weights.shape), phases, cout, K)
+    d.weights = weights.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.Cout = cout
+    d.phases = phases
+    Wt, Ht, Nt = tile_space
+    d.Wt, d.Ht, d.Nt = Wt, Ht, Nt
+    d.TW, d.TH, d.TN = choose_tile(Wt, Ht, Nt)
+    m_tiles = -(-Wt // d.TW) * -(-Ht // d.TH) * -(-Nt // d.TN)
+    d.block_n = block_n or choose_block_n(cout, m_tiles, phases)
+    d.out_sy, d.out_sx = out_scale
+    d.relu = 1 if relu else 0
+    if head is None:
+        d.mode = 0
+        d.out = out.data_ptr() + 2 * out_offset_elems
+        d.out_pitch_w, d.out_pitch_h, d.out_pitch_n = out_pitches
+        d.residual = residual.data_ptr() if residual is not None else None
+    else:
+        head_w, head_b, head_out, classes = head
+        d.mode = 1
+        d.head_classes = classes
+        d.head_w = head_w.data_ptr()
+        d.head_b = head_b.data_ptr()
+        d.head_out = head_out.data_ptr()
+    return d
+
+
+class UNetEngine:
+    """Static-shape inference plan for `UNet(num_classes)` on one GPU."""
+
+    def __init__(self, state_dict, num_classes, batch, height, width, device="cuda", plan_only=False):
+        """plan_only=True builds buffers and descriptors on `device` without touching the GPU library
+        (used by the CPU tests, which execute the descriptors with tests/emulate.py)."""
+        assert height % 32 == 0 and width % 32 == 0, "image resolution has to be divisible by 32 for resnet"
+        self.plan_only = plan_only
+        if not plan_only:
+            _lib.require_device()
+        self.device = torch.device(device)
+        self.N, self.H, self.W, self.C = batch, height, width, num_classes
+        self.ops = []  # ("conv", ConvOp) | ("prepass",) | ("maxpool", src, dst, N, H, W, C, k, s, p)
+        self.feats = OrderedDict()  # name -> (tensor, (N, H, W, C) logical view) for layer-wise checks
+        self._keep = []
+        self._build(_strip(state_dict))
+
+    # ---------------------------------------------------------------- helpers
+    def _buf(self, *shape, dtype=torch.float16):
+        t = torch.zeros(shape, dtype=dtype, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def _dev(self, t, dtype):
+        t = t.to(dtype).contiguous().to(self.device)
+        self._keep.append(t)
+        return t
+
+    def _add_conv(self, name, desc, keep=()):
+        op = ConvOp(name, desc, keep, create_plan=not self.plan_only)
+        self.ops.append(("conv", op))
+        return op
+
+    # ---------------------------------------------------------------- graph
+    def _build(self, sd):
+        N, H, W = self.N, self.H, self.W
+        H2, W2 = H // 2, W // 2
+        dev = self._dev
+
+        # input pre-pass: fp32 NCHW (or u8 NHWC) -> space-to-depth fp16 [N, H2, W2+4, 16]
+        self.s2d = self._buf(N, H2, W2 + 4, 16)
+        self.ops.append(("prepass",))
+
+        # stem: conv1 7x7/2 + bn1 + relu (unet.py:122-124) on tensor cores via the overlapped window view
+        w, b = fold_bn(sd, "resnet.conv1.weight", "resnet.bn1")
+        wp, bp = dev(pack_stem(w), torch.float16), dev(b, torch.float32)
+        stem = self._buf(N, H2, W2, 64)
+        Wp = W2 + 4
+        src = ConvSrc(self.s2d.data_ptr(), 16, Wp * 16, H2 * Wp * 16, 64, W2, H2, N)
+        segs = [(0, t - 2, 0, 1) for t in range(4)]
+        self._add_conv("stem", make_conv_desc([src], segs, wp, bp, 64, 1, (W2, H2, N), stem, (64, W2 * 64, H2 * W2 * 64)))
+        self.feats["stem"] = (stem, (N, H2, W2, 64))
+
+        # maxpool 3x3/2 pad 1 (unet.py:125)
+        H4, W4 = H // 4, W // 4
+        enc0 = self._buf(N, H4, W4, 64)
+        self.ops.append(("maxpool", stem, enc0, N, H2, W2, 64, 3, 2, 1))
+        self.feats["enc0"] = (enc0, (N, H4, W4, 64))
+
+        # resnet layer1..4 (unet.py:127-130)
+        cur, curC, curH, curW = enc0, 64, H4, W4
+        encs = []
+        for li, blocks in enumerate(RESNET50_BLOCKS, start=1):
+            planes = 64 * 2 ** (li - 1)
+            for bi in range(blocks):
+                p = "resnet.layer%d.%d" % (li, bi)
+                stride = 2 if (bi == 0 and li > 1) else 1
+                oH, oW = curH // stride, curW // stride
+                # conv1 1x1 + bn1 + relu
+                w, b = fold_bn(sd, p + ".conv1.weight", p + ".bn1")
+                t1 = self._buf(N, curH, curW, planes)
+                self._add_conv(p + ".conv1", make_conv_desc(
+                    [_src_dense(cur, N, curH, curW, curC)], [(0, 0, 0, curC // 64)], dev(pack_conv(w), torch.float16),
+                    dev(b, torch.float32), planes, 1, (curW, curH, N), t1, (planes, curW * planes, curH * curW * planes)))
+                # conv2 3x3 (stride) + bn2 + relu
+                w, b = fold_bn(sd, p + ".conv2.weight", p + ".bn2")
+                t2 = self._buf(N, oH, oW, planes)
+                if stride == 1:
+                    srcs = [_src_dense(t1, N, curH, curW, planes)]
+                    segs = [(0, kh - 1, kw - 1, planes // 64) for kh in range(3) for kw in range(3)]
+                else:
+                    srcs = [_src_parity(t1, N, curH, curW, planes, ph, pw) for ph in range(2) for pw in range(2)]
+                    segs = []
+                    for kh in range(3):
+                        for kw in range(3):
+                            ph, dh = (kh - 1) % 2, (kh - 1) // 2
+                            pw, dw = (kw - 1) % 2, (kw - 1) // 2
+                            segs.append((ph * 2 + pw, dh, dw, planes // 64))
+                self._add_conv(p + ".conv2", make_conv_desc(
+                    srcs, segs, dev(pack_conv(w), torch.float16), dev(b, torch.float32), planes, 1, (oW, oH, N), t2,
+                    (planes, oW * planes, oH * oW * planes)))
+                # identity / downsample 1x1 (stride) + bn
+                outC = planes * 4
+                if (p + ".downsample.0.weight") in sd:
+                    w, b = fold_bn(sd, p + ".downsample.0.weight", p + ".downsample.1")
+                    idt = self._buf(N, oH, oW, outC)
+                    s = _src_dense(cur, N, curH, curW, curC) if stride == 1 else _src_parity(cur, N, curH, curW, curC, 0, 0)
+                    self._add_conv(p + ".downsample", make_conv_desc(
+                        [s], [(0, 0, 0, curC // 64)], dev(pack_conv(w), torch.float16), dev(b, torch.float32), outC, 1,
+                        (oW, oH, N), idt, (outC, oW * outC, oH * oW * outC), relu=False))
+                else:
+                    idt = cur
+                # conv3 1x1 + bn3 + identity + relu
+                w, b = fold_bn(sd, p + ".conv3.weight", p + ".bn3")
+                out = self._buf(N, oH, oW, outC)
+                self._add_conv(p + ".conv3", make_conv_desc(
+                    [_src_dense(t2, N, oH, oW, planes)], [(0, 0, 0, planes // 64)], dev(pack_conv(w), torch.float16),
+                    dev(b, torch.float32), outC, 1, (oW, oH, N), out, (outC, oW * outC, oH * oW * outC), residual=idt))
+                self.feats[p] = (out, (N, oH, oW, outC))
+                cur, curC, curH, curW = out, outC, oH, oW
+            encs.append((cur, curC, curH, curW))
+            self.feats["enc%d" % li] = (cur, (N, curH, curW, curC))
+        (enc1, c1, h1, w1), (enc2, c2, h2, w2), (enc3, c3, h3, w3), (enc4, c4, h4, w4) = encs
+
+        # max_pool2d(enc4, 2, 2) (unet.py:132)
+        hp, wpx = h4 // 2, w4 // 2
+        pool4 = self._buf(N, hp, wpx, c4)
+        self.ops.append(("maxpool", enc4, pool4, N, h4, w4, c4, 2, 2, 0))
+        self.feats["pool4"] = (pool4, (N, hp, wpx, c4))
+
+        def decoder(name, sources, lh, lw, cout, out, out_pitches, out_offset=0):
+            # DecoderBlock: nearest x2 + 3x3 conv + relu (unet.py:73, :44) as 4 phases of 2x2 taps on the low-res inputs
+            w = sd[name + ".block.block.weight"].float()
+            srcs = [_src_dense(t, N, lh, lw, c) for t, c in sources]
+            segs = [(si, th - 1, tw - 1, c // 64) for th in range(2) for tw in range(2) for si, (_, c) in enumerate(sources)]
+            self._add_conv(name, make_conv_desc(
+                srcs, segs, dev(pack_upsample_phases(w), torch.float16), None, cout, 4, (lw, lh, N), out, out_pitches,
+                out_scale=(2, 2), out_offset_elems=out_offset))
+
+        def dense_pitches(h, w, c):
+            return (c, w * c, h * w * c)
+
+        center = self._buf(N, h4, w4, 256)
+        decoder("center", [(pool4, c4)], hp, wpx, 256, center, dense_pitches(h4, w4, 256))
+        self.feats["center"] = (center, (N, h4, w4, 256))
+        dec0 = self._buf(N, h3, w3, 256)
+        decoder("dec0", [(enc4, c4), (center, 256)], h4, w4, 256, dec0, dense_pitches(h3, w3, 256))
+        self.feats["dec0"] = (dec0, (N, h3, w3, 256))
+        dec1 = self._buf(N, h2, w2, 256)
+        decoder("dec1", [(enc3, c3), (dec0, 256)], h3, w3, 256, dec1, dense_pitches(h2, w2, 256))
+        self.feats["dec1"] = (dec1, (N, h2, w2, 256))
+        dec2 = self._buf(N, h1, w1, 64)
+        decoder("dec2", [(enc2, c2), (dec1, 256)], h2, w2, 64, dec2, dense_pitches(h1, w1, 64))
+        self.feats["dec2"] = (dec2, (N, h1, w1, 64))
+        dec3 = self._buf(N, H2, W2, 128)
+        decoder("dec3", [(enc1, c1), (dec2, 64)], h1, w1, 128, dec3, dense_pitches(H2, W2, 128))
+        self.feats["dec3"] = (dec3, (N, H2, W2, 128))
+
+        # dec4 writes into a W-padded buffer [N, H, W+4, 32] (pixel w at column w+1) so dec5 can read 4-pixel windows
+        Wq = W + 4
+        self.dec4 = self._buf(N, H, Wq, 32)
+        decoder("dec4", [(dec3, 128)], H2, W2, 32, self.dec4, (32, Wq * 32, H * Wq * 32), out_offset=32)
+        self.feats["dec4"] = (self.dec4, (N, H, Wq, 32))
+
+        # dec5 (3x3 32->32 + relu, unet.py:139) fused with final (1x1 32->C + bias, unet.py:141) -> fp32 NCHW logits
+        w5 = sd["dec5.block.weight"].float()
+        self.logits = self._buf(N, self.C, H, W, dtype=torch.float32)
+        head_w = dev(sd["final.weight"].float().reshape(self.C, 32), torch.float32)
+        head_b = dev(sd["final.bias"].float(), torch.float32)
+        src = ConvSrc(self.dec4.data_ptr(), 32, Wq * 32, H * Wq * 32, 128, W, H, N)
+        segs = [(0, kh - 1, 0, 2) for kh in range(3)]
+        self._add_conv("dec5+final", make_conv_desc(
+            [src], segs, dev(pack_window3(w5), torch.float16), None, 32, 1, (W, H, N), None, None,
+            head=(head_w, head_b, self.logits, self.C)))
+
+        self._mean = (ctypes.c_float * 3)(*IMAGENET_MEAN)
+        self._std = (ctypes.c_float * 3)(*IMAGENET_STD)
+
+    # ---------------------------------------------------------------- execution
+    def conv_ops(self):
+        return [op[1] for op in self.ops if op[0] == "conv"]
+
+    def num_launches(self):
+        return len(self.ops)
+
+    def forward(self, x):
+        """x: fp32 NCHW normalised (reference API) or uint8 NHWC raw RGB, on this engine's device.
+        Returns the engine-owned fp32 NCHW logits buffer (valid until the next call)."""
+        if self.plan_only:
+            raise _lib.RsbError("UNetEngine was built with plan_only=True; there is no CPU execution path")
+        lib = _lib.load()
+        N, H, W = self.N, self.H, self.W
+        if x.dtype == torch.float32:
+            assert tuple(x.shape) == (N, 3, H, W) and x.is_contiguous() and x.is_cuda, "expected contiguous cuda fp32 [N,3,H,W]"
+            kind = 0
+        elif x.dtype == torch.uint8:
+            assert tuple(x.shape) == (N, H, W, 3) and x.is_contiguous() and x.is_cuda, "expected contiguous cuda uint8 [N,H,W,3]"
+            kind = 1
+        else:
+            raise TypeError("unsupported input dtype %s" % x.dtype)
+        stream = _lib.current_stream_ptr()
+        for op in self.ops:
+            if op[0] == "conv":
+                op[1].run(stream)
+            elif op[0] == "prepass":
+                _lib.check(lib.rsb_prepass_s2d(x.data_ptr(), kind, self.s2d.data_ptr(), N, H, W, self._mean, self._std, stream), "rsb_prepass_s2d")
+            else:
+                _, src, dst, n, h, w, c, k, s, p = op
+                _lib.check(lib.rsb_maxpool_nhwc(src.data_ptr(), dst.data_ptr(), n, h, w, c, k, s, p, stream), "rsb_maxpool_nhwc")
+        return self.logits
+
+    def feature_nchw(self, name):
+        """Debug/parity view of an intermediate as fp32 NCHW on the CPU."""
+        t, (n, h, w, c) = self.feats[name]
+        t = t.detach().float().cpu().reshape(n, h, w, c)
+        if name == "dec4":
+            t = t[:, :, 1:w - 3, :]
+        return t.permute(0, 3, 1, 2).contiguous()

@@ -1,0 +1,172 @@
+"""Builders for single-convolution parity cases shared by the GPU tests and scripts/gpu_diag.py.
+
+Each case builds an `rsb_conv_desc` exactly the way `robosat_b200.engine.UNetEngine` does for that layer
+kind, plus a CPU fp32 reference of the same operation (torch functional ops on the fp16-rounded operands,
+i.e. the reference's own call sites: F.conv2d / F.interpolate / torch.cat, robosat/unet.py:44,73,134-141).
+"""
+
+import torch
+import torch.nn.functional as F
+
+from robosat_b200 import engine as E
+from robosat_b200._lib import ConvSrc
+
+
+def _rand(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen) * scale)
+
+
+def _nhwc_half(x_nchw, device):
+    return x_nchw.permute(0, 2, 3, 1).contiguous().half().to(device)
+
+
+def _out_nchw(t, shape_nhwc):
+    return t.float().cpu().reshape(shape_nhwc).permute(0, 3, 1, 2).contiguous()
+
+
+class Case:
+    def __init__(self, name, desc, keep, out, out_view, ref):
+        self.name, self.desc, self.keep, self.out, self.out_view, self.ref = name, desc, keep, out, out_view, ref
+
+    def result(self):
+        """device output as fp32 NCHW on the CPU"""
+        return self.out_view(self.out)
+
+
+def conv_case(kind, N, H, W, cin, cout, device, seed=0, residual=False, relu=True, bias=True, block_n=None):
+    """kind: '1x1' | '3x3' | '3x3s2' | '1x1s2'"""
+    g = torch.Generator().manual_seed(seed)
+    k = 3 if kind.startswith("3x3") else 1
+    stride = 2 if kind.endswith("s2") else 1
+    x = _rand((N, cin, H, W), g).half().float()
+    w = _rand((cout, cin, k, k), g, (2.0 / (cin * k * k)) ** 0.5)
+    b = _rand((cout,), g, 0.1) if bias else None
+    oH, oW = H // stride, W // stride
+    xd = _nhwc_half(x, device)
+    wp = E.pack_conv(w).half().to(device)
+    bd = b.float().to(device) if bias else None
+    out = torch.zeros(N, oH, oW, cout, dtype=torch.float16, device=device)
+    res = _rand((N, cout, oH, oW), g).half().float() if residual else None
+    resd = _nhwc_half(res, device) if residual else None
+    if stride == 1:
+        srcs = [E._src_dense(xd, N, H, W, cin)]
+        segs = [(0, kh - k // 2, kw - k // 2, cin // 64) for kh in range(k) for kw in range(k)]
+    else:
+        srcs = [E._src_parity(xd, N, H, W, cin, ph, pw) for ph in range(2) for pw in range(2)]
+        segs = []
+        for kh in range(k):
+            for kw in range(k):
+                ph, dh = (kh - k // 2) % 2, (kh - k // 2) // 2
+                pw, dw = (kw - k // 2) % 2, (kw - k // 2) // 2
+                segs.append((ph * 2 + pw, dh, dw, cin // 64))
+        if k == 1:
+            srcs = srcs[:1]
+    desc = E.make_conv_desc(srcs, segs, wp, bd, cout, 1, (oW, oH, N), out, (cout, oW * cout, oH * oW * cout),
+                            residual=resd, relu=relu, block_n=block_n)
+
+    def ref():
+        y = F.conv2d(x, w.half().float(), b, stride=stride, padding=k // 2)
+        if residual:
+            y = y + res
+        return F.relu(y) if relu else y
+
+    return Case("%s_%dx%dx%d_%d-%d" % (kind, N, H, W, cin, cout), desc, (xd, wp, bd, resd), out,
+                lambda t: _out_nchw(t, (N, oH, oW, cout)), ref)
+
+
+def decoder_case(N, lh, lw, cins, cout, device, seed=0, block_n=None):
+    """DecoderBlock on cat(sources): nearest x2 -> 3x3 conv -> relu, as 4 phases on the low-res inputs."""
+    g = torch.Generator().manual_seed(seed)
+    xs = [_rand((N, c, lh, lw), g).half().float() for c in cins]
+    ctot = sum(cins)
+    w = _rand((cout, ctot, 3, 3), g, (2.0 / (ctot * 9)) ** 0.5)
+    xds = [_nhwc_half(x, device) for x in xs]
+    wp = E.pack_upsample_phases(w).half().to(device)
+    oH, oW = 2 * lh, 2 * lw
+    out = torch.zeros(N, oH, oW, cout, dtype=torch.float16, device=device)
+    srcs = [E._src_dense(t, N, lh, lw, c) for t, c in zip(xds, cins)]
+    segs = [(si, th - 1, tw - 1, c // 64) for th in range(2) for tw in range(2) for si, c in enumerate(cins)]
+    desc = E.make_conv_desc(srcs, segs, wp, None, cout, 4, (lw, lh, N), out, (cout, oW * cout, oH * oW * cout),
+                            out_scale=(2, 2), block_n=block_n)
+
+    def ref():
+        up = F.interpolate(torch.cat(xs, dim=1), scale_factor=2, mode="nearest")
+        return F.relu(F.conv2d(up, w, None, padding=1))
+
+    return Case("decoder_%dx%dx%d_%s-%d" % (N, lh, lw, "+".join(map(str, cins)), cout), desc, (xds, wp), out,
+                lambda t: _out_nchw(t, (N, oH, oW, cout)), ref)
+
+
+def stem_case(N, H, W, device, seed=0):
+    """resnet conv1 7x7/2 pad 3 + folded bn + relu through the pre-pass and the overlapped-window view."""
+    from robosat_b200 import _lib
+    import ctypes
+
+    g = torch.Generator().manual_seed(seed)
+    x = _rand((N, 3, H, W), g)
+    w = _rand((64, 3, 7, 7), g, (2.0 / 147) ** 0.5)
+    b = _rand((64,), g, 0.1)
+    H2, W2, Wp = H // 2, W // 2, W // 2 + 4
+    xd = x.contiguous().to(device)
+    if torch.device(device).type == "cpu":
+        import emulate
+
+        s2d = emulate.prepass_s2d_cpu(x)
+    else:
+        s2d = torch.zeros(N, H2, Wp, 16, dtype=torch.float16, device=device)
+        lib = _lib.load()
+        _lib.check(lib.rsb_prepass_s2d(xd.data_ptr(), 0, s2d.data_ptr(), N, H, W, None, None, _lib.current_stream_ptr()), "prepass")
+    wp = E.pack_stem(w).half().to(device)
+    bd = b.to(device)
+    out = torch.zeros(N, H2, W2, 64, dtype=torch.float16, device=device)
+    src = ConvSrc(s2d.data_ptr(), 16, Wp * 16, H2 * Wp * 16, 64, W2, H2, N)
+    segs = [(0, t - 2, 0, 1) for t in range(4)]
+    desc = E.make_conv_desc([src], segs, wp, bd, 64, 1, (W2, H2, N), out, (64, W2 * 64, H2 * W2 * 64))
+
+    def ref():
+        return F.relu(F.conv2d(x.half().float(), w.half().float(), b, stride=2, padding=3))
+
+    return Case("stem_%dx%dx%d" % (N, H, W), desc, (xd, s2d, wp, bd), out, lambda t: _out_nchw(t, (N, H2, W2, 64)), ref)
+
+
+def head_case(N, H, W, classes, device, seed=0):
+    """dec5 (3x3 32->32 + relu) fused with final (1x1 32->classes + bias) reading the W-padded dec4 buffer."""
+    g = torch.Generator().manual_seed(seed)
+    x = _rand((N, 32, H, W), g).half().float()
+    w5 = _rand((32, 32, 3, 3), g, (2.0 / 288) ** 0.5)
+    wf = _rand((classes, 32, 1, 1), g, 0.3)
+    bf = _rand((classes,), g, 0.1)
+    Wq = W + 4
+    buf = torch.zeros(N, H, Wq, 32, dtype=torch.float16, device=device)
+    buf[:, :, 1:W + 1, :] = _nhwc_half(x, device)
+    wp = E.pack_window3(w5).half().to(device)
+    hw = wf.reshape(classes, 32).contiguous().to(device)
+    hb = bf.to(device)
+    logits = torch.zeros(N, classes, H, W, dtype=torch.float32, device=device)
+    src = ConvSrc(buf.data_ptr(), 32, Wq * 32, H * Wq * 32, 128, W, H, N)
+    segs = [(0, kh - 1, 0, 2) for kh in range(3)]
+    desc = E.make_conv_desc([src], segs, wp, None, 32, 1, (W, H, N), None, None, head=(hw, hb, logits, classes))
+
+    def ref():
+        return F.conv2d(F.relu(F.conv2d(x, w5.half().float(), None, padding=1)), wf, bf)
+
+    return Case("head_%dx%dx%d_c%d" % (N, H, W, classes), desc, (buf, wp, hw, hb), logits, lambda t: t.float().cpu(), ref)
+
+
+def default_cases(device):
+    """One case per layer kind the U-Net uses, small enough for the CPU reference to take milliseconds."""
+    return [
+        lambda: conv_case("1x1", 2, 16, 16, 64, 64, device, seed=1),
+        lambda: conv_case("1x1", 1, 16, 32, 256, 128, device, seed=2, residual=True, block_n=128),
+        lambda: conv_case("3x3", 2, 16, 16, 64, 64, device, seed=3),
+        lambda: conv_case("3x3", 1, 24, 40, 128, 256, device, seed=4, block_n=256),
+        lambda: conv_case("3x3s2", 2, 32, 32, 128, 128, device, seed=5),
+        lambda: conv_case("1x1s2", 2, 32, 32, 256, 512, device, seed=6, relu=False),
+        lambda: conv_case("1x1", 3, 8, 8, 512, 2048, device, seed=7, residual=True, block_n=256),
+        lambda: decoder_case(2, 8, 8, [128, 64], 64, device, seed=8),
+        lambda: decoder_case(1, 16, 16, [128], 32, device, seed=9),
+        lambda: decoder_case(3, 4, 4, [256, 256], 256, device, seed=10, block_n=128),
+        lambda: stem_case(2, 64, 64, device, seed=11),
+        lambda: head_case(2, 32, 32, 2, device, seed=12),
+        lambda: head_case(1, 32, 64, 6, device, seed=13),
+    ]
