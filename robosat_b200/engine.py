@@ -213,6 +213,8 @@ class UNetEngine:
         """plan_only=True builds buffers and descriptors on `device` without touching the GPU library
         (used by the CPU tests, which execute the descriptors with tests/emulate.py)."""
         assert height % 32 == 0 and width % 32 == 0, "image resolution has to be divisible by 32 for resnet"
+        # the reference's torch.cat([enc4, center]) (unet.py:134) only works when enc4's extent is even
+        assert height % 64 == 0 and width % 64 == 0, "enc4 must have even extents (input divisible by 64), as in the reference"
         self.plan_only = plan_only
         if not plan_only:
             _lib.require_device()

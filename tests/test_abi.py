@@ -1,0 +1,55 @@
+"""The C-ABI library must load without a GPU and export exactly what include/rsb200.h declares."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+from robosat_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    text = open(os.path.join(ROOT, "include", "rsb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rsb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _header_functions()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), "librsb200.so does not export %s" % n
+    # and the ctypes table binds the same set
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_struct_layout_matches_header():
+    # sizes follow from the C declarations (8-byte aligned, no packing pragmas)
+    assert ctypes.sizeof(_lib.ConvSrc) == 48
+    assert ctypes.sizeof(_lib.ConvSeg) == 16
+    assert _lib.ConvDesc.srcs.offset == 8 and _lib.ConvDesc.segs.offset == 8 + 4 * 48 + 4
+    assert ctypes.sizeof(_lib.ConvDesc) % 8 == 0
+
+
+def test_version_and_error_string_without_gpu():
+    lib = _lib.load()
+    assert lib.rsb_version() >= 100
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.RsbError):
+        _lib.require_device()
+    from robosat_b200 import synth
+    from robosat_b200.engine import UNetEngine
+
+    with pytest.raises(_lib.RsbError):
+        UNetEngine(synth.make_state_dict(2), 2, 1, 64, 64, device="cpu")

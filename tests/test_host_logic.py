@@ -1,0 +1,67 @@
+"""Host-side logic without a GPU: weight packing, parity / phase / window views and the whole engine graph,
+executed by the CPU emulator of the kernel's addressing (tests/emulate.py) and compared with the oracle."""
+
+import numpy as np
+import pytest
+import torch
+
+import conv_cases
+import emulate
+from oracle import unet_oracle
+from robosat_b200 import synth
+from robosat_b200.engine import UNetEngine, choose_block_n, choose_tile, pack_upsample_phases
+
+
+@pytest.mark.parametrize("i", range(len(conv_cases.default_cases("cpu"))))
+def test_single_conv_descriptor_semantics(i):
+    case = conv_cases.default_cases("cpu")[i]()
+    emulate.run_desc(case.desc)
+    got, ref = case.result(), case.ref()
+    err = (got - ref).abs().max().item()
+    # fp16 output rounding (half an ulp at |x| < 16 is 4e-3) + fp16 rounding of pre-summed phase weights
+    assert err <= 6e-3 * max(1.0, ref.abs().max().item() / 8), (case.name, err)
+
+
+def test_upsample_phase_decomposition_is_exact_in_fp64():
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(8, 5, 3, 3, generator=g, dtype=torch.float64)
+    x = torch.randn(2, 5, 6, 7, generator=g, dtype=torch.float64)
+    ref = torch.nn.functional.conv2d(torch.nn.functional.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    wp = pack_upsample_phases(w.float()).double().reshape(4, 8, 2, 2, 5)  # float32 sums: compare loosely
+    out = torch.zeros_like(ref)
+    xp = torch.nn.functional.pad(x, (1, 1, 1, 1))
+    for a in range(2):
+        for b in range(2):
+            acc = 0
+            for th in range(2):
+                for tw in range(2):
+                    patch = xp[:, :, a + th:a + th + 6, b + tw:b + tw + 7]
+                    acc = acc + torch.einsum("nchw,oc->nohw", patch, wp[2 * a + b, :, th, tw, :])
+            out[:, :, a::2, b::2] = acc
+    assert (out - ref).abs().max().item() < 1e-5
+
+
+def test_tile_and_block_choice():
+    for dims in [(256, 256, 32), (16, 16, 32), (8, 8, 32), (4, 4, 2), (72, 72, 1), (9, 9, 2), (5, 5, 3)]:
+        tw, th, tn = choose_tile(*dims)
+        assert tw * th * tn == 128
+    assert choose_block_n(2048, 64, 1) == 256
+    assert choose_block_n(32, 10, 1) == 32
+    assert choose_block_n(64, 100000, 1) == 64
+
+
+@pytest.mark.parametrize("size,batch,classes", [(64, 2, 2), (128, 1, 6)])
+def test_engine_graph_matches_oracle(size, batch, classes):
+    sd = synth.make_state_dict(classes, seed=0)
+    x = synth.normalize_tiles(synth.make_tiles_u8(batch, size, seed=1))
+    eng = UNetEngine(sd, classes, batch, size, size, device="cpu", plan_only=True)
+    got = emulate.run_engine(eng, x)
+    with torch.no_grad():
+        ref, feats = unet_oracle.unet_forward(sd, x, return_features=True)
+    rel_l2 = ((got - ref).pow(2).sum().sqrt() / ref.pow(2).sum().sqrt()).item()
+    assert rel_l2 < 5e-3, rel_l2
+    for name in ("stem", "enc0", "enc1", "enc2", "enc3", "enc4", "center", "dec0", "dec1", "dec2", "dec3", "dec4"):
+        a, b = eng.feature_nchw(name), feats[name]
+        r = ((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt()).item()
+        assert r < 3e-3, (name, r)
+    assert len(eng.ops) == 63  # 1 pre-pass + 2 max pools + 60 convolution launches (dec5 + final fused)
