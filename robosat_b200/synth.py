@@ -138,7 +138,7 @@ def normalize_tiles(tiles_u8):
     x = tiles_u8.permute(0, 3, 1, 2).to(torch.float32).div(255)
     mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32).view(1, 3, 1, 1)
     std = torch.tensor(IMAGENET_STD, dtype=torch.float32).view(1, 3, 1, 1)
-    return x.sub(mean).div(std)
+    return x.sub(mean).div(std).contiguous()
 
 
 def make_masks(n, size, num_classes=2, seed=3):

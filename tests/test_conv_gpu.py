@@ -1,0 +1,85 @@
+"""GPU parity of the tcgen05/TMA convolution kernel, one case per layer kind, through the C ABI.
+
+Checker: CPU fp32 torch ops on the same fp16-rounded operands (the reference's own call sites), and the
+SIMT global-memory checker kernel for bisecting. Tolerance: the kernel accumulates in fp32 and rounds the
+output to fp16 once, so |err| <= 1 fp16 ulp of the output magnitude (+ fp16 rounding of pre-summed weights).
+"""
+
+import ctypes
+
+import pytest
+import torch
+
+import conv_cases
+from robosat_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("i", range(len(conv_cases.default_cases(None))))
+def test_conv_case_matches_cpu_reference(i, cuda_device):
+    lib = _lib.load()
+    case = conv_cases.default_cases(cuda_device)[i]()
+    ref = case.ref()
+    stream = _lib.current_stream_ptr()
+    plan = ctypes.c_void_p()
+    _lib.check(lib.rsb_conv_plan_create(ctypes.byref(case.desc), ctypes.byref(plan)), "plan_create")
+    try:
+        for _ in range(3):  # re-running the same plan must give the same answer (pipeline state resets)
+            case.out.zero_()
+            _lib.check(lib.rsb_conv_run(plan, stream), "conv_run")
+            torch.cuda.synchronize()
+            got = case.result()
+            tol = 6e-3 * max(1.0, ref.abs().max().item() / 8)
+            assert (got - ref).abs().max().item() <= tol, case.name
+        # bisecting aid: the SIMT checker agrees with the tensor-core path to within output rounding
+        tc = case.result()
+        case.out.zero_()
+        _lib.check(lib.rsb_conv_run_simt_check(ctypes.byref(case.desc), stream), "simt")
+        torch.cuda.synchronize()
+        assert (case.result() - tc).abs().max().item() <= tol
+    finally:
+        lib.rsb_conv_plan_destroy(plan)
+
+
+@pytest.mark.parametrize("block_n", [64, 128, 256])
+def test_conv_multi_wave_persistent_schedule(block_n, cuda_device):
+    """More tiles than SMs: every CTA loops over several tiles and both TMEM accumulator stages are reused."""
+    lib = _lib.load()
+    case = conv_cases.conv_case("3x3", 8, 64, 64, 64, 256, cuda_device, seed=21, block_n=block_n)
+    plan = ctypes.c_void_p()
+    _lib.check(lib.rsb_conv_plan_create(ctypes.byref(case.desc), ctypes.byref(plan)), "plan_create")
+    _lib.check(lib.rsb_conv_run(plan, _lib.current_stream_ptr()), "conv_run")
+    torch.cuda.synchronize()
+    ref = case.ref()
+    assert (case.result() - ref).abs().max().item() <= 6e-3 * max(1.0, ref.abs().max().item() / 8)
+    lib.rsb_conv_plan_destroy(plan)
+
+
+def test_prepass_u8_matches_reference_transform(cuda_device):
+    """uint8 NHWC -> normalised fp16 s2d == ToTensor + Normalize (predict.py:71-73) then fp16 rounding."""
+    import emulate
+    from robosat_b200 import synth
+
+    lib = _lib.load()
+    u8 = synth.make_tiles_u8(2, 64, seed=5)
+    ref = emulate.prepass_s2d_cpu(synth.normalize_tiles(u8))
+    dst = torch.zeros(2, 32, 36, 16, dtype=torch.float16, device=cuda_device)
+    mean = (ctypes.c_float * 3)(*synth.IMAGENET_MEAN)
+    std = (ctypes.c_float * 3)(*synth.IMAGENET_STD)
+    _lib.check(lib.rsb_prepass_s2d(u8.to(cuda_device).data_ptr(), 1, dst.data_ptr(), 2, 64, 64, mean, std, _lib.current_stream_ptr()), "prepass")
+    torch.cuda.synchronize()
+    assert torch.equal(dst.cpu(), ref)
+
+
+def test_maxpool_matches_torch(cuda_device):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(3)
+    for (N, H, W, C, k, s, p) in [(2, 32, 32, 64, 3, 2, 1), (3, 8, 8, 2048, 2, 2, 0)]:
+        x = torch.randn((N, C, H, W), generator=g).half()
+        ref = torch.nn.functional.max_pool2d(x.float(), k, s, p).half()
+        src = x.permute(0, 2, 3, 1).contiguous().to(cuda_device)
+        dst = torch.zeros(N, ref.shape[2], ref.shape[3], C, dtype=torch.float16, device=cuda_device)
+        _lib.check(lib.rsb_maxpool_nhwc(src.data_ptr(), dst.data_ptr(), N, H, W, C, k, s, p, _lib.current_stream_ptr()), "maxpool")
+        torch.cuda.synchronize()
+        assert torch.equal(dst.cpu().permute(0, 3, 1, 2), ref)
