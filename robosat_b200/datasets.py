@@ -1,0 +1,87 @@
+"""PyTorch datasets over slippy-map directories; API identical to robosat/datasets.py:16-136.
+
+    SlippyMapTiles(root, transform)[i]                         -> (image, Tile), sorted by tile
+    SlippyMapTilesConcatenation(inputs, target, joint)[i]      -> (cat(images), mask, [Tile])
+    BufferedSlippyMapDirectory(root, transform, size, overlap)[i] -> (image, IntTensor[x, y, z]); .unbuffer(probs)
+"""
+
+import torch
+import torch.utils.data
+from PIL import Image
+
+from robosat_b200.tiles import buffer_tile_image, tiles_from_slippy_map
+
+
+class SlippyMapTiles(torch.utils.data.Dataset):
+    """One slippy-map directory of images."""
+
+    def __init__(self, root, transform=None):
+        super().__init__()
+        self.transform = transform
+        self.tiles = sorted(tiles_from_slippy_map(root), key=lambda pair: pair[0])
+
+    def __len__(self):
+        return len(self.tiles)
+
+    def __getitem__(self, i):
+        tile, path = self.tiles[i]
+        image = Image.open(path)
+        if self.transform is not None:
+            image = self.transform(image)
+        return image, tile
+
+
+class SlippyMapTilesConcatenation(torch.utils.data.Dataset):
+    """Several image directories plus one label directory, transformed jointly and concatenated on channels."""
+
+    def __init__(self, inputs, target, joint_transform=None):
+        super().__init__()
+        self.joint_transform = joint_transform
+        self.inputs = [SlippyMapTiles(path) for path in inputs]
+        self.target = SlippyMapTiles(target)
+        assert len({len(ds) for ds in self.inputs}) == 1, "same number of tiles in all images"
+        assert len(self.target) == len(self.inputs[0]), "same number of tiles in images and label"
+
+    def __len__(self):
+        return len(self.target)
+
+    def __getitem__(self, i):
+        pairs = [ds[i] for ds in self.inputs]
+        images = [image for image, _ in pairs]
+        tiles = [tile for _, tile in pairs]
+        mask, mask_tile = self.target[i]
+        assert len(set(tiles)) == 1, "all images are for the same tile"
+        assert tiles[0] == mask_tile, "image tile is the same as label tile"
+        if self.joint_transform is not None:
+            images, mask = self.joint_transform(images, mask)
+        return torch.cat(images, dim=0), mask, tiles
+
+
+class BufferedSlippyMapDirectory(torch.utils.data.Dataset):
+    """Tiles with an `overlap` border taken from their neighbours; `unbuffer` crops predictions back."""
+
+    def __init__(self, root, transform=None, size=512, overlap=32):
+        super().__init__()
+        assert overlap >= 0
+        assert size >= 256
+        self.transform = transform
+        self.size = size
+        self.overlap = overlap
+        self.tiles = list(tiles_from_slippy_map(root))
+        self._index = dict(self.tiles)  # built once: O(1) neighbour lookups (the reference rebuilds it per item)
+
+    def __len__(self):
+        return len(self.tiles)
+
+    def __getitem__(self, i):
+        tile, _ = self.tiles[i]
+        image = buffer_tile_image(tile, self._index, overlap=self.overlap, tile_size=self.size)
+        if self.transform is not None:
+            image = self.transform(image)
+        return image, torch.IntTensor([tile.x, tile.y, tile.z])
+
+    def unbuffer(self, probs):
+        """[C, H, W] -> [C, H - 2*overlap, W - 2*overlap]"""
+        o = self.overlap
+        _, h, w = probs.shape
+        return probs[:, o:h - o, o:w - o]

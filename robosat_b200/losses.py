@@ -1,0 +1,102 @@
+"""Loss modules with the reference's class names and call signature (robosat/losses.py:8-119):
+`forward(inputs fp32 [N, C, H, W], targets int64 [N, H, W]) -> 0-dim tensor` supporting `.backward()` / `.item()`.
+
+LovaszLoss2d and CrossEntropyLoss2d run entirely in librsb200.so: the forward kernel pipeline also produces the
+closed-form gradient, which `backward` just scales by the incoming gradient. FocalLoss2d / mIoULoss2d stay
+selectable (train.py:97-102) but are NOT accelerated yet: they raise instead of silently running elsewhere.
+"""
+
+import torch
+import torch.nn as nn
+
+from robosat_b200 import _lib
+
+
+class _LovaszFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, targets):
+        if not inputs.is_cuda:
+            raise _lib.RsbError("LovaszLoss2d runs on the GPU kernels only (no CPU fallback)")
+        lib = _lib.load()
+        n, c, h, w = inputs.shape
+        x = inputs.detach().contiguous().float()
+        t = targets.contiguous().long()
+        nbytes = lib.rsb_lovasz_workspace_bytes(n, c, h * w)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x)
+        _lib.check(lib.rsb_lovasz(x.data_ptr(), t.data_ptr(), loss.data_ptr(), grad.data_ptr(), ws.data_ptr(), nbytes, n, c, h * w,
+                                  _lib.current_stream_ptr()), "rsb_lovasz")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        return grad * grad_out, None
+
+
+class _CrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, targets, weight):
+        if not inputs.is_cuda:
+            raise _lib.RsbError("CrossEntropyLoss2d runs on the GPU kernels only (no CPU fallback)")
+        lib = _lib.load()
+        n, c, h, w = inputs.shape
+        x = inputs.detach().contiguous().float()
+        t = targets.contiguous().long()
+        wt = weight.to(x.device).contiguous().float() if weight is not None else None
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x)
+        scratch = torch.empty(2, dtype=torch.float64, device=x.device)
+        _lib.check(lib.rsb_cross_entropy(x.data_ptr(), t.data_ptr(), wt.data_ptr() if wt is not None else None, loss.data_ptr(), grad.data_ptr(),
+                                         scratch.data_ptr(), n, c, h * w, _lib.current_stream_ptr()), "rsb_cross_entropy")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        return grad * grad_out, None, None
+
+
+class CrossEntropyLoss2d(nn.Module):
+    """Class-weighted cross entropy (losses.py:8-25)."""
+
+    def __init__(self, weight=None):
+        super().__init__()
+        self.register_buffer("weight", weight if weight is None else torch.as_tensor(weight, dtype=torch.float32))
+
+    def forward(self, inputs, targets):
+        return _CrossEntropyFn.apply(inputs, targets, self.weight)
+
+
+class LovaszLoss2d(nn.Module):
+    """Lovasz hinge over the flattened C*H*W vector of every image (losses.py:86-119)."""
+
+    def __init__(self):
+        super().__init__()
+
+    def forward(self, inputs, targets):
+        return _LovaszFn.apply(inputs, targets)
+
+
+class FocalLoss2d(nn.Module):
+    """Kept selectable like the reference (losses.py:28-50); no B200 kernel yet -> explicit error."""
+
+    def __init__(self, gamma=2, weight=None):
+        super().__init__()
+        self.gamma = gamma
+
+    def forward(self, inputs, targets):
+        raise NotImplementedError("FocalLoss2d has no sm_100a kernel yet; use 'Lovasz' or 'CrossEntropy' in [opt].loss")
+
+
+class mIoULoss2d(nn.Module):
+    """Kept selectable like the reference (losses.py:53-83); no B200 kernel yet -> explicit error."""
+
+    def __init__(self, weight=None):
+        super().__init__()
+
+    def forward(self, inputs, targets):
+        raise NotImplementedError("mIoULoss2d has no sm_100a kernel yet; use 'Lovasz' or 'CrossEntropy' in [opt].loss")

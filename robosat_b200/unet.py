@@ -1,0 +1,94 @@
+"""`UNet` with the reference's constructor, attribute names and state_dict layout (robosat/unet.py:76-141),
+whose forward pass runs on librsb200.so.
+
+The module tree exists to hold parameters under the reference's names (`resnet.*`, `center`, `dec0..dec5`, `final`)
+so checkpoints written by either implementation load into the other (`module.`-prefixed when wrapped in
+`nn.DataParallel`, train.py:69). `forward` (eval mode) builds -- and caches per input shape -- a `UNetEngine`
+plan from the current parameters and replays it; nothing in it is executed by torch ops.
+
+Training-mode forward/backward (batch-statistics BatchNorm, dgrad/wgrad) is not part of this round: calling the
+module in training mode raises instead of silently running elsewhere.
+"""
+
+import torch
+import torch.nn as nn
+
+from robosat_b200 import _lib
+from robosat_b200.engine import UNetEngine
+
+
+class ConvRelu(nn.Module):
+    """3x3 convolution (no bias) + ReLU parameter holder (unet.py:18-44)."""
+
+    def __init__(self, num_in, num_out):
+        super().__init__()
+        self.block = nn.Conv2d(num_in, num_out, kernel_size=3, padding=1, bias=False)
+
+
+class DecoderBlock(nn.Module):
+    """Nearest x2 upsample + ConvRelu parameter holder (unet.py:47-73)."""
+
+    def __init__(self, num_in, num_out):
+        super().__init__()
+        self.block = ConvRelu(num_in, num_out)
+
+
+def _resnet50_container(pretrained):
+    from torchvision.models import resnet50  # parameter container only; its forward is never called
+
+    if pretrained:
+        try:
+            return resnet50(weights="IMAGENET1K_V1")
+        except Exception as exc:  # no network / no cached weights: checkpoints overwrite these anyway
+            import warnings
+
+            warnings.warn("ImageNet weights unavailable (%s); the encoder starts from random weights" % exc)
+    return resnet50(weights=None)
+
+
+class UNet(nn.Module):
+    def __init__(self, num_classes, num_filters=32, pretrained=True):
+        super().__init__()
+        assert num_filters == 32, "the B200 plan is built for the reference's num_filters=32"
+        self.num_classes = num_classes
+        self.resnet = _resnet50_container(pretrained)
+        self.center = DecoderBlock(2048, num_filters * 8)
+        self.dec0 = DecoderBlock(2048 + num_filters * 8, num_filters * 8)
+        self.dec1 = DecoderBlock(1024 + num_filters * 8, num_filters * 8)
+        self.dec2 = DecoderBlock(512 + num_filters * 8, num_filters * 2)
+        self.dec3 = DecoderBlock(256 + num_filters * 2, num_filters * 2 * 2)
+        self.dec4 = DecoderBlock(num_filters * 2 * 2, num_filters)
+        self.dec5 = ConvRelu(num_filters, num_filters)
+        self.final = nn.Conv2d(num_filters, num_classes, kernel_size=1)
+        self._engines = {}
+        self._weights_version = 0
+
+    # any weight change invalidates the packed plans
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_plans()
+        return out
+
+    def invalidate_plans(self):
+        self._engines.clear()
+
+    def _engine_for(self, x):
+        key = (tuple(x.shape), x.dtype, x.device.index)
+        eng = self._engines.get(key)
+        if eng is None:
+            n = x.shape[0]
+            h, w = (x.shape[2], x.shape[3]) if x.dtype == torch.float32 else (x.shape[1], x.shape[2])
+            sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+            eng = UNetEngine(sd, self.num_classes, n, h, w, device=x.device)
+            self._engines[key] = eng
+        return eng
+
+    def forward(self, x):
+        """x: fp32 [N, 3, H, W] normalised (reference API) or uint8 [N, H, W, 3] raw RGB -> fp32 [N, C, H, W] logits."""
+        if x.dtype == torch.float32:
+            assert x.size(-1) % 32 == 0 and x.size(-2) % 32 == 0, "image resolution has to be divisible by 32 for resnet"
+        if self.training or torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and x.requires_grad:
+            raise NotImplementedError("robosat_b200.UNet: the training forward/backward kernels are not built yet; call .eval() under torch.no_grad()")
+        if not x.is_cuda:
+            raise _lib.RsbError("robosat_b200.UNet runs on sm_100a kernels only (no CPU fallback); move the input to a CUDA device")
+        return self._engine_for(x).forward(x.contiguous()).clone()
