@@ -33,6 +33,8 @@ static constexpr int kNumThreads = 192;
 struct alignas(64) ConvKParams {
     CUtensorMap tmA[RSB_MAX_SRCS];
     CUtensorMap tmB;
+    CUtensorMap tmC[4];  // output view per phase (TMA store)
+    CUtensorMap tmR;     // residual view (TMA load), phases == 1 only
     int32_t nseg;
     int32_t seg_src[RSB_MAX_SEGS];
     int32_t seg_dh[RSB_MAX_SEGS];
@@ -55,14 +57,23 @@ struct alignas(64) ConvKParams {
     float* head_out;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE, bool HAS_RES>
 struct ConvCfg {
-    static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
+    // epilogue staging: the C tile leaves through shared memory in chunks of kChunk columns (TMA store), and the
+    // residual tile arrives the same way (TMA load); 2 buffers each
+    static constexpr int kChunk = BLOCK_N >= 64 ? 64 : 32;
+    static constexpr int kNumChunks = BLOCK_N / kChunk;
+    static constexpr int kChunkBytes = kBlockM * kChunk * 2;
+    static constexpr int kEpiBytes = MODE == 0 ? (2 + (HAS_RES ? 2 : 0)) * kChunkBytes : 0;
+    static constexpr int kBarBytes = 256;
+    static constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
+    static constexpr int kAvail = kMaxSmem - 1024 - kBarBytes - kEpiBytes;
+    static constexpr int kStages = (kAvail / kStageBytes) > 8 ? 8 : (kAvail / kStageBytes);
+    static_assert(kStages >= 3, "pipeline too shallow");
     static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
-    // stages + barriers (full, empty per stage; tmem_full, tmem_empty x2) + tmem ptr, plus 1 KB alignment slack
-    static constexpr int kSmemBytes = kStages * kStageBytes + (2 * kStages + 4) * 8 + 16 + 1024;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
 };
 
 struct TileCoord {
@@ -85,19 +96,22 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int id) {
     return t;
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool HAS_RES>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
-    using Cfg = ConvCfg<BLOCK_N>;
+    using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES>;
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle atoms repeat every 1024 bytes: tile bases must be 1024-byte aligned
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + Cfg::kStages * kABytes;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+    uint8_t* smem_c = smem + Cfg::kStages * Cfg::kStageBytes;          // 2 store buffers (1024-aligned)
+    uint8_t* smem_r = smem_c + 2 * Cfg::kChunkBytes;                     // 2 residual buffers (HAS_RES)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
     uint64_t* empty_bar = full_bar + Cfg::kStages;
     uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* res_full_bar = tmem_empty_bar + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full_bar + 2);
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -112,6 +126,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
             mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+            mbar_init(&res_full_bar[i], 1);
+        }
+        if (MODE == 0) {
+            for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmC[i]);
+            if (HAS_RES) tma_prefetch_desc(&p.tmR);
         }
         mbar_fence_init();
     }
@@ -191,6 +210,23 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         const int tn = row / (p.TW * p.TH);
         int acc = 0;
         uint32_t acc_phase = 0;
+        const bool is_leader = (warp_idx == 2) && (lane == 0);
+        uint32_t gchunk = 0;          // running chunk counter of this CTA (selects the staging buffer)
+        int res_tile = blockIdx.x;    // residual prefetch cursor (leader only)
+        int res_chunk = 0;
+        if (MODE == 0 && HAS_RES && is_leader) {
+#pragma unroll 1
+            for (int i = 0; i < 2 && res_tile < p.total_tiles; ++i) {
+                const TileCoord rt = decode_tile(p, res_tile);
+                mbar_expect_tx(&res_full_bar[i], Cfg::kChunkBytes);
+                tma_load_4d(smem_r + i * Cfg::kChunkBytes, &p.tmR, &res_full_bar[i], rt.n_blk * BLOCK_N + res_chunk * Cfg::kChunk,
+                            rt.w0, rt.h0, rt.n0);
+                if (++res_chunk == Cfg::kNumChunks) {
+                    res_chunk = 0;
+                    res_tile += gridDim.x;
+                }
+            }
+        }
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile);
             const int w = t.w0 + tw, h = t.h0 + th, n = t.n0 + tn;
@@ -200,55 +236,88 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
 
             if constexpr (MODE == 0) {
-                const int64_t off = static_cast<int64_t>(n) * p.out_pitch_n +
-                                    static_cast<int64_t>(h * p.out_sy + t.pa) * p.out_pitch_h +
-                                    static_cast<int64_t>(w * p.out_sx + t.pb) * p.out_pitch_w + t.n_blk * BLOCK_N;
-                __half* optr = p.out + off;
-                const __half* rptr = p.residual ? p.residual + off : nullptr;
                 const float* bptr = p.bias ? p.bias + t.n_blk * BLOCK_N : nullptr;
 #pragma unroll 1
-                for (int c = 0; c < BLOCK_N; c += 32) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + c, r);
-                    tmem_ld_wait();
-                    float v[32];
+                for (int ck = 0; ck < Cfg::kNumChunks; ++ck, ++gchunk) {
+                    const int buf = gchunk & 1;
+                    uint8_t* cbuf = smem_c + buf * Cfg::kChunkBytes;
+                    const uint8_t* rbuf = smem_r + buf * Cfg::kChunkBytes;
+                    if (HAS_RES) mbar_wait(&res_full_bar[buf], (gchunk >> 1) & 1);
+                    // the TMA store issued two chunks ago (same buffer) must have finished reading shared memory
+                    if (is_leader) tma_store_wait_read<1>();
+                    named_bar_sync(1, 128);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-                    if (bptr) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bptr + c + j));
-                            v[j] += b4.x;
-                            v[j + 1] += b4.y;
-                            v[j + 2] += b4.z;
-                            v[j + 3] += b4.w;
+                    for (int half = 0; half < Cfg::kChunk / 32; ++half) {
+                        const int c = ck * Cfg::kChunk + half * 32;
+                        uint32_t r[32];
+                        tmem_ld_32x32(taddr + c, r);
+                        tmem_ld_wait();
+                        if (ck == Cfg::kNumChunks - 1 && half == Cfg::kChunk / 32 - 1) {
+                            // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
                         }
-                    }
-                    if (rptr && valid) {
+                        float v[32];
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(rptr + c + j));
-                            const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
+                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        if (bptr) {
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) {
-                                const float2 f = __half22float2(h2[u]);
-                                v[j + 2 * u] += f.x;
-                                v[j + 2 * u + 1] += f.y;
+                            for (int j = 0; j < 32; j += 4) {
+                                const float4 b4 = __ldg(reinterpret_cast<const float4*>(bptr + c + j));
+                                v[j] += b4.x;
+                                v[j + 1] += b4.y;
+                                v[j + 2] += b4.z;
+                                v[j + 3] += b4.w;
                             }
                         }
-                    }
-                    if (p.relu) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
-                    }
-                    if (valid) {
+                        for (int j = 0; j < 4; ++j) {
+                            // 16-byte unit `u` of this row inside the chunk, at its swizzled position
+                            const int u = half * 4 + j;
+                            const int su = Cfg::kChunk == 64 ? (u ^ (row & 7)) : (u ^ ((row >> 1) & 3));
+                            const int soff = row * (Cfg::kChunk * 2) + su * 16;
+                            if (HAS_RES) {
+                                const uint4 r4 = *reinterpret_cast<const uint4*>(rbuf + soff);
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
+                                for (int e = 0; e < 4; ++e) {
+                                    const float2 f = __half22float2(h2[e]);
+                                    v[j * 8 + 2 * e] += f.x;
+                                    v[j * 8 + 2 * e + 1] += f.y;
+                                }
+                            }
                             uint4 o4;
-                            __half2* h2 = reinterpret_cast<__half2*>(&o4);
+                            __half2* o2 = reinterpret_cast<__half2*>(&o4);
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) h2[u] = __floats2half2_rn(v[j + 2 * u], v[j + 2 * u + 1]);
-                            *reinterpret_cast<uint4*>(optr + c + j) = o4;
+                            for (int e = 0; e < 4; ++e) {
+                                float a = v[j * 8 + 2 * e], b = v[j * 8 + 2 * e + 1];
+                                if (p.relu) {
+                                    a = fmaxf(a, 0.0f);
+                                    b = fmaxf(b, 0.0f);
+                                }
+                                o2[e] = __floats2half2_rn(a, b);
+                            }
+                            *reinterpret_cast<uint4*>(cbuf + soff) = o4;
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    named_bar_sync(1, 128);
+                    if (is_leader) {
+                        tma_store_4d(&p.tmC[t.phase], cbuf, t.n_blk * BLOCK_N + ck * Cfg::kChunk, t.w0, t.h0, t.n0);
+                        tma_store_commit();
+                        if (HAS_RES) {
+                            // residual buffer `buf` has been consumed by every epilogue thread: refill it two chunks ahead
+                            if (res_tile < p.total_tiles) {
+                                const TileCoord rt = decode_tile(p, res_tile);
+                                mbar_expect_tx(&res_full_bar[buf], Cfg::kChunkBytes);
+                                tma_load_4d(smem_r + buf * Cfg::kChunkBytes, &p.tmR, &res_full_bar[buf],
+                                            rt.n_blk * BLOCK_N + res_chunk * Cfg::kChunk, rt.w0, rt.h0, rt.n0);
+                                if (++res_chunk == Cfg::kNumChunks) {
+                                    res_chunk = 0;
+                                    res_tile += gridDim.x;
+                                }
+                            }
                         }
                     }
                 }
@@ -275,14 +344,17 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
                 }
             }
 
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if constexpr (MODE == 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            }
             if (++acc == 2) {
                 acc = 0;
                 acc_phase ^= 1;
             }
         }
+        if (MODE == 0 && is_leader) tma_store_wait<0>();  // all output tiles written before the CTA retires
     }
 
     tc_fence_before();
@@ -359,6 +431,7 @@ struct rsb_conv_plan {
     int mode;
     int grid;
     int smem;
+    bool has_res;
 };
 
 static int validate_desc(const rsb_conv_desc* d, int* K_out) {
@@ -405,19 +478,26 @@ static int validate_desc(const rsb_conv_desc* d, int* K_out) {
     return RSB_OK;
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool HAS_RES>
 static int launch_conv(const rsb_conv_plan* plan, cudaStream_t stream) {
-    auto kern = conv_tc_kernel<BLOCK_N, MODE>;
+    using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES>;
+    auto kern = conv_tc_kernel<BLOCK_N, MODE, HAS_RES>;
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ConvCfg<BLOCK_N>::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv)");
         attr_set = true;
     }
-    kern<<<plan->grid, kNumThreads, ConvCfg<BLOCK_N>::kSmemBytes, stream>>>(plan->kp);
+    kern<<<plan->grid, kNumThreads, Cfg::kSmemBytes, stream>>>(plan->kp);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "conv_tc_kernel launch");
     return RSB_OK;
+}
+
+template <int BLOCK_N>
+static int smem_for(int mode, bool res) {
+    if (mode == 1) return ConvCfg<BLOCK_N, 1, false>::kSmemBytes;
+    return res ? ConvCfg<BLOCK_N, 0, true>::kSmemBytes : ConvCfg<BLOCK_N, 0, false>::kSmemBytes;
 }
 
 extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_plan) {
@@ -455,6 +535,40 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
             delete plan;
             return rc;
         }
+    }
+    if (d->mode == 0) {
+        // output (and residual) views in tile space: pixel (w, h, n) of phase (a, b) lives at
+        // out + n*pitch_n + (h*sy + a)*pitch_h + (w*sx + b)*pitch_w; stored / loaded in 64- (or 32-) channel chunks
+        const int sy = d->out_sy > 0 ? d->out_sy : 1, sx = d->out_sx > 0 ? d->out_sx : 1;
+        const int chunk = d->block_n >= 64 ? 64 : 32;
+        const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wt, (uint64_t)d->Ht, (uint64_t)d->Nt};
+        const uint64_t strides[3] = {(uint64_t)sx * d->out_pitch_w * 2, (uint64_t)sy * d->out_pitch_h * 2, (uint64_t)d->out_pitch_n * 2};
+        const uint32_t box[4] = {(uint32_t)chunk, (uint32_t)d->TW, (uint32_t)d->TH, (uint32_t)d->TN};
+        for (int ph = 0; ph < 4; ++ph) {
+            const int a = ph >> 1, b = ph & 1;
+            const __half* base = static_cast<const __half*>(d->out) + (ph < d->phases ? a * d->out_pitch_h + b * d->out_pitch_w : 0);
+            rc = encode_tiled_f16(&kp.tmC[ph], 4, base, dims, strides, box, chunk * 2);
+            if (rc) {
+                delete plan;
+                return rc;
+            }
+        }
+        if (d->residual) {
+            if (d->phases != 1) {
+                delete plan;
+                return set_error(RSB_E_INVALID, "conv: residual needs phases == 1");
+            }
+            rc = encode_tiled_f16(&kp.tmR, 4, d->residual, dims, strides, box, chunk * 2);
+            if (rc) {
+                delete plan;
+                return rc;
+            }
+        } else {
+            kp.tmR = kp.tmC[0];
+        }
+    } else {
+        for (int ph = 0; ph < 4; ++ph) kp.tmC[ph] = kp.tmA[0];
+        kp.tmR = kp.tmA[0];
     }
     kp.nseg = d->nseg;
     for (int s = 0; s < d->nseg; ++s) {
@@ -495,11 +609,12 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
     plan->mode = d->mode;
     const int sms = num_sms();
     plan->grid = kp.total_tiles < sms ? kp.total_tiles : sms;
+    plan->has_res = d->mode == 0 && d->residual != nullptr;
     switch (d->block_n) {
-        case 32: plan->smem = ConvCfg<32>::kSmemBytes; break;
-        case 64: plan->smem = ConvCfg<64>::kSmemBytes; break;
-        case 128: plan->smem = ConvCfg<128>::kSmemBytes; break;
-        default: plan->smem = ConvCfg<256>::kSmemBytes; break;
+        case 32: plan->smem = smem_for<32>(d->mode, plan->has_res); break;
+        case 64: plan->smem = smem_for<64>(d->mode, plan->has_res); break;
+        case 128: plan->smem = smem_for<128>(d->mode, plan->has_res); break;
+        default: plan->smem = smem_for<256>(d->mode, plan->has_res); break;
     }
     *out_plan = plan;
     return RSB_OK;
@@ -519,12 +634,21 @@ extern "C" int rsb_conv_plan_info(const rsb_conv_plan* plan, int32_t* grid, int3
 extern "C" int rsb_conv_run(const rsb_conv_plan* plan, void* stream_) {
     if (!plan) return set_error(RSB_E_INVALID, "conv: null plan");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (plan->mode == 1) return launch_conv<32, 1>(plan, stream);
-    switch (plan->block_n) {
-        case 32: return launch_conv<32, 0>(plan, stream);
-        case 64: return launch_conv<64, 0>(plan, stream);
-        case 128: return launch_conv<128, 0>(plan, stream);
-        case 256: return launch_conv<256, 0>(plan, stream);
+    if (plan->mode == 1) return launch_conv<32, 1, false>(plan, stream);
+    if (plan->has_res) {
+        switch (plan->block_n) {
+            case 32: return launch_conv<32, 0, true>(plan, stream);
+            case 64: return launch_conv<64, 0, true>(plan, stream);
+            case 128: return launch_conv<128, 0, true>(plan, stream);
+            case 256: return launch_conv<256, 0, true>(plan, stream);
+        }
+    } else {
+        switch (plan->block_n) {
+            case 32: return launch_conv<32, 0, false>(plan, stream);
+            case 64: return launch_conv<64, 0, false>(plan, stream);
+            case 128: return launch_conv<128, 0, false>(plan, stream);
+            case 256: return launch_conv<256, 0, false>(plan, stream);
+        }
     }
     return set_error(RSB_E_INVALID, "conv: bad block_n");
 }

@@ -43,7 +43,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 int encode_tiled_f16(CUtensorMap* map, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box) {
+                     const uint32_t* box, int swizzle_bytes) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return set_error(RSB_E_NODEVICE, "cuTensorMapEncodeTiled driver entry point unavailable (no CUDA driver?)");
     cuuint64_t gdim[5];
@@ -56,8 +56,10 @@ int encode_tiled_f16(CUtensorMap* map, int rank, const void* base, const uint64_
         estr[i] = 1;
     }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    const CUtensorMapSwizzle swz = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : (swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE);
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
-                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         char buf[256];

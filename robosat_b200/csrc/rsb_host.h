@@ -14,7 +14,7 @@ int set_cuda_error(cudaError_t e, const char* what);
 // cuTensorMapEncodeTiled through cudaGetDriverEntryPoint (no link-time dependency on libcuda, so the
 // library still loads on a machine without a driver). fp16 elements, 128-byte swizzle, zero OOB fill.
 int encode_tiled_f16(CUtensorMap* map, int rank, const void* base, const uint64_t* dims, const uint64_t* strides_bytes,
-                     const uint32_t* box);
+                     const uint32_t* box, int swizzle_bytes = 128);
 
 int num_sms();
 

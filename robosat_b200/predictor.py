@@ -73,12 +73,14 @@ class TilePredictor:
         main = torch.cuda.current_stream(self.device)
         if slot.get("busy"):
             slot["done"].synchronize()  # host side: the pinned buffers of this slot are free again
-        if tiles_u8_host is not slot["h_in"]:
-            slot["h_in"].copy_(tiles_u8_host)  # stage into pinned memory (no-op when the caller filled it directly)
+        src = tiles_u8_host
+        if not src.is_pinned():
+            slot["h_in"].copy_(src)  # pageable memory: stage through the slot's pinned buffer
+            src = slot["h_in"]
         with torch.cuda.stream(self._copy_in):
             if slot.get("busy"):
                 self._copy_in.wait_event(slot["consumed"])  # previous forward that read d_in has finished
-            slot["d_in"].copy_(slot["h_in"], non_blocking=True)
+            slot["d_in"].copy_(src, non_blocking=True)  # pinned source: DMA straight from the caller's buffer
             slot["loaded"].record(self._copy_in)
         main.wait_event(slot["loaded"])
         logits = self.engine.forward(slot["d_in"])
