@@ -1,0 +1,212 @@
+"""`rs train`: same flags, configuration keys, log lines and checkpoint layout as robosat/tools/train.py:42-276.
+
+What is B200-native today: the losses (`LovaszLoss2d`, `CrossEntropyLoss2d`: sort/scan + closed-form gradient
+kernels), the metrics (one counting kernel per batch, one read-back per epoch instead of 4 syncs per sample), and
+Adam (one fused kernel over a flat arena). The network's training forward/backward (batch-statistics BatchNorm,
+dgrad, wgrad) is the next row of SURVEY.md §8 and is NOT built yet: `UNet.forward` raises in training mode, so this
+tool exits with that message instead of silently training on another implementation. Validation (eval mode, no
+grad) already runs on the B200 inference plan.
+"""
+
+import argparse
+import collections
+import os
+import sys
+
+import torch
+from PIL import Image
+
+from robosat_b200.config import load_config
+from robosat_b200.datasets import SlippyMapTilesConcatenation
+from robosat_b200.log import Log
+from robosat_b200.losses import CrossEntropyLoss2d, FocalLoss2d, LovaszLoss2d, mIoULoss2d
+from robosat_b200.metrics import Metrics
+from robosat_b200.optim import Adam
+from robosat_b200.transforms import (ConvertImageMode, ImageToTensor, JointCompose, JointRandomHorizontalFlip, JointRandomRotation,
+                                     JointTransform, MaskToTensor)
+from robosat_b200.unet import UNet
+
+
+def add_parser(subparser):
+    parser = subparser.add_parser("train", help="trains model on dataset", formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    parser.add_argument("--model", type=str, required=True, help="path to model configuration file")
+    parser.add_argument("--dataset", type=str, required=True, help="path to dataset configuration file")
+    parser.add_argument("--checkpoint", type=str, required=False, help="path to a model checkpoint (to retrain)")
+    parser.add_argument("--resume", type=bool, default=False, help="resume training or fine-tuning (if checkpoint)")  # type=bool quirk kept (train.py:50)
+    parser.add_argument("--workers", type=int, default=0, help="number of workers pre-processing images")
+    parser.set_defaults(func=main)
+
+
+def _plot(path, history):
+    try:  # matplotlib is optional here; the reference requires it (utils.py)
+        import matplotlib
+
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+    except ImportError:
+        return
+    plt.figure()
+    n = max(map(len, history.values()))
+    plt.xticks(range(n), [v + 1 for v in range(n)])
+    plt.grid()
+    for values in history.values():
+        plt.plot(values)
+    plt.xlabel("epoch")
+    plt.legend(list(history))
+    plt.savefig(path, format="png")
+    plt.close()
+
+
+class _Normalize:
+    def __init__(self, mean, std):
+        self.mean = torch.tensor(mean).view(3, 1, 1)
+        self.std = torch.tensor(std).view(3, 1, 1)
+
+    def __call__(self, t):
+        return (t - self.mean) / self.std
+
+
+class _ResizeCrop:
+    """Resize(target, mode) followed by CenterCrop(target) on a PIL image (train.py:250-251)."""
+
+    def __init__(self, size, mode):
+        self.size, self.mode = size, mode
+
+    def __call__(self, image):
+        if image.size != self.size:
+            image = image.resize(self.size, self.mode)
+        return image
+
+
+def get_dataset_loaders(model, dataset, workers):
+    from torch.utils.data import DataLoader
+
+    target_size = (model["common"]["image_size"],) * 2
+    batch_size = model["common"]["batch_size"]
+    path = dataset["common"]["dataset"]
+    mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
+    transform = JointCompose([
+        JointTransform(ConvertImageMode("RGB"), ConvertImageMode("P")),
+        JointTransform(_ResizeCrop(target_size, Image.BILINEAR), _ResizeCrop(target_size, Image.NEAREST)),
+        JointRandomHorizontalFlip(0.5),
+        JointRandomRotation(0.5, 90),
+        JointRandomRotation(0.5, 90),
+        JointRandomRotation(0.5, 90),
+        JointTransform(ImageToTensor(), MaskToTensor()),
+        JointTransform(_Normalize(mean, std), None),
+    ])
+    train_dataset = SlippyMapTilesConcatenation([os.path.join(path, "training", "images")], os.path.join(path, "training", "labels"), transform)
+    val_dataset = SlippyMapTilesConcatenation([os.path.join(path, "validation", "images")], os.path.join(path, "validation", "labels"), transform)
+    assert len(train_dataset) > 0, "at least one tile in training dataset"
+    assert len(val_dataset) > 0, "at least one tile in validation dataset"
+    train_loader = DataLoader(train_dataset, batch_size=batch_size, shuffle=True, drop_last=True, num_workers=workers)
+    val_loader = DataLoader(val_dataset, batch_size=batch_size, shuffle=False, drop_last=True, num_workers=workers)
+    return train_loader, val_loader
+
+
+def _epoch(loader, num_classes, device, net, criterion, optimizer=None):
+    """One pass of train() (train.py:163-201) or validate() (train.py:204-238): same bookkeeping, batched metrics."""
+    training = optimizer is not None
+    num_samples, running_loss = 0, torch.zeros((), dtype=torch.float32, device=device)
+    metrics = Metrics(range(num_classes))
+    net.train() if training else net.eval()
+    for images, masks, _tiles in loader:
+        images = images.to(device, non_blocking=True)
+        masks = masks.to(device, non_blocking=True)
+        assert images.size()[2:] == masks.size()[1:], "resolutions for images and masks are in sync"
+        num_samples += int(images.size(0))
+        if training:
+            optimizer.zero_grad()
+            outputs = net(images)
+        else:
+            with torch.no_grad():
+                outputs = net(images)
+        assert outputs.size()[2:] == masks.size()[1:], "resolutions for predictions and masks are in sync"
+        assert outputs.size()[1] == num_classes, "classes for predictions and dataset are in sync"
+        loss = criterion(outputs, masks)
+        if training:
+            loss.backward()
+            optimizer.step()
+        running_loss += loss.detach()  # stays on the device: one read-back per epoch instead of one per batch
+        metrics.add_batch(masks, outputs.detach())
+    return {"loss": running_loss.item() / num_samples, "miou": metrics.get_miou(), "fg_iou": metrics.get_fg_iou(), "mcc": metrics.get_mcc()}
+
+
+def main(args):
+    model = load_config(args.model)
+    dataset = load_config(args.dataset)
+    if not model["common"]["cuda"]:
+        sys.exit("Error: robosat_b200 runs on CUDA devices only; set cuda = true in the model configuration")
+    if not torch.cuda.is_available():
+        sys.exit("Error: CUDA requested but not available")
+    device = torch.device("cuda")
+    os.makedirs(model["common"]["checkpoint"], exist_ok=True)
+
+    num_classes = len(dataset["common"]["classes"])
+    net = torch.nn.DataParallel(UNet(num_classes), device_ids=[0])  # keeps the `module.` checkpoint prefix (train.py:69)
+    net = net.to(device)
+
+    try:
+        weight = torch.Tensor(dataset["weights"]["values"])
+    except KeyError:
+        if model["opt"]["loss"] in ("CrossEntropy", "mIoU", "Focal"):
+            sys.exit("Error: The loss function used, need dataset weights values")
+
+    optimizer = Adam(net.parameters(), lr=model["opt"]["lr"])
+    optimizer.mark_used([not n.startswith("module.resnet.fc.") for n, _ in net.named_parameters()])
+
+    resume = 0
+    if args.checkpoint:
+        chkpt = torch.load(args.checkpoint, map_location="cpu")
+        net.load_state_dict(chkpt["state_dict"])
+        if args.resume:
+            optimizer.load_state_dict(chkpt["optimizer"])
+            resume = chkpt["epoch"]
+
+    loss_name = model["opt"]["loss"]
+    if loss_name == "CrossEntropy":
+        criterion = CrossEntropyLoss2d(weight=weight).to(device)
+    elif loss_name == "mIoU":
+        criterion = mIoULoss2d(weight=weight).to(device)
+    elif loss_name == "Focal":
+        criterion = FocalLoss2d(weight=weight).to(device)
+    elif loss_name == "Lovasz":
+        criterion = LovaszLoss2d().to(device)
+    else:
+        sys.exit("Error: Unknown [opt][loss] value !")
+
+    train_loader, val_loader = get_dataset_loaders(model, dataset, args.workers)
+    num_epochs = model["opt"]["epochs"]
+    if resume >= num_epochs:
+        sys.exit("Error: Epoch {} set in {} already reached by the checkpoint provided".format(num_epochs, args.model))
+
+    history = collections.defaultdict(list)
+    log = Log(os.path.join(model["common"]["checkpoint"], "log"))
+    log.log("--- Hyper Parameters on Dataset: {} ---".format(dataset["common"]["dataset"]))
+    log.log("Batch Size:\t {}".format(model["common"]["batch_size"]))
+    log.log("Image Size:\t {}".format(model["common"]["image_size"]))
+    log.log("Learning Rate:\t {}".format(model["opt"]["lr"]))
+    log.log("Loss function:\t {}".format(model["opt"]["loss"]))
+    if "weight" in locals():
+        log.log("Weights :\t {}".format(dataset["weights"]["values"]))
+    log.log("---")
+
+    fg = dataset["common"]["classes"][1]
+    for epoch in range(resume, num_epochs):
+        log.log("Epoch: {}/{}".format(epoch + 1, num_epochs))
+        try:
+            train_hist = _epoch(train_loader, num_classes, device, net, criterion, optimizer)
+        except NotImplementedError as exc:
+            sys.exit("Error: {}".format(exc))
+        log.log("Train    loss: {:.4f}, mIoU: {:.3f}, {} IoU: {:.3f}, MCC: {:.3f}".format(
+            train_hist["loss"], train_hist["miou"], fg, train_hist["fg_iou"], train_hist["mcc"]))
+        for k, v in train_hist.items():
+            history["train " + k].append(v)
+        val_hist = _epoch(val_loader, num_classes, device, net, criterion)
+        log.log("Validate loss: {:.4f}, mIoU: {:.3f}, {} IoU: {:.3f}, MCC: {:.3f}".format(
+            val_hist["loss"], val_hist["miou"], fg, val_hist["fg_iou"], val_hist["mcc"]))
+        for k, v in val_hist.items():
+            history["val " + k].append(v)
+        _plot(os.path.join(model["common"]["checkpoint"], "history-{:05d}-of-{:05d}.png".format(epoch + 1, num_epochs)), history)
+        states = {"epoch": epoch + 1, "state_dict": net.state_dict(), "optimizer": optimizer.state_dict()}
+        torch.save(states, os.path.join(model["common"]["checkpoint"], "checkpoint-{:05d}-of-{:05d}.pth".format(epoch + 1, num_epochs)))

@@ -11,7 +11,7 @@ class ImageToTensor:
     """PIL RGB image -> fp32 CHW in [0, 1] (what torchvision's ToTensor does for uint8 images)."""
 
     def __call__(self, image):
-        arr = np.asarray(image, dtype=np.uint8)
+        arr = np.array(image, dtype=np.uint8)
         if arr.ndim == 2:
             arr = arr[:, :, None]
         return torch.from_numpy(np.ascontiguousarray(arr)).permute(2, 0, 1).float().div(255)
@@ -21,7 +21,7 @@ class ImageToUint8Tensor:
     """PIL RGB image -> uint8 HWC tensor: the raw form the B200 pre-pass normalises on the device."""
 
     def __call__(self, image):
-        return torch.from_numpy(np.ascontiguousarray(np.asarray(image.convert("RGB"), dtype=np.uint8)))
+        return torch.from_numpy(np.array(image.convert("RGB"), dtype=np.uint8))
 
 
 class MaskToTensor:

@@ -104,7 +104,35 @@ def main():
         opt.step()
         res["adam_p%d" % (s + 1)] = p.detach().numpy().copy()
     np.savez_compressed(os.path.join(HERE, "losses.npz"), **res)
-    for f in ("unet_64.npz", "unet_stats.npz", "losses.npz"):
+    # halo stitching (tiles.py:162-227) and the probability palette (colors.py:70-95) on a synthetic 3x3 grid with a hole
+    import tempfile
+
+    from PIL import Image
+    from robosat.colors import continuous_palette_for_color, make_palette
+    from robosat.tiles import buffer_tile_image, tiles_from_slippy_map
+
+    rng = np.random.RandomState(5)
+    with tempfile.TemporaryDirectory() as tmp:
+        grid = {}
+        for x in range(10, 13):
+            for y in range(20, 23):
+                if (x, y) == (12, 20):
+                    continue  # missing neighbour -> nodata border
+                arr = rng.randint(0, 256, (16, 16, 3)).astype(np.uint8)
+                os.makedirs(os.path.join(tmp, "7", str(x)), exist_ok=True)
+                Image.fromarray(arr).save(os.path.join(tmp, "7", str(x), "%d.png" % y))
+                grid["tile_%d_%d" % (x, y)] = arr
+        tiles = list(tiles_from_slippy_map(tmp))
+        centre = [t for t, _ in tiles if (t.x, t.y) == (11, 21)][0]
+        corner = [t for t, _ in tiles if (t.x, t.y) == (10, 20)][0]
+        grid["buffered_centre_o4"] = np.array(buffer_tile_image(centre, tiles, overlap=4, tile_size=16))
+        grid["buffered_corner_o4"] = np.array(buffer_tile_image(corner, tiles, overlap=4, tile_size=16))
+        grid["buffered_centre_o0"] = np.array(buffer_tile_image(centre, tiles, overlap=0, tile_size=16))
+    grid["palette_pink_256"] = np.array(continuous_palette_for_color("pink", 256), dtype=np.int64)
+    grid["palette_denim_orange"] = np.array(make_palette("denim", "orange"), dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "tiles.npz"), **grid)
+
+    for f in ("unet_64.npz", "unet_stats.npz", "losses.npz", "tiles.npz"):
         print(f, os.path.getsize(os.path.join(HERE, f)), "bytes")
 
 
