@@ -66,12 +66,17 @@ struct ConvCfg {
     static constexpr int kChunk = BLOCK_N >= 64 ? 64 : 32;
     static constexpr int kNumChunks = BLOCK_N / kChunk;
     static constexpr int kChunkBytes = kBlockM * kChunk * 2;
-    static constexpr int kEpiBytes = MODE == 0 ? (2 + (HAS_RES ? 2 : 0)) * kChunkBytes : 0;
-    static constexpr int kBarBytes = 256;
+    // every epilogue warp owns its 32 rows of the tile end to end (own staging slices, own TMA stores / residual
+    // loads, no cross-warp barrier): kStoreBufs store slices and kResBufs residual slices of kWarpChunkBytes each
+    static constexpr int kWarpChunkBytes = 32 * kChunk * 2;
+    static constexpr int kStoreBufs = 2;
+    static constexpr int kResBufs = HAS_RES ? 4 : 0;
+    static constexpr int kEpiBytes = MODE == 0 ? (kStoreBufs + kResBufs) * kChunkBytes : 0;
+    static constexpr int kBarBytes = 384;
     static constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
     static constexpr int kAvail = kMaxSmem - 1024 - kBarBytes - kEpiBytes;
     static constexpr int kStages = (kAvail / kStageBytes) > 8 ? 8 : (kAvail / kStageBytes);
-    static_assert(kStages >= 3, "pipeline too shallow");
+    static_assert(kStages >= 2, "pipeline too shallow");
     static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
 };
@@ -105,13 +110,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + Cfg::kStages * kABytes;
     uint8_t* smem_c = smem + Cfg::kStages * Cfg::kStageBytes;          // 2 store buffers (1024-aligned)
-    uint8_t* smem_r = smem_c + 2 * Cfg::kChunkBytes;                     // 2 residual buffers (HAS_RES)
+    uint8_t* smem_r = smem_c + Cfg::kStoreBufs * Cfg::kChunkBytes;       // residual buffers (HAS_RES)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
     uint64_t* empty_bar = full_bar + Cfg::kStages;
     uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint64_t* res_full_bar = tmem_empty_bar + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full_bar + 2);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full_bar + 16);  // res_full_bar[warp q][buffer]
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -126,8 +131,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
             mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
-            mbar_init(&res_full_bar[i], 1);
         }
+        for (int i = 0; i < 16; ++i) mbar_init(&res_full_bar[i], 1);
         if (MODE == 0) {
             for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmC[i]);
             if (HAS_RES) tma_prefetch_desc(&p.tmR);
@@ -210,22 +215,30 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         const int tn = row / (p.TW * p.TH);
         int acc = 0;
         uint32_t acc_phase = 0;
-        const bool is_leader = (warp_idx == 2) && (lane == 0);
-        uint32_t gchunk = 0;          // running chunk counter of this CTA (selects the staging buffer)
-        int res_tile = blockIdx.x;    // residual prefetch cursor (leader only)
+        // this warp's quarter of the tile box: rows [32q, 32q+32) -> box offset (qw, qh, qn) inside the TW x TH x TN tile
+        const int qrow0 = q * 32;
+        const int qw = qrow0 % p.TW, qh = (qrow0 / p.TW) % p.TH, qn = qrow0 / (p.TW * p.TH);
+        uint8_t* my_c = smem_c + q * Cfg::kWarpChunkBytes;   // + buf * kChunkBytes
+        uint8_t* my_r = smem_r + q * Cfg::kWarpChunkBytes;
+        uint64_t* my_res_bar = res_full_bar + q * 4;
+        uint32_t wchunk = 0;          // running chunk counter of this warp (selects staging buffers)
+        int res_tile = blockIdx.x;    // residual prefetch cursor (lane 0)
         int res_chunk = 0;
-        if (MODE == 0 && HAS_RES && is_leader) {
-#pragma unroll 1
-            for (int i = 0; i < 2 && res_tile < p.total_tiles; ++i) {
+        auto issue_residual = [&](int rb) {
+            if (res_tile < p.total_tiles) {
                 const TileCoord rt = decode_tile(p, res_tile);
-                mbar_expect_tx(&res_full_bar[i], Cfg::kChunkBytes);
-                tma_load_4d(smem_r + i * Cfg::kChunkBytes, &p.tmR, &res_full_bar[i], rt.n_blk * BLOCK_N + res_chunk * Cfg::kChunk,
-                            rt.w0, rt.h0, rt.n0);
+                mbar_expect_tx(&my_res_bar[rb], Cfg::kWarpChunkBytes);
+                tma_load_4d(my_r + rb * Cfg::kChunkBytes, &p.tmR, &my_res_bar[rb], rt.n_blk * BLOCK_N + res_chunk * Cfg::kChunk,
+                            rt.w0 + qw, rt.h0 + qh, rt.n0 + qn);
                 if (++res_chunk == Cfg::kNumChunks) {
                     res_chunk = 0;
                     res_tile += gridDim.x;
                 }
             }
+        };
+        if (MODE == 0 && HAS_RES && lane == 0) {
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) issue_residual(i);
         }
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile);
@@ -238,14 +251,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
             if constexpr (MODE == 0) {
                 const float* bptr = p.bias ? p.bias + t.n_blk * BLOCK_N : nullptr;
 #pragma unroll 1
-                for (int ck = 0; ck < Cfg::kNumChunks; ++ck, ++gchunk) {
-                    const int buf = gchunk & 1;
-                    uint8_t* cbuf = smem_c + buf * Cfg::kChunkBytes;
-                    const uint8_t* rbuf = smem_r + buf * Cfg::kChunkBytes;
-                    if (HAS_RES) mbar_wait(&res_full_bar[buf], (gchunk >> 1) & 1);
-                    // the TMA store issued two chunks ago (same buffer) must have finished reading shared memory
-                    if (is_leader) tma_store_wait_read<1>();
-                    named_bar_sync(1, 128);
+                for (int ck = 0; ck < Cfg::kNumChunks; ++ck, ++wchunk) {
+                    const int rb = wchunk & 3;
+                    uint8_t* cbuf = my_c + (wchunk & 1) * Cfg::kChunkBytes;
+                    const uint8_t* rbuf = my_r + rb * Cfg::kChunkBytes;
+                    if (HAS_RES) mbar_wait(&my_res_bar[rb], (wchunk >> 2) & 1);
+                    // the TMA store this warp issued two chunks ago (same slice) must have finished reading shared memory
+                    if (lane == 0) tma_store_wait_read<1>();
+                    __syncwarp();
 #pragma unroll
                     for (int half = 0; half < Cfg::kChunk / 32; ++half) {
                         const int c = ck * Cfg::kChunk + half * 32;
@@ -275,8 +288,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
                         for (int j = 0; j < 4; ++j) {
                             // 16-byte unit `u` of this row inside the chunk, at its swizzled position
                             const int u = half * 4 + j;
-                            const int su = Cfg::kChunk == 64 ? (u ^ (row & 7)) : (u ^ ((row >> 1) & 3));
-                            const int soff = row * (Cfg::kChunk * 2) + su * 16;
+                            const int su = Cfg::kChunk == 64 ? (u ^ (lane & 7)) : (u ^ ((lane >> 1) & 3));
+                            const int soff = lane * (Cfg::kChunk * 2) + su * 16;
                             if (HAS_RES) {
                                 const uint4 r4 = *reinterpret_cast<const uint4*>(rbuf + soff);
                                 const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
@@ -302,23 +315,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
                         }
                     }
                     fence_proxy_async_smem();
-                    named_bar_sync(1, 128);
-                    if (is_leader) {
-                        tma_store_4d(&p.tmC[t.phase], cbuf, t.n_blk * BLOCK_N + ck * Cfg::kChunk, t.w0, t.h0, t.n0);
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&p.tmC[t.phase], cbuf, t.n_blk * BLOCK_N + ck * Cfg::kChunk, t.w0 + qw, t.h0 + qh, t.n0 + qn);
                         tma_store_commit();
-                        if (HAS_RES) {
-                            // residual buffer `buf` has been consumed by every epilogue thread: refill it two chunks ahead
-                            if (res_tile < p.total_tiles) {
-                                const TileCoord rt = decode_tile(p, res_tile);
-                                mbar_expect_tx(&res_full_bar[buf], Cfg::kChunkBytes);
-                                tma_load_4d(smem_r + buf * Cfg::kChunkBytes, &p.tmR, &res_full_bar[buf],
-                                            rt.n_blk * BLOCK_N + res_chunk * Cfg::kChunk, rt.w0, rt.h0, rt.n0);
-                                if (++res_chunk == Cfg::kNumChunks) {
-                                    res_chunk = 0;
-                                    res_tile += gridDim.x;
-                                }
-                            }
-                        }
+                        // residual slice `rb` has been consumed by the whole warp: refill it four chunks ahead
+                        if (HAS_RES) issue_residual(rb);
                     }
                 }
             } else {
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
                 acc_phase ^= 1;
             }
         }
-        if (MODE == 0 && is_leader) tma_store_wait<0>();  // all output tiles written before the CTA retires
+        if (MODE == 0 && lane == 0) tma_store_wait<0>();  // all output slices written before the CTA retires
     }
 
     tc_fence_before();
@@ -543,7 +545,15 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
         const int chunk = d->block_n >= 64 ? 64 : 32;
         const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wt, (uint64_t)d->Ht, (uint64_t)d->Nt};
         const uint64_t strides[3] = {(uint64_t)sx * d->out_pitch_w * 2, (uint64_t)sy * d->out_pitch_h * 2, (uint64_t)d->out_pitch_n * 2};
-        const uint32_t box[4] = {(uint32_t)chunk, (uint32_t)d->TW, (uint32_t)d->TH, (uint32_t)d->TN};
+        // one box per epilogue warp = 32 consecutive tile rows
+        const int bw = d->TW < 32 ? d->TW : 32;
+        const int bh = (32 / bw) < d->TH ? (32 / bw) : d->TH;
+        const int bn = 32 / (bw * bh);
+        if (32 % d->TW && d->TW % 32) {
+            delete plan;
+            return set_error(RSB_E_INVALID, "conv: TW must divide or be a multiple of 32");
+        }
+        const uint32_t box[4] = {(uint32_t)chunk, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
         for (int ph = 0; ph < 4; ++ph) {
             const int a = ph >> 1, b = ph & 1;
             const __half* base = static_cast<const __half*>(d->out) + (ph < d->phases ? a * d->out_pitch_h + b * d->out_pitch_w : 0);

@@ -189,6 +189,8 @@ def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out
     d.TW, d.TH, d.TN = choose_tile(Wt, Ht, Nt)
     m_tiles = -(-Wt // d.TW) * -(-Ht // d.TH) * -(-Nt // d.TN)
     d.block_n = block_n or choose_block_n(cout, m_tiles, phases)
+    if residual is not None and block_n is None and d.block_n == 256:
+        d.block_n = 128  # residual epilogues keep 4 residual slices in flight per warp: leave room for 4 pipeline stages
     d.out_sy, d.out_sx = out_scale
     d.relu = 1 if relu else 0
     if head is None:
@@ -299,23 +301,25 @@ class UNetEngine:
                 self._add_conv(p + ".conv2", make_conv_desc(
                     srcs, segs, dev(pack_conv(w), torch.float16), dev(b, torch.float32), planes, 1, (oW, oH, N), t2,
                     (planes, oW * planes, oH * oW * planes)))
-                # identity / downsample 1x1 (stride) + bn
                 outC = planes * 4
-                if (p + ".downsample.0.weight") in sd:
-                    w, b = fold_bn(sd, p + ".downsample.0.weight", p + ".downsample.1")
-                    idt = self._buf(N, oH, oW, outC)
-                    s = _src_dense(cur, N, curH, curW, curC) if stride == 1 else _src_parity(cur, N, curH, curW, curC, 0, 0)
-                    self._add_conv(p + ".downsample", make_conv_desc(
-                        [s], [(0, 0, 0, curC // 64)], dev(pack_conv(w), torch.float16), dev(b, torch.float32), outC, 1,
-                        (oW, oH, N), idt, (outC, oW * outC, oH * oW * outC), relu=False))
-                else:
-                    idt = cur
-                # conv3 1x1 + bn3 + identity + relu
-                w, b = fold_bn(sd, p + ".conv3.weight", p + ".bn3")
+                w3, b3 = fold_bn(sd, p + ".conv3.weight", p + ".bn3")
                 out = self._buf(N, oH, oW, outC)
-                self._add_conv(p + ".conv3", make_conv_desc(
-                    [_src_dense(t2, N, oH, oW, planes)], [(0, 0, 0, planes // 64)], dev(pack_conv(w), torch.float16),
-                    dev(b, torch.float32), outC, 1, (oW, oH, N), out, (outC, oW * outC, oH * oW * outC), residual=idt))
+                t2src = _src_dense(t2, N, oH, oW, planes)
+                if (p + ".downsample.0.weight") in sd:
+                    # block 0: relu(bn3(conv3(t2)) + bn_d(downsample(x))) is ONE contraction over [t2 | x]:
+                    # two 1x1 convs into the same output = two segments with concatenated weights and summed biases.
+                    # The identity branch is never written to / re-read from HBM.
+                    wd, bd = fold_bn(sd, p + ".downsample.0.weight", p + ".downsample.1")
+                    xsrc = _src_dense(cur, N, curH, curW, curC) if stride == 1 else _src_parity(cur, N, curH, curW, curC, 0, 0)
+                    wcat = torch.cat([pack_conv(w3), pack_conv(wd)], dim=1)
+                    self._add_conv(p + ".conv3+downsample", make_conv_desc(
+                        [t2src, xsrc], [(0, 0, 0, planes // 64), (1, 0, 0, curC // 64)], dev(wcat, torch.float16), dev(b3 + bd, torch.float32),
+                        outC, 1, (oW, oH, N), out, (outC, oW * outC, oH * oW * outC)))
+                else:
+                    # conv3 1x1 + bn3 + identity + relu
+                    self._add_conv(p + ".conv3", make_conv_desc(
+                        [t2src], [(0, 0, 0, planes // 64)], dev(pack_conv(w3), torch.float16), dev(b3, torch.float32), outC, 1,
+                        (oW, oH, N), out, (outC, oW * outC, oH * oW * outC), residual=cur))
                 self.feats[p] = (out, (N, oH, oW, outC))
                 cur, curC, curH, curW = out, outC, oH, oW
             encs.append((cur, curC, curH, curW))
