@@ -28,7 +28,6 @@ namespace rsb {
 static constexpr int kBlockM = 128;
 static constexpr int kBlockK = 64;  // fp16 elements = 128 bytes = one swizzle row
 static constexpr int kABytes = kBlockM * kBlockK * 2;
-static constexpr int kNumThreads = 192;
 
 struct alignas(64) ConvKParams {
     CUtensorMap tmA[RSB_MAX_SRCS];
@@ -68,11 +67,16 @@ struct ConvCfg {
     static constexpr int kChunkBytes = kBlockM * kChunk * 2;
     // every epilogue warp owns its 32 rows of the tile end to end (own staging slices, own TMA stores / residual
     // loads, no cross-warp barrier): kStoreBufs store slices and kResBufs residual slices of kWarpChunkBytes each
+    // A single warp per SM sub-partition is latency-bound (ncu: ~5 cycles per issued instruction), so wide tiles get
+    // two epilogue warps per TMEM lane quarter; the pair splits the tile's column chunks (even / odd).
+    static constexpr int kEpiWarps = (MODE == 0 && BLOCK_N >= 128) ? 8 : 4;
+    static constexpr int kChunkStride = kEpiWarps / 4;
+    static constexpr int kThreads = 64 + 32 * kEpiWarps;
     static constexpr int kWarpChunkBytes = 32 * kChunk * 2;
-    static constexpr int kStoreBufs = 2;
-    static constexpr int kResBufs = HAS_RES ? 4 : 0;
-    static constexpr int kEpiBytes = MODE == 0 ? (kStoreBufs + kResBufs) * kChunkBytes : 0;
-    static constexpr int kBarBytes = 384;
+    static constexpr int kStoreBufs = kEpiWarps == 8 ? 1 : 2;                 // per warp
+    static constexpr int kResBufs = HAS_RES ? (kEpiWarps == 8 ? 2 : 4) : 0;   // per warp
+    static constexpr int kEpiBytes = MODE == 0 ? (kStoreBufs + kResBufs) * kEpiWarps * kWarpChunkBytes : 0;
+    static constexpr int kBarBytes = 512;
     static constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
     static constexpr int kAvail = kMaxSmem - 1024 - kBarBytes - kEpiBytes;
     static constexpr int kStages = (kAvail / kStageBytes) > 8 ? 8 : (kAvail / kStageBytes);
@@ -102,7 +106,7 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int id) {
 }
 
 template <int BLOCK_N, int MODE, bool HAS_RES>
-__global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
+__global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
     using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES>;
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle atoms repeat every 1024 bytes: tile bases must be 1024-byte aligned
@@ -110,13 +114,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + Cfg::kStages * kABytes;
     uint8_t* smem_c = smem + Cfg::kStages * Cfg::kStageBytes;          // 2 store buffers (1024-aligned)
-    uint8_t* smem_r = smem_c + Cfg::kStoreBufs * Cfg::kChunkBytes;       // residual buffers (HAS_RES)
+    uint8_t* smem_r = smem_c + Cfg::kStoreBufs * Cfg::kEpiWarps * Cfg::kWarpChunkBytes;  // residual slices (HAS_RES)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
     uint64_t* empty_bar = full_bar + Cfg::kStages;
     uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint64_t* res_full_bar = tmem_empty_bar + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full_bar + 16);  // res_full_bar[warp q][buffer]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full_bar + 32);  // res_full_bar[epilogue warp][buffer]
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -130,9 +134,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty_bar[i], Cfg::kEpiWarps);  // one arrive per epilogue warp
         }
-        for (int i = 0; i < 16; ++i) mbar_init(&res_full_bar[i], 1);
+        for (int i = 0; i < 32; ++i) mbar_init(&res_full_bar[i], 1);
         if (MODE == 0) {
             for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmC[i]);
             if (HAS_RES) tma_prefetch_desc(&p.tmR);
@@ -144,6 +148,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap
+    // the tail of the previous kernel in the stream; from here on we touch memory it produced.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp_idx == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -218,27 +227,30 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
         // this warp's quarter of the tile box: rows [32q, 32q+32) -> box offset (qw, qh, qn) inside the TW x TH x TN tile
         const int qrow0 = q * 32;
         const int qw = qrow0 % p.TW, qh = (qrow0 / p.TW) % p.TH, qn = qrow0 / (p.TW * p.TH);
-        uint8_t* my_c = smem_c + q * Cfg::kWarpChunkBytes;   // + buf * kChunkBytes
-        uint8_t* my_r = smem_r + q * Cfg::kWarpChunkBytes;
-        uint64_t* my_res_bar = res_full_bar + q * 4;
+        const int ew = warp_idx - 2;                 // epilogue warp index
+        const int chunk0 = ew >> 2;                  // first column chunk of this warp; it takes every kChunkStride-th
+        uint8_t* my_c = smem_c + ew * Cfg::kStoreBufs * Cfg::kWarpChunkBytes;
+        uint8_t* my_r = smem_r + ew * (Cfg::kResBufs > 0 ? Cfg::kResBufs : 1) * Cfg::kWarpChunkBytes;
+        uint64_t* my_res_bar = res_full_bar + ew * 4;
         uint32_t wchunk = 0;          // running chunk counter of this warp (selects staging buffers)
         int res_tile = blockIdx.x;    // residual prefetch cursor (lane 0)
-        int res_chunk = 0;
+        int res_chunk = chunk0;
         auto issue_residual = [&](int rb) {
             if (res_tile < p.total_tiles) {
                 const TileCoord rt = decode_tile(p, res_tile);
                 mbar_expect_tx(&my_res_bar[rb], Cfg::kWarpChunkBytes);
-                tma_load_4d(my_r + rb * Cfg::kChunkBytes, &p.tmR, &my_res_bar[rb], rt.n_blk * BLOCK_N + res_chunk * Cfg::kChunk,
+                tma_load_4d(my_r + rb * Cfg::kWarpChunkBytes, &p.tmR, &my_res_bar[rb], rt.n_blk * BLOCK_N + res_chunk * Cfg::kChunk,
                             rt.w0 + qw, rt.h0 + qh, rt.n0 + qn);
-                if (++res_chunk == Cfg::kNumChunks) {
-                    res_chunk = 0;
+                res_chunk += Cfg::kChunkStride;
+                if (res_chunk >= Cfg::kNumChunks) {
+                    res_chunk = chunk0;
                     res_tile += gridDim.x;
                 }
             }
         };
         if (MODE == 0 && HAS_RES && lane == 0) {
 #pragma unroll 1
-            for (int i = 0; i < 4; ++i) issue_residual(i);
+            for (int i = 0; i < Cfg::kResBufs; ++i) issue_residual(i);
         }
         for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
             const TileCoord t = decode_tile(p, tile);
@@ -251,13 +263,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
             if constexpr (MODE == 0) {
                 const float* bptr = p.bias ? p.bias + t.n_blk * BLOCK_N : nullptr;
 #pragma unroll 1
-                for (int ck = 0; ck < Cfg::kNumChunks; ++ck, ++wchunk) {
-                    const int rb = wchunk & 3;
-                    uint8_t* cbuf = my_c + (wchunk & 1) * Cfg::kChunkBytes;
-                    const uint8_t* rbuf = my_r + rb * Cfg::kChunkBytes;
-                    if (HAS_RES) mbar_wait(&my_res_bar[rb], (wchunk >> 2) & 1);
-                    // the TMA store this warp issued two chunks ago (same slice) must have finished reading shared memory
-                    if (lane == 0) tma_store_wait_read<1>();
+                for (int ck = chunk0; ck < Cfg::kNumChunks; ck += Cfg::kChunkStride, ++wchunk) {
+                    constexpr int kRB = Cfg::kResBufs > 0 ? Cfg::kResBufs : 1;
+                    const int rb = wchunk % kRB;
+                    uint8_t* cbuf = my_c + (wchunk % Cfg::kStoreBufs) * Cfg::kWarpChunkBytes;
+                    const uint8_t* rbuf = my_r + rb * Cfg::kWarpChunkBytes;
+                    if (HAS_RES) mbar_wait(&my_res_bar[rb], (wchunk / kRB) & 1);
+                    // the TMA store this warp issued kStoreBufs chunks ago (same slice) must have finished reading shared memory
+                    if (lane == 0) tma_store_wait_read<Cfg::kStoreBufs - 1>();
                     __syncwarp();
 #pragma unroll
                     for (int half = 0; half < Cfg::kChunk / 32; ++half) {
@@ -265,7 +278,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
                         uint32_t r[32];
                         tmem_ld_32x32(taddr + c, r);
                         tmem_ld_wait();
-                        if (ck == Cfg::kNumChunks - 1 && half == Cfg::kChunk / 32 - 1) {
+                        if (ck + Cfg::kChunkStride >= Cfg::kNumChunks && half == Cfg::kChunk / 32 - 1) {
                             // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
                             tc_fence_before();
                             __syncwarp();
@@ -319,7 +332,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
                     if (lane == 0) {
                         tma_store_4d(&p.tmC[t.phase], cbuf, t.n_blk * BLOCK_N + ck * Cfg::kChunk, t.w0 + qw, t.h0 + qh, t.n0 + qn);
                         tma_store_commit();
-                        // residual slice `rb` has been consumed by the whole warp: refill it four chunks ahead
+                        // residual slice `rb` has been consumed by the whole warp: refill it kResBufs chunks ahead
                         if (HAS_RES) issue_residual(rb);
                     }
                 }
@@ -490,8 +503,17 @@ static int launch_conv(const rsb_conv_plan* plan, cudaStream_t stream) {
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv)");
         attr_set = true;
     }
-    kern<<<plan->grid, kNumThreads, Cfg::kSmemBytes, stream>>>(plan->kp);
-    cudaError_t e = cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan->grid);
+    cfg.blockDim = dim3(Cfg::kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, plan->kp);
     if (e != cudaSuccess) return set_cuda_error(e, "conv_tc_kernel launch");
     return RSB_OK;
 }
