@@ -159,6 +159,14 @@ int rsb_metrics_count(const float* logits, const int64_t* targets, int64_t* coun
 int rsb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float b1,
                   float b2, float eps, int32_t step, void* stream);
 
+/* Hardware-behaviour probe for tcgen05 shared-memory descriptors (tests / bring-up only; see csrc/rsb_debug.cu).
+ * mode 0: D[128][64] = A[row_offset + i][0:64] . B[n][0:64]^T with a K-major operand window starting `row_offset` rows
+ *         into a TMA-written box of `a_rows` rows (descriptor base_offset as given).
+ * mode 1: D[m][n] = sum_k A[k][m] * B[n][k] with A given as [64 k][128 m] (MN-major operand), descriptor LBO/SBO as given. */
+int rsb_debug_umma(const void* a, int32_t a_total_rows, int32_t a_cols, const void* b, float* out, int32_t mode, int32_t a_rows,
+                   int32_t a_blocks, int32_t row_offset, int32_t base_offset, int32_t lbo, int32_t sbo, int32_t k_step_bytes,
+                   void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,6 +89,7 @@ SIGNATURES = {
     "rsb_lovasz": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "rsb_metrics_count": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rsb_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp]),
+    "rsb_debug_umma": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp] + [_i32] * 8 + [_vp]),
 }
 
 _lib = None

@@ -1,0 +1,131 @@
+// Hardware-behaviour probes (tests / bring-up only, never on the product path).
+//
+// rsb_debug_umma answers two questions about tcgen05 shared-memory descriptors on sm_100a that the public
+// guides leave open and that decide the design of the next kernels:
+//   (1) K-major SWIZZLE_128B operand whose start address is NOT 1024-byte aligned (start = tile + r*128 B):
+//       does a row-shifted window of a larger TMA-written box work, and which `base_offset` does it need?
+//       (line-buffer convolution: one halo row in shared memory serves all three horizontal taps)
+//   (2) MN-major SWIZZLE_128B A operand (rows = K index, 64 M-elements contiguous per row), as produced by a TMA
+//       load of an NHWC activation tile: which LBO / SBO encode it? (wgrad contracts over pixels)
+
+#include <cuda_fp16.h>
+
+#include "../../include/rsb200.h"
+#include "rsb_host.h"
+#include "rsb_ptx.cuh"
+
+namespace rsb {
+
+struct DebugParams {
+    CUtensorMap tmA;  // 2D [rows][64] fp16, box {64, a_rows}
+    CUtensorMap tmB;  // 2D [64 n][64 k] fp16, box {64, 64}
+    float* out;       // [128][64] fp32
+    int a_rows;       // rows loaded for A (<= 256)
+    int a_blocks;     // number of A boxes loaded back to back (MN-major: 2 blocks of 64 M columns)
+    int mode;         // 0: K-major shifted window; 1: MN-major A
+    int row_offset;   // mode 0: window start row
+    int base_offset;  // value for descriptor bits [49,52)
+    int lbo, sbo;     // mode 1: descriptor LBO / SBO in bytes
+    int k_step_bytes; // mode 1: start-address advance per K=16 MMA
+};
+
+__global__ void __launch_bounds__(128, 1) debug_umma_kernel(const __grid_constant__ DebugParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sa = smem;                  // up to 2 x 256 rows x 128 B = 64 KB
+    uint8_t* sb = smem + 65536;          // 64 x 128 B
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 65536 + 8192);
+    uint64_t* mma_bar = bar + 1;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_init(mma_bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc<64>(tmem_ptr);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, p.a_blocks * p.a_rows * 128 + 64 * 128);
+        for (int b = 0; b < p.a_blocks; ++b) tma_load_2d(sa + b * p.a_rows * 128, &p.tmA, bar, b * 64, 0);
+        tma_load_2d(sb, &p.tmB, bar, 0, 0);
+        mbar_wait(bar, 0);
+        tc_fence_after();
+        const uint64_t db = make_sw128_kmajor_desc(smem_u32(sb));
+        for (int k = 0; k < 4; ++k) {
+            uint64_t da;
+            uint32_t idesc = make_idesc_f16(128, 64);
+            if (p.mode == 0) {
+                da = make_sw128_kmajor_desc(smem_u32(sa) + p.row_offset * 128) + 2 * k;
+                da |= static_cast<uint64_t>(p.base_offset & 7) << 49;
+            } else {
+                const uint32_t addr = smem_u32(sa) + k * p.k_step_bytes;
+                da = static_cast<uint64_t>((addr & 0x3FFFF) >> 4);
+                da |= static_cast<uint64_t>((p.lbo >> 4) & 0x3FFF) << 16;
+                da |= static_cast<uint64_t>((p.sbo >> 4) & 0x3FFF) << 32;
+                da |= static_cast<uint64_t>(1) << 46;
+                da |= static_cast<uint64_t>(2) << 61;
+                idesc |= (1u << 15);  // A is MN-major
+            }
+            umma_f16(tmem, da, db + 2 * k, idesc, k > 0 ? 1u : 0u);
+        }
+        umma_commit(mma_bar);
+    }
+    __syncthreads();
+    mbar_wait(mma_bar, 0);
+    tc_fence_after();
+    for (int c = 0; c < 64; c += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16) + c, r);
+        tmem_ld_wait();
+        for (int j = 0; j < 32; ++j) p.out[(warp * 32 + lane) * 64 + c + j] = __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+}  // namespace rsb
+
+using namespace rsb;
+
+extern "C" int rsb_debug_umma(const void* a, int32_t a_total_rows, int32_t a_cols, const void* b, float* out, int32_t mode,
+                              int32_t a_rows, int32_t a_blocks, int32_t row_offset, int32_t base_offset, int32_t lbo, int32_t sbo,
+                              int32_t k_step_bytes, void* stream) {
+    if (!a || !b || !out || a_rows < 1 || a_rows > 256 || a_blocks < 1 || a_blocks > 2) return set_error(RSB_E_INVALID, "debug_umma: bad arguments");
+    int rc = rsb_device_ok();
+    if (rc) return rc;
+    DebugParams p = {};
+    {
+        const uint64_t dims[2] = {(uint64_t)a_cols, (uint64_t)a_total_rows};
+        const uint64_t strides[1] = {(uint64_t)a_cols * 2};
+        const uint32_t box[2] = {64, (uint32_t)a_rows};
+        rc = encode_tiled_f16(&p.tmA, 2, a, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        const uint64_t dims[2] = {64, 64};
+        const uint64_t strides[1] = {128};
+        const uint32_t box[2] = {64, 64};
+        rc = encode_tiled_f16(&p.tmB, 2, b, dims, strides, box);
+        if (rc) return rc;
+    }
+    p.out = out;
+    p.a_rows = a_rows;
+    p.a_blocks = a_blocks;
+    p.mode = mode;
+    p.row_offset = row_offset;
+    p.base_offset = base_offset;
+    p.lbo = lbo;
+    p.sbo = sbo;
+    p.k_step_bytes = k_step_bytes;
+    const int smem = 65536 + 8192 + 64 + 1024;
+    cudaError_t e = cudaFuncSetAttribute(debug_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return set_cuda_error(e, "debug_umma attr");
+    debug_umma_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "debug_umma launch");
+}
