@@ -27,7 +27,7 @@ extern "C" {
 #define RSB_E_CUDA -2      /* CUDA runtime or driver error */
 #define RSB_E_NODEVICE -3  /* no sm_100 device / driver entry point missing */
 
-#define RSB_MAX_SEGS 12
+#define RSB_MAX_SEGS 16
 #define RSB_MAX_SRCS 4
 
 int rsb_version(void);
@@ -158,6 +158,50 @@ int rsb_metrics_count(const float* logits, const int64_t* targets, int64_t* coun
  * betas (b1,b2), eps, no weight decay, no amsgrad; `step` is the 1-based step count for bias correction. */
 int rsb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float b1,
                   float b2, float eps, int32_t step, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Training path (robosat/tools/train.py:163-201: net.train() forward, loss.backward()). Activations and activation
+ * gradients are NHWC fp16 [M = N*H*W][C]; gradients carry the caller's loss scale; parameter gradients are fp32, unscaled.
+ */
+/* train-mode BatchNorm2d (torchvision resnet50 inside unet.py:122-130): batch sums -> statistics / running-stat update -> apply.
+ * sums: 2*C doubles of scratch. finalize writes mean, invstd, scale = gamma*invstd, shift = beta - mean*scale and updates
+ * running_mean / running_var (unbiased, momentum) / num_batches_tracked when those pointers are non-NULL. */
+int rsb_bn_stats(const void* z, double* sums, int64_t M, int32_t C, void* stream);
+int rsb_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                    int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int32_t C, int64_t M, float eps,
+                    float momentum, void* stream);
+/* y = relu?(z*scale + shift (+ residual)) */
+int rsb_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y, int64_t M, int32_t C,
+                 int32_t relu, void* stream);
+/* autograd of relu(bn(z) (+ identity)): g = dy * (y > 0) (y NULL: no mask); dz = gamma*invstd*(g - mean(g) - zhat*mean(g*zhat));
+ * g_out (optional) receives g = the gradient of the identity branch; dgamma/dbeta fp32 multiplied by inv_loss_scale. */
+int rsb_bn_backward(const void* dy, const void* y, const void* z, const float* mean, const float* invstd, const float* gamma,
+                    double* sums, void* dz, void* g_out, float* dgamma, float* dbeta, float inv_loss_scale, int64_t M, int32_t C,
+                    void* stream);
+/* out = (a (+ b)) * (y > 0): ReLU backward with optional gradient fan-in (skip connections); y NULL: plain sum */
+int rsb_relu_backward(const void* a, const void* b, const void* y, void* out, int64_t n, void* stream);
+/* autograd of max_pool2d (unet.py:125, :132) on NHWC fp16: first maximum of every window receives its gradient */
+int rsb_maxpool_backward(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t s,
+                         int32_t p, void* stream);
+/* final 1x1 conv 32 -> classes with bias (unet.py:141) as its own step in training: fp32 NCHW logits from NHWC fp16 dec5 */
+int rsb_final_forward(const void* y5, const float* w, const float* b, float* logits, int32_t N, int32_t HW, int32_t classes,
+                      void* stream);
+/* its autograd: dy5 (fp16, times loss_scale), dW [classes][32], db [classes] (fp32, unscaled). acc: classes*32 + 8 doubles. */
+int rsb_final_backward(const float* dlogits, const void* y5, const float* w, void* dy5, double* acc, float* dw, float* db,
+                       float loss_scale, int32_t N, int32_t HW, int32_t classes, void* stream);
+/* fp32 OIHW master weights -> fp16 packed operand matrix: dst[i] = half(sum of src[map4[4i..4i+3]] (entries < 0 skipped)) */
+int rsb_pack_weights(const float* src, const int32_t* map4, void* dst, int64_t n, void* stream);
+/* packed fp32 gradient -> OIHW fp32 gradient: grad[map4[4i+j]] += packed_grad[i] * mul (the transpose of rsb_pack_weights) */
+int rsb_unpack_grads(const float* packed_grad, const int32_t* map4, float* grad, int64_t n, float mul, void* stream);
+
+/* Weight gradient of the convolution described by `fwd` (same sources / segments / phases / tile space), on tensor cores:
+ *   dw_packed[phase*Cout + co][k] = sum_pixels dy_phase[pixel][co] * x_segment(k)[pixel + (dh,dw)][k % 64-block]   (fp32)
+ * i.e. the gradient in the forward kernel's packed weight layout (rsb_unpack_grads folds it back to OIHW).
+ * dy is addressed like fwd->out (same pitches / phase strides). Replaces autograd's conv weight gradients (train.py:186). */
+typedef struct rsb_wgrad_plan rsb_wgrad_plan;
+int rsb_wgrad_plan_create(const rsb_conv_desc* fwd, const void* dy, float* dw_packed, rsb_wgrad_plan** out_plan);
+void rsb_wgrad_plan_destroy(rsb_wgrad_plan* plan);
+int rsb_wgrad_run(const rsb_wgrad_plan* plan, void* stream);
 
 /* Hardware-behaviour probe for tcgen05 shared-memory descriptors (tests / bring-up only; see csrc/rsb_debug.cu).
  * mode 0: D[128][64] = A[row_offset + i][0:64] . B[n][0:64]^T with a K-major operand window starting `row_offset` rows

@@ -34,8 +34,15 @@ def _strip(sd):
     return dict(sd)
 
 
+_TRAIN = [False]
+
+
 def _bn(x, sd, p):
     # eval-mode BatchNorm2d: (x - running_mean) / sqrt(running_var + eps) * weight + bias
+    # train mode (net.train(), train.py:168): batch statistics, running stats updated in place with momentum 0.1
+    if _TRAIN[0]:
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                            training=True, momentum=0.1, eps=BN_EPS)
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
                         training=False, eps=BN_EPS)
 
@@ -53,6 +60,16 @@ def _bottleneck(x, sd, p, stride, conv):
 
 def _conv(x, w, b, stride, padding):
     return F.conv2d(x, w, b, stride=stride, padding=padding)
+
+
+def unet_forward_train(state_dict, x, return_features=False):
+    """train-mode forward (batch-statistics BatchNorm; `running_mean` / `running_var` of `state_dict` are updated in place,
+    like net.train() + net(images) at train.py:168,180). Tensors with requires_grad=True give autograd gradients."""
+    _TRAIN[0] = True
+    try:
+        return unet_forward(state_dict, x, return_features=return_features)
+    finally:
+        _TRAIN[0] = False
 
 
 def unet_forward(state_dict, x, conv=_conv, return_features=False):

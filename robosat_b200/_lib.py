@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librsb200.so")
 
-RSB_MAX_SEGS = 12
+RSB_MAX_SEGS = 16
 RSB_MAX_SRCS = 4
 
 
@@ -89,6 +89,19 @@ SIGNATURES = {
     "rsb_lovasz": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "rsb_metrics_count": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rsb_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp]),
+    "rsb_bn_stats": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    "rsb_bn_finalize": (ctypes.c_int, [_vp] * 10 + [_i32, _i64, _f32, _f32, _vp]),
+    "rsb_bn_apply": (ctypes.c_int, [_vp] * 5 + [_i64, _i32, _i32, _vp]),
+    "rsb_bn_backward": (ctypes.c_int, [_vp] * 11 + [_f32, _i64, _i32, _vp]),
+    "rsb_relu_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
+    "rsb_maxpool_backward": (ctypes.c_int, [_vp, _vp, _vp] + [_i32] * 7 + [_vp]),
+    "rsb_final_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "rsb_final_backward": (ctypes.c_int, [_vp] * 7 + [_f32, _i32, _i32, _i32, _vp]),
+    "rsb_pack_weights": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "rsb_unpack_grads": (ctypes.c_int, [_vp, _vp, _vp, _i64, _f32, _vp]),
+    "rsb_wgrad_plan_create": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, ctypes.POINTER(_vp)]),
+    "rsb_wgrad_plan_destroy": (None, [_vp]),
+    "rsb_wgrad_run": (ctypes.c_int, [_vp, _vp]),
     "rsb_debug_umma": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp] + [_i32] * 8 + [_vp]),
 }
 

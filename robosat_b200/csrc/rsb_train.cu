@@ -1,0 +1,497 @@
+// Training-path helper kernels around the tensor-core convolutions (HBM-bound elementwise / reduction work):
+// train-mode BatchNorm (batch statistics, running-stat update, apply, backward), ReLU / max-pool / final-1x1
+// backward, and the fp32-master <-> fp16-packed weight conversions run every optimiser step.
+//
+// Reference semantics: nn.BatchNorm2d in training mode (torchvision resnet50 inside robosat/unet.py:122-130):
+// biased batch variance for normalisation, running_var updated with the unbiased estimate, momentum 0.1, eps 1e-5;
+// autograd of conv / relu / max_pool2d / interpolate / cat triggered by loss.backward() (robosat/tools/train.py:186).
+// All activations and activation gradients are NHWC fp16 (gradients carry the loss scale), reductions run in
+// fp32 per thread and fp64 across blocks, parameter gradients are fp32.
+
+#include <cuda_fp16.h>
+
+#include "../../include/rsb200.h"
+#include "rsb_host.h"
+
+namespace rsb {
+
+static inline unsigned tr_blocks(int64_t total, int block, int cap = 148 * 8) {
+    int64_t b = (total + block - 1) / block;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return static_cast<unsigned>(b);
+}
+
+__device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
+    const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        v[2 * i] = f.x;
+        v[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
+    uint4 q;
+    __half2* h = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-channel sums over M rows of an NHWC fp16 tensor [M][C]; up to two fused reductions:
+//   KIND 0 (forward stats)   : s0 += z            s1 += z*z
+//   KIND 1 (BN backward)     : g = dy * (y > 0 or no mask); s0 += g ; s1 += g * (z - mean) * invstd
+// 256 threads: C/8 threads cover one row (8 channels = 16 bytes each), 256/(C/8) rows per iteration.
+template <int KIND>
+__global__ void channel_reduce_kernel(const __half* __restrict__ a, const __half* __restrict__ y, const __half* __restrict__ z,
+                                      const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ s0,
+                                      double* __restrict__ s1, int64_t M, int C) {
+    __shared__ float sh0[256 * 8];
+    __shared__ float sh1[256 * 8];
+    const int tpr = C / 8;
+    const int rows_per_iter = 256 / tpr;
+    const int col = (threadIdx.x % tpr) * 8;
+    const int rsub = threadIdx.x / tpr;
+    float acc0[8], acc1[8], mu[8], is[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        acc0[i] = acc1[i] = 0.f;
+        mu[i] = (KIND == 1) ? mean[col + i] : 0.f;
+        is[i] = (KIND == 1) ? invstd[col + i] : 0.f;
+    }
+    for (int64_t r = static_cast<int64_t>(blockIdx.x) * rows_per_iter + rsub; r < M; r += static_cast<int64_t>(gridDim.x) * rows_per_iter) {
+        float v[8];
+        load8(a + r * C + col, v);
+        if (KIND == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                acc0[i] += v[i];
+                acc1[i] += v[i] * v[i];
+            }
+        } else {
+            float zz[8];
+            load8(z + r * C + col, zz);
+            if (y) {
+                float yy[8];
+                load8(y + r * C + col, yy);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = yy[i] > 0.f ? v[i] : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                acc0[i] += v[i];
+                acc1[i] += v[i] * (zz[i] - mu[i]) * is[i];
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        sh0[threadIdx.x * 8 + i] = acc0[i];
+        sh1[threadIdx.x * 8 + i] = acc1[i];
+    }
+    __syncthreads();
+    // threads 0..C-1 (at most 2048 channels -> loop) fold the row-groups
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int t0 = c / 8, e = c % 8;
+        float a0 = 0.f, a1 = 0.f;
+        for (int g = 0; g < rows_per_iter; ++g) {
+            a0 += sh0[(g * tpr + t0) * 8 + e];
+            a1 += sh1[(g * tpr + t0) * 8 + e];
+        }
+        atomicAdd(&s0[c], static_cast<double>(a0));
+        atomicAdd(&s1[c], static_cast<double>(a1));
+    }
+}
+
+// mean / invstd / folded scale+shift from the batch sums, running-stat update (momentum, unbiased variance)
+__global__ void bn_finalize_kernel(const double* __restrict__ s0, const double* __restrict__ s1, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   int64_t* __restrict__ num_batches, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   float* __restrict__ scale_out, float* __restrict__ shift_out, int C, double M, float eps, float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches) *num_batches += 1;
+    if (c >= C) return;
+    const double mean = s0[c] / M;
+    double var = s1[c] / M - mean * mean;
+    if (var < 0) var = 0;
+    const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    const float sc = gamma[c] * invstd;
+    mean_out[c] = static_cast<float>(mean);
+    invstd_out[c] = invstd;
+    scale_out[c] = sc;
+    shift_out[c] = beta[c] - static_cast<float>(mean) * sc;
+    if (running_mean) {
+        const double unbiased = M > 1 ? var * M / (M - 1.0) : var;
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    }
+}
+
+// y = relu?(z * scale + shift (+ res))
+__global__ void bn_apply_kernel(const __half* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
+                                const __half* __restrict__ res, __half* __restrict__ y, int64_t M, int C, int relu) {
+    const int C8 = C / 8;
+    const int64_t total = M * C8;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int col = static_cast<int>(i % C8) * 8;
+        float v[8], r[8];
+        load8(z + i * 8, v);
+        if (res) load8(res + i * 8, r);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float o = v[e] * scale[col + e] + shift[col + e];
+            if (res) o += r[e];
+            v[e] = relu ? fmaxf(o, 0.f) : o;
+        }
+        store8(y + i * 8, v);
+    }
+}
+
+// dz = gamma*invstd * (g - sum_g/M - zhat * sum_gz/M), g = dy * (y > 0); optionally also writes g (identity-branch gradient)
+__global__ void bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, const __half* __restrict__ z,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                    const double* __restrict__ s0, const double* __restrict__ s1, __half* __restrict__ dz,
+                                    __half* __restrict__ g_out, float* __restrict__ dgamma, float* __restrict__ dbeta, float inv_scale,
+                                    int64_t M, int C) {
+    const int C8 = C / 8;
+    const int64_t total = M * C8;
+    const float invM = 1.0f / static_cast<float>(M);
+    if (blockIdx.x == 0) {
+        // parameter gradients (unscaled fp32); written once
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            dgamma[c] = static_cast<float>(s1[c]) * inv_scale;
+            dbeta[c] = static_cast<float>(s0[c]) * inv_scale;
+        }
+    }
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int col = static_cast<int>(i % C8) * 8;
+        float g[8], zz[8];
+        load8(dy + i * 8, g);
+        load8(z + i * 8, zz);
+        if (y) {
+            float yy[8];
+            load8(y + i * 8, yy);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] = yy[e] > 0.f ? g[e] : 0.f;
+        }
+        if (g_out) store8(g_out + i * 8, g);
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int c = col + e;
+            const float zhat = (zz[e] - mean[c]) * invstd[c];
+            o[e] = gamma[c] * invstd[c] * (g[e] - static_cast<float>(s0[c]) * invM - zhat * static_cast<float>(s1[c]) * invM);
+        }
+        store8(dz + i * 8, o);
+    }
+}
+
+// out = a * (y > 0) (+ b): ReLU backward with an optional second gradient stream (skip connection fan-in)
+__global__ void relu_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__ b, const __half* __restrict__ y,
+                                __half* __restrict__ out, int64_t total8) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float g[8], yy[8];
+        load8(a + i * 8, g);
+        if (b) {
+            float h[8];
+            load8(b + i * 8, h);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] += h[e];
+        }
+        if (y) {
+            load8(y + i * 8, yy);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] = yy[e] > 0.f ? g[e] : 0.f;
+        }
+        store8(out + i * 8, g);
+    }
+}
+
+// max-pool backward: dx[h][w] = sum over the windows that contain (h, w) and whose argmax is (h, w) (first max wins, like ATen)
+__global__ void maxpool_bwd_kernel(const __half* __restrict__ x, const __half* __restrict__ dy, __half* __restrict__ dx, int N, int H, int W,
+                                   int C, int k, int s, int p, int OH, int OW) {
+    const int C8 = C / 8;
+    const int64_t total = static_cast<int64_t>(N) * H * W * C8;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int c8 = static_cast<int>(i % C8);
+        int64_t r = i / C8;
+        const int w = static_cast<int>(r % W);
+        r /= W;
+        const int h = static_cast<int>(r % H);
+        const int n = static_cast<int>(r / H);
+        float xv[8], acc[8];
+        load8(x + i * 8, xv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        // windows (oh, ow) covering this input pixel
+        const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
+        const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
+        for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+            for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+                // is (h, w) the first maximum of window (oh, ow)?
+                bool first[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) first[e] = true;
+                for (int dyy = 0; dyy < k; ++dyy) {
+                    const int hh = oh * s - p + dyy;
+                    if (hh < 0 || hh >= H) continue;
+                    for (int dxx = 0; dxx < k; ++dxx) {
+                        const int ww = ow * s - p + dxx;
+                        if (ww < 0 || ww >= W || (hh == h && ww == w)) continue;
+                        float o[8];
+                        load8(x + ((static_cast<int64_t>(n) * H + hh) * W + ww) * C + c8 * 8, o);
+                        const bool before = (hh < h) || (hh == h && ww < w);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            if (o[e] > xv[e] || (before && o[e] == xv[e])) first[e] = false;
+                        }
+                    }
+                }
+                float g[8];
+                load8(dy + ((static_cast<int64_t>(n) * OH + oh) * OW + ow) * C + c8 * 8, g);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] += first[e] ? g[e] : 0.f;
+            }
+        }
+        store8(dx + i * 8, acc);
+    }
+}
+
+// final 1x1 conv (32 -> C classes, with bias) forward: logits fp32 NCHW from NHWC fp16 activations (unet.py:141)
+__global__ void final_fwd_kernel(const __half* __restrict__ y5, const float* __restrict__ w, const float* __restrict__ b,
+                                 float* __restrict__ logits, int64_t P, int64_t HW, int classes) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < P; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t[8];
+            load8(y5 + i * 32 + j * 8, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[j * 8 + e] = t[e];
+        }
+        const int64_t n = i / HW, pix = i % HW;
+        for (int k = 0; k < classes; ++k) {
+            float s = b[k];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) s = fmaf(w[k * 32 + c], v[c], s);
+            logits[(n * classes + k) * HW + pix] = s;
+        }
+    }
+}
+
+// final 1x1 backward, input gradient: dy5[p][c] = loss_scale * sum_k dlogits[p][k] * w[k][c]  (fp16; dec5's ReLU mask is applied later)
+__global__ void final_bwd_dx_kernel(const float* __restrict__ dlogits, const float* __restrict__ w, __half* __restrict__ dy5,
+                                    float loss_scale, int64_t P, int64_t HW, int classes) {
+    __shared__ float sw[8 * 32];
+    for (int i = threadIdx.x; i < classes * 32; i += blockDim.x) sw[i] = w[i];
+    __syncthreads();
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < P; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t n = i / HW, pix = i % HW;
+        float d[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) d[c] = 0.f;
+        for (int k = 0; k < classes; ++k) {
+            const float g = dlogits[(n * classes + k) * HW + pix] * loss_scale;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) d[c] = fmaf(g, sw[k * 32 + c], d[c]);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t[e] = d[j * 8 + e];
+            store8(dy5 + i * 32 + j * 8, t);
+        }
+    }
+}
+
+// final 1x1 backward, parameter gradients for ONE class k: dW[k][c] = sum_p dlogits[p][k] * y5[p][c], db[k] = sum_p dlogits[p][k]
+__global__ void final_bwd_dw_kernel(const float* __restrict__ dlogits, const __half* __restrict__ y5, double* __restrict__ dw_acc,
+                                    double* __restrict__ db_acc, int k, int64_t P, int64_t HW, int classes) {
+    float ldw[32];
+    float ldb = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) ldw[c] = 0.f;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < P; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t n = i / HW, pix = i % HW;
+        const float g = dlogits[(n * classes + k) * HW + pix];
+        ldb += g;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t[8];
+            load8(y5 + i * 32 + j * 8, t);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ldw[j * 8 + e] = fmaf(g, t[e], ldw[j * 8 + e]);
+        }
+    }
+    // warp reduce, then one fp64 atomic per warp and channel
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        float v = ldw[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&dw_acc[k * 32 + c], static_cast<double>(v));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ldb += __shfl_xor_sync(0xffffffffu, ldb, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&db_acc[k], static_cast<double>(ldb));
+}
+
+__global__ void f64_to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int n, float mul) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = static_cast<float>(src[i]) * mul;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 master weights -> fp16 packed operand matrices, and packed fp32 gradients -> fp32 OIHW gradients.
+// A packed matrix is [rows][K]; `map` gives, for every packed element, up to 4 source indices into the OIHW tensor
+// (-1 = none): forward packs gather one element, the upsample phases sum up to four taps. The same map drives the
+// gradient scatter (packed gradient element added to each of its sources).
+__global__ void pack_gather_kernel(const float* __restrict__ src, const int32_t* __restrict__ map, __half* __restrict__ dst, int64_t n) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int4 m = __ldg(reinterpret_cast<const int4*>(map) + i);
+        float v = 0.f;
+        if (m.x >= 0) v += src[m.x];
+        if (m.y >= 0) v += src[m.y];
+        if (m.z >= 0) v += src[m.z];
+        if (m.w >= 0) v += src[m.w];
+        dst[i] = __float2half_rn(v);
+    }
+}
+
+__global__ void unpack_scatter_kernel(const float* __restrict__ packed_grad, const int32_t* __restrict__ map, float* __restrict__ grad,
+                                      int64_t n, float mul) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int4 m = __ldg(reinterpret_cast<const int4*>(map) + i);
+        const float g = packed_grad[i] * mul;
+        if (m.x >= 0) atomicAdd(&grad[m.x], g);
+        if (m.y >= 0) atomicAdd(&grad[m.y], g);
+        if (m.z >= 0) atomicAdd(&grad[m.z], g);
+        if (m.w >= 0) atomicAdd(&grad[m.w], g);
+    }
+}
+
+}  // namespace rsb
+
+using namespace rsb;
+
+#define RSB_LAUNCH_CHECK(what)                                            \
+    do {                                                                  \
+        cudaError_t e__ = cudaGetLastError();                             \
+        if (e__ != cudaSuccess) return set_cuda_error(e__, what);         \
+    } while (0)
+
+static bool bad_c(int C) { return C <= 0 || (C % 8) || (C > 2048) || (256 % (C / 8 > 256 ? 256 : C / 8)); }
+
+extern "C" int rsb_bn_stats(const void* z, double* sums, int64_t M, int32_t C, void* stream) {
+    if (!z || !sums || M <= 0 || bad_c(C) || C < 64) return set_error(RSB_E_INVALID, "bn_stats: bad arguments (C in 64..2048, power of two)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    if (e != cudaSuccess) return set_cuda_error(e, "bn_stats memset");
+    const int rows_per_iter = 256 / (C / 8);
+    channel_reduce_kernel<0><<<tr_blocks((M + rows_per_iter - 1) / rows_per_iter, 1, 148 * 4), 256, 0, st>>>(
+        static_cast<const __half*>(z), nullptr, nullptr, nullptr, nullptr, sums, sums + C, M, C);
+    RSB_LAUNCH_CHECK("bn_stats launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                               int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int32_t C, int64_t M,
+                               float eps, float momentum, void* stream) {
+    if (!sums || !gamma || !beta || !mean || !invstd || !scale || !shift || C <= 0 || M <= 0) return set_error(RSB_E_INVALID, "bn_finalize: bad arguments");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, sums + C, gamma, beta, running_mean, running_var,
+                                                                                   num_batches, mean, invstd, scale, shift, C,
+                                                                                   static_cast<double>(M), eps, momentum);
+    RSB_LAUNCH_CHECK("bn_finalize launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y, int64_t M, int32_t C,
+                            int32_t relu, void* stream) {
+    if (!z || !scale || !shift || !y || M <= 0 || C <= 0 || (C % 8)) return set_error(RSB_E_INVALID, "bn_apply: bad arguments");
+    bn_apply_kernel<<<tr_blocks(M * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(z), scale, shift, static_cast<const __half*>(residual), static_cast<__half*>(y), M, C, relu);
+    RSB_LAUNCH_CHECK("bn_apply launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_bn_backward(const void* dy, const void* y, const void* z, const float* mean, const float* invstd, const float* gamma,
+                               double* sums, void* dz, void* g_out, float* dgamma, float* dbeta, float inv_loss_scale, int64_t M,
+                               int32_t C, void* stream) {
+    if (!dy || !z || !mean || !invstd || !gamma || !sums || !dz || !dgamma || !dbeta || M <= 0 || bad_c(C) || C < 64)
+        return set_error(RSB_E_INVALID, "bn_backward: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    if (e != cudaSuccess) return set_cuda_error(e, "bn_backward memset");
+    const int rows_per_iter = 256 / (C / 8);
+    channel_reduce_kernel<1><<<tr_blocks((M + rows_per_iter - 1) / rows_per_iter, 1, 148 * 4), 256, 0, st>>>(
+        static_cast<const __half*>(dy), static_cast<const __half*>(y), static_cast<const __half*>(z), mean, invstd, sums, sums + C, M, C);
+    bn_bwd_apply_kernel<<<tr_blocks(M * (C / 8), 256), 256, 0, st>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
+                                                                   static_cast<const __half*>(z), mean, invstd, gamma, sums, sums + C,
+                                                                   static_cast<__half*>(dz), static_cast<__half*>(g_out), dgamma, dbeta,
+                                                                   inv_loss_scale, M, C);
+    RSB_LAUNCH_CHECK("bn_backward launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_relu_backward(const void* a, const void* b, const void* y, void* out, int64_t n, void* stream) {
+    if (!a || !out || n <= 0 || (n % 8)) return set_error(RSB_E_INVALID, "relu_backward: bad arguments");
+    relu_bwd_kernel<<<tr_blocks(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<const __half*>(y), static_cast<__half*>(out), n / 8);
+    RSB_LAUNCH_CHECK("relu_backward launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_maxpool_backward(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
+                                    int32_t s, int32_t p, void* stream) {
+    if (!x || !dy || !dx || N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 8) || k < 1 || s < 1 || p < 0)
+        return set_error(RSB_E_INVALID, "maxpool_backward: bad arguments");
+    const int OH = (H + 2 * p - k) / s + 1, OW = (W + 2 * p - k) / s + 1;
+    maxpool_bwd_kernel<<<tr_blocks(static_cast<int64_t>(N) * H * W * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x), static_cast<const __half*>(dy), static_cast<__half*>(dx), N, H, W, C, k, s, p, OH, OW);
+    RSB_LAUNCH_CHECK("maxpool_backward launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_final_forward(const void* y5, const float* w, const float* b, float* logits, int32_t N, int32_t HW, int32_t classes,
+                                 void* stream) {
+    if (!y5 || !w || !b || !logits || N <= 0 || HW <= 0 || classes < 1 || classes > 8) return set_error(RSB_E_INVALID, "final_forward: bad arguments");
+    const int64_t P = static_cast<int64_t>(N) * HW;
+    final_fwd_kernel<<<tr_blocks(P, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __half*>(y5), w, b, logits, P, HW, classes);
+    RSB_LAUNCH_CHECK("final_forward launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_final_backward(const float* dlogits, const void* y5, const float* w, void* dy5, double* acc, float* dw, float* db,
+                                  float loss_scale, int32_t N, int32_t HW, int32_t classes, void* stream) {
+    if (!dlogits || !y5 || !w || !dy5 || !acc || !dw || !db || N <= 0 || HW <= 0 || classes < 1 || classes > 8)
+        return set_error(RSB_E_INVALID, "final_backward: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(acc, 0, sizeof(double) * (classes * 32 + 8), st);
+    if (e != cudaSuccess) return set_cuda_error(e, "final_backward memset");
+    const int64_t P = static_cast<int64_t>(N) * HW;
+    final_bwd_dx_kernel<<<tr_blocks(P, 256), 256, 0, st>>>(dlogits, w, static_cast<__half*>(dy5), loss_scale, P, HW, classes);
+    for (int k = 0; k < classes; ++k)
+        final_bwd_dw_kernel<<<tr_blocks(P, 256, 148 * 2), 256, 0, st>>>(dlogits, static_cast<const __half*>(y5), acc, acc + classes * 32, k, P, HW, classes);
+    f64_to_f32_kernel<<<(classes * 32 + 127) / 128, 128, 0, st>>>(acc, dw, classes * 32, 1.0f);
+    f64_to_f32_kernel<<<1, 128, 0, st>>>(acc + classes * 32, db, classes, 1.0f);
+    RSB_LAUNCH_CHECK("final_backward launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_pack_weights(const float* src, const int32_t* map4, void* dst, int64_t n, void* stream) {
+    if (!src || !map4 || !dst || n <= 0) return set_error(RSB_E_INVALID, "pack_weights: bad arguments");
+    pack_gather_kernel<<<tr_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, map4, static_cast<__half*>(dst), n);
+    RSB_LAUNCH_CHECK("pack_weights launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_unpack_grads(const float* packed_grad, const int32_t* map4, float* grad, int64_t n, float mul, void* stream) {
+    if (!packed_grad || !map4 || !grad || n <= 0) return set_error(RSB_E_INVALID, "unpack_grads: bad arguments");
+    unpack_scatter_kernel<<<tr_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(packed_grad, map4, grad, n, mul);
+    RSB_LAUNCH_CHECK("unpack_grads launch");
+    return RSB_OK;
+}

@@ -1,0 +1,552 @@
+"""Host-side plan of one U-Net TRAINING step (forward in train mode + full backward) on librsb200.so.
+
+Replaces what `outputs = net(images); loss.backward()` does in the reference's hot loop
+(robosat/tools/train.py:180,186) for `UNet` (robosat/unet.py:110-141) with train-mode BatchNorm (torchvision resnet50):
+
+  forward   per conv: fp32 master weights -> fp16 packed (rsb_pack_weights) -> tcgen05 conv (raw output z)
+            -> batch statistics (rsb_bn_stats / rsb_bn_finalize, running stats updated) -> y = relu(bn(z) (+ identity))
+            decoder convs have no BN: y = relu(conv) in the conv epilogue; final 1x1 conv is its own small kernel
+  backward  per conv: BN / ReLU backward (rsb_bn_backward, rsb_relu_backward) -> weight gradient on tensor cores in the
+            forward's packed layout (rsb_wgrad_*) -> rsb_unpack_grads to OIHW fp32 -> input gradient = the SAME conv
+            kernel with transposed / flipped packed weights (strided convs and the fused upsample become 4-phase scatters,
+            concat becomes one launch per source, fan-in sums ride on the kernel's residual input)
+
+The engine only builds buffers, descriptors and two op lists (`fwd_ops`, `bwd_ops`); an executor replays them. The GPU
+executor calls the C ABI; tests/emulate.py replays the same lists on the CPU to check the host logic against autograd.
+Activation gradients are fp16 and carry `loss_scale`; parameter gradients are fp32 and unscaled.
+"""
+
+import ctypes
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from robosat_b200 import _lib
+from robosat_b200._lib import ConvSrc
+from robosat_b200.engine import ConvOp, _src_dense, _src_parity, make_conv_desc
+
+RESNET50_BLOCKS = (3, 4, 6, 3)
+BN_EPS = 1e-5
+BN_MOMENTUM = 0.1
+_UP_GROUPS = {0: ((0,), (1, 2)), 1: ((0, 1), (2,))}  # rows of the 3x3 kernel summed per (phase a, tap th)
+
+
+# --------------------------------------------------------------------------------------------------
+# index maps: packed element -> up to 4 flat OIHW source indices (-1 = none). One map drives rsb_pack_weights
+# (gather + sum) and, for forward layouts, rsb_unpack_grads (scatter-add).
+# --------------------------------------------------------------------------------------------------
+def _flat_index(shape):
+    return np.arange(int(np.prod(shape)), dtype=np.int64).reshape(shape)
+
+
+def _map4(single):
+    """[...] int64 gather map (with -1) -> [n, 4] int32"""
+    m = np.full((single.size, 4), -1, dtype=np.int32)
+    m[:, 0] = single.reshape(-1)
+    return m
+
+
+def map_conv_fwd(shape):
+    idx = _flat_index(shape)  # [co, ci, kh, kw]
+    return _map4(idx.transpose(0, 2, 3, 1))  # [co][kh][kw][ci]
+
+
+def map_conv_dgrad(shape, pad_co_to=None):
+    """stride-1 dgrad operand: rows = ci, K = (kh', kw', co) with the taps flipped; co optionally zero-padded to a 64-block"""
+    co, ci, kh, kw = shape
+    idx = _flat_index(shape)[:, :, ::-1, ::-1].transpose(1, 2, 3, 0)  # [ci][kh'][kw'][co]
+    if pad_co_to and pad_co_to > co:
+        full = np.full((ci, kh, kw, pad_co_to), -1, dtype=np.int64)
+        full[..., :co] = idx
+        idx = full
+    return _map4(idx)
+
+
+def map_up_fwd(shape):
+    """fused nearest-x2 + 3x3: [phase][co][(th,tw)][ci] <- sum of the taps of group (a,th) x (b,tw)"""
+    co, ci, _, _ = shape
+    idx = _flat_index(shape)
+    m = np.full((4, co, 2, 2, ci, 4), -1, dtype=np.int32)
+    for a in (0, 1):
+        for b in (0, 1):
+            for th in (0, 1):
+                for tw in (0, 1):
+                    j = 0
+                    for kh in _UP_GROUPS[a][th]:
+                        for kw in _UP_GROUPS[b][tw]:
+                            m[2 * a + b, :, th, tw, :, j] = idx[:, :, kh, kw]
+                            j += 1
+    return m.reshape(-1, 4)
+
+
+def map_up_dgrad(shape, ci_lo, ci_hi, pad_co_to):
+    """dgrad of the fused upsample conv w.r.t. source channels [ci_lo, ci_hi): rows = ci, K = 16 segments
+    (a, b, th, tw) x co (padded to a 64-block), each the transposed phase weight block (sum of its taps)."""
+    co, _, _, _ = shape
+    idx = _flat_index(shape)
+    n_ci = ci_hi - ci_lo
+    m = np.full((n_ci, 2, 2, 2, 2, pad_co_to, 4), -1, dtype=np.int32)
+    for a in (0, 1):
+        for b in (0, 1):
+            for th in (0, 1):
+                for tw in (0, 1):
+                    j = 0
+                    for kh in _UP_GROUPS[a][th]:
+                        for kw in _UP_GROUPS[b][tw]:
+                            m[:, a, b, th, tw, :co, j] = idx[:, ci_lo:ci_hi, kh, kw].T
+                            j += 1
+    return m.reshape(-1, 4)
+
+
+def map_s2_dgrad(shape):
+    """dgrad of a 3x3 stride-2 pad-1 conv as 4 output phases of 2x2 taps on dy: [phase][ci][(th,tw)][co]"""
+    co, ci, _, _ = shape
+    idx = _flat_index(shape)
+    ksel = {(0, 0): None, (0, 1): 1, (1, 0): 2, (1, 1): 0}  # (phase bit, tap) -> kernel index
+    m = np.full((4, ci, 2, 2, co), -1, dtype=np.int64)
+    for a in (0, 1):
+        for b in (0, 1):
+            for th in (0, 1):
+                for tw in (0, 1):
+                    kh, kw = ksel[(a, th)], ksel[(b, tw)]
+                    if kh is None or kw is None:
+                        continue
+                    m[2 * a + b, :, th, tw, :] = idx[:, :, kh, kw].T
+    return _map4(m)
+
+
+def map_stem_fwd(shape):
+    co = shape[0]
+    idx = _flat_index(shape)
+    m = np.full((co, 4, 4, 16), -1, dtype=np.int64)
+    for t in range(4):
+        for ph in range(2):
+            kh = 2 * t + ph - 1
+            if not 0 <= kh < 7:
+                continue
+            for u in range(4):
+                for pw in range(2):
+                    kw = 2 * u + pw - 1
+                    if not 0 <= kw < 7:
+                        continue
+                    m[:, t, u, (ph * 2 + pw) * 3:(ph * 2 + pw) * 3 + 3] = idx[:, :, kh, kw]
+    return _map4(m)
+
+
+def map_window3_fwd(shape):
+    co, ci, _, _ = shape
+    idx = _flat_index(shape)
+    m = np.full((co, 3, 4, ci), -1, dtype=np.int64)
+    m[:, :, :3, :] = idx.transpose(0, 2, 3, 1)
+    return _map4(m)
+
+
+class Unit:
+    """One convolution of the network with everything its forward and backward need."""
+
+    def __init__(self, name):
+        self.name = name
+
+
+class UNetTrainEngine:
+    def __init__(self, params, num_classes, batch, height, width, device="cuda", loss_scale=4096.0, plan_only=False):
+        """params: name -> fp32 tensor on `device` with the reference's state_dict names WITHOUT the `module.` prefix
+        (weights, BN affine + running stats + num_batches_tracked). They are read (and the BN buffers updated) in place.
+        Gradients are written to `self.grads[name]` (fp32, zeroed at the start of every backward)."""
+        assert height % 64 == 0 and width % 64 == 0
+        self.plan_only = plan_only
+        if not plan_only:
+            _lib.require_device()
+        self.device = torch.device(device)
+        self.N, self.H, self.W, self.C = batch, height, width, num_classes
+        self.params = params
+        self.loss_scale = float(loss_scale)
+        self.fwd_ops, self.bwd_ops = [], []
+        self._keep = []
+        self.grads = OrderedDict()
+        self.units = OrderedDict()
+        self.feats = OrderedDict()
+        self.relu_outs = OrderedDict()  # name -> (post-ReLU activation buffer, logical NHWC shape): masks for tests / debugging
+        self._build()
+
+    # ---------------------------------------------------------------- allocation helpers
+    def _buf(self, *shape, dtype=torch.float16):
+        t = torch.zeros(shape, dtype=dtype, device=self.device)
+        self._keep.append(t)
+        return t
+
+    def _dev(self, arr, dtype=None):
+        t = torch.as_tensor(arr)
+        if dtype is not None:
+            t = t.to(dtype)
+        t = t.contiguous().to(self.device)
+        self._keep.append(t)
+        return t
+
+    def _grad(self, name):
+        if name not in self.grads:
+            self.grads[name] = torch.zeros_like(self.params[name], dtype=torch.float32)
+        return self.grads[name]
+
+    def _conv_op(self, name, desc):
+        return ConvOp(name, desc, (), create_plan=not self.plan_only)
+
+    def _packed(self, wname, map4):
+        """(packed fp16 buffer, device map) for parameter `wname`; a ("pack", ...) op refreshes it every step"""
+        m = self._dev(map4, torch.int32)
+        dst = self._buf(m.shape[0])
+        return dst, m
+
+    # ---------------------------------------------------------------- unit construction
+    def _add_unit(self, name, wname, fwd_map, srcs, segs, cout, phases, tile_space, out, out_pitches, out_scale=(1, 1), relu=False,
+                  out_offset=0, residual=None):
+        """forward conv (raw output unless relu=True) + its weight-gradient plan"""
+        u = Unit(name)
+        u.wname = wname
+        w = self.params[wname]
+        u.wshape = tuple(w.shape)
+        u.w_packed, u.fwd_map = self._packed(wname, fwd_map)
+        K = 64 * sum(s[3] for s in segs)
+        wp = u.w_packed.view(phases * cout, K)
+        u.desc = make_conv_desc(srcs, segs, wp, None, cout, phases, tile_space, out, out_pitches, out_scale=out_scale, relu=relu,
+                                out_offset_elems=out_offset, residual=residual)
+        u.fwd = self._conv_op(name, u.desc)
+        u.dw_packed = self._buf(phases * cout * K, dtype=torch.float32)
+        u.out, u.out_offset = out, out_offset
+        self.units[name] = u
+        self.fwd_ops.append(("pack", wname, u.fwd_map, u.w_packed))
+        self.fwd_ops.append(("conv", u.fwd))
+        return u
+
+    def _wgrad_ops(self, u, dy):
+        """weight gradient of unit u from dy (addressed like u's forward output), unpacked into the OIHW gradient"""
+        self._grad(u.wname)
+        return [("wgrad", u, dy), ("unpack", u.dw_packed, u.fwd_map, u.wname, 1.0 / self.loss_scale)]
+
+    def _dgrad(self, name, wname, map4, srcs, segs, cout, phases, tile_space, out, out_pitches, out_scale=(1, 1), residual=None,
+               out_offset=0):
+        """input-gradient conv: same kernel, weights re-packed by `map4` every step"""
+        wp, m = self._packed(wname, map4)
+        K = 64 * sum(s[3] for s in segs)
+        desc = make_conv_desc(srcs, segs, wp.view(phases * cout, K), None, cout, phases, tile_space, out, out_pitches, out_scale=out_scale,
+                              relu=False, residual=residual, out_offset_elems=out_offset)
+        op = self._conv_op(name, desc)
+        return [("pack", wname, m, wp), ("conv", op)]
+
+    def _bn(self, prefix, z, M, C):
+        b = Unit(prefix)
+        b.prefix, b.z, b.M, b.C = prefix, z, M, C
+        b.sums = self._buf(2 * C, dtype=torch.float64)
+        b.mean, b.invstd, b.scale, b.shift = (self._buf(C, dtype=torch.float32) for _ in range(4))
+        return b
+
+    def _bn_fwd_ops(self, b, y, residual, relu):
+        self.fwd_ops.append(("bn_stats", b))
+        self.fwd_ops.append(("bn_finalize", b))
+        self.fwd_ops.append(("bn_apply", b, residual, y, relu))
+
+    # ---------------------------------------------------------------- graph
+    def _build(self):
+        P = self.params
+        N, H, W = self.N, self.H, self.W
+        H2, W2, H4, W4 = H // 2, W // 2, H // 4, W // 4
+        bwd = []  # built in forward order as blocks of ops; emitted reversed at the end
+
+        def dense(h, w, c):
+            return (c, w * c, h * w * c)
+
+        # ---- stem
+        self.x_in = None
+        self.s2d = self._buf(N, H2, W2 + 4, 16)
+        self.fwd_ops.append(("prepass",))
+        Wp = W2 + 4
+        z0 = self._buf(N, H2, W2, 64)
+        y0 = self._buf(N, H2, W2, 64)
+        src = ConvSrc(self.s2d.data_ptr(), 16, Wp * 16, H2 * Wp * 16, 64, W2, H2, N)
+        stem = self._add_unit("stem", "resnet.conv1.weight", map_stem_fwd(tuple(P["resnet.conv1.weight"].shape)), [src],
+                              [(0, t - 2, 0, 1) for t in range(4)], 64, 1, (W2, H2, N), z0, dense(H2, W2, 64))
+        bn0 = self._bn("resnet.bn1", z0, N * H2 * W2, 64)
+        self._bn_fwd_ops(bn0, y0, None, True)
+        p0 = self._buf(N, H4, W4, 64)
+        self.fwd_ops.append(("maxpool", y0, p0, N, H2, W2, 64, 3, 2, 1))
+        self.feats["stem"] = (y0, (N, H2, W2, 64))
+        self.relu_outs["stem"] = (y0, (N, H2, W2, 64))
+        self.feats["enc0"] = (p0, (N, H4, W4, 64))
+        d_p0 = self._buf(N, H4, W4, 64)   # gradient w.r.t. p0, produced by layer1.0's backward
+        d_y0 = self._buf(N, H2, W2, 64)
+        dz0 = self._buf(N, H2, W2, 64)
+        bwd.append([("maxpool_bwd", y0, d_p0, d_y0, N, H2, W2, 64, 3, 2, 1), ("bn_bwd", bn0, d_y0, y0, dz0, None)] + self._wgrad_ops(stem, dz0))
+
+        # ---- encoder
+        cur, curC, curH, curW, d_cur = p0, 64, H4, W4, d_p0
+        encs = []
+        for li, blocks in enumerate(RESNET50_BLOCKS, start=1):
+            planes = 64 * 2 ** (li - 1)
+            for bi in range(blocks):
+                p = "resnet.layer%d.%d" % (li, bi)
+                stride = 2 if (bi == 0 and li > 1) else 1
+                oH, oW = curH // stride, curW // stride
+                outC = planes * 4
+                has_ds = (p + ".downsample.0.weight") in P
+                M_in, M_out = N * curH * curW, N * oH * oW
+                # forward
+                z1, y1 = self._buf(N, curH, curW, planes), self._buf(N, curH, curW, planes)
+                u1 = self._add_unit(p + ".conv1", p + ".conv1.weight", map_conv_fwd(tuple(P[p + ".conv1.weight"].shape)),
+                                    [_src_dense(cur, N, curH, curW, curC)], [(0, 0, 0, curC // 64)], planes, 1, (curW, curH, N), z1,
+                                    dense(curH, curW, planes))
+                b1 = self._bn(p + ".bn1", z1, M_in, planes)
+                self._bn_fwd_ops(b1, y1, None, True)
+                z2, y2 = self._buf(N, oH, oW, planes), self._buf(N, oH, oW, planes)
+                if stride == 1:
+                    srcs2 = [_src_dense(y1, N, curH, curW, planes)]
+                    segs2 = [(0, kh - 1, kw - 1, planes // 64) for kh in range(3) for kw in range(3)]
+                else:
+                    srcs2 = [_src_parity(y1, N, curH, curW, planes, ph, pw) for ph in range(2) for pw in range(2)]
+                    segs2 = [(((kh - 1) % 2) * 2 + (kw - 1) % 2, (kh - 1) // 2, (kw - 1) // 2, planes // 64) for kh in range(3) for kw in range(3)]
+                u2 = self._add_unit(p + ".conv2", p + ".conv2.weight", map_conv_fwd(tuple(P[p + ".conv2.weight"].shape)), srcs2, segs2,
+                                    planes, 1, (oW, oH, N), z2, dense(oH, oW, planes))
+                b2 = self._bn(p + ".bn2", z2, M_out, planes)
+                self._bn_fwd_ops(b2, y2, None, True)
+                z3 = self._buf(N, oH, oW, outC)
+                u3 = self._add_unit(p + ".conv3", p + ".conv3.weight", map_conv_fwd(tuple(P[p + ".conv3.weight"].shape)),
+                                    [_src_dense(y2, N, oH, oW, planes)], [(0, 0, 0, planes // 64)], outC, 1, (oW, oH, N), z3, dense(oH, oW, outC))
+                b3 = self._bn(p + ".bn3", z3, M_out, outC)
+                if has_ds:
+                    zd, idt = self._buf(N, oH, oW, outC), self._buf(N, oH, oW, outC)
+                    sd_ = _src_dense(cur, N, curH, curW, curC) if stride == 1 else _src_parity(cur, N, curH, curW, curC, 0, 0)
+                    ud = self._add_unit(p + ".downsample", p + ".downsample.0.weight", map_conv_fwd(tuple(P[p + ".downsample.0.weight"].shape)),
+                                        [sd_], [(0, 0, 0, curC // 64)], outC, 1, (oW, oH, N), zd, dense(oH, oW, outC))
+                    bd = self._bn(p + ".downsample.1", zd, M_out, outC)
+                    self._bn_fwd_ops(bd, idt, None, False)
+                else:
+                    idt = cur
+                out = self._buf(N, oH, oW, outC)
+                self._bn_fwd_ops(b3, out, idt, True)
+                self.feats[p] = (out, (N, oH, oW, outC))
+                self.relu_outs[p + ".relu1"] = (y1, (N, curH, curW, planes))
+                self.relu_outs[p + ".relu2"] = (y2, (N, oH, oW, planes))
+                self.relu_outs[p + ".out"] = (out, (N, oH, oW, outC))
+                d_out = self._buf(N, oH, oW, outC)  # gradient w.r.t. this block's output (written by its consumers)
+
+                # backward of this block (executed after all later blocks)
+                ops = []
+                dz3, g = self._buf(N, oH, oW, outC), self._buf(N, oH, oW, outC)
+                ops.append(("bn_bwd", b3, d_out, out, dz3, g))
+                ops += self._wgrad_ops(u3, dz3)
+                dy2 = self._buf(N, oH, oW, planes)
+                ops += self._dgrad(p + ".conv3.dgrad", p + ".conv3.weight", map_conv_dgrad(u3.wshape), [_src_dense(dz3, N, oH, oW, outC)],
+                                   [(0, 0, 0, outC // 64)], planes, 1, (oW, oH, N), dy2, dense(oH, oW, planes))
+                dz2 = self._buf(N, oH, oW, planes)
+                ops.append(("bn_bwd", b2, dy2, y2, dz2, None))
+                ops += self._wgrad_ops(u2, dz2)
+                dy1 = self._buf(N, curH, curW, planes)
+                if stride == 1:
+                    ops += self._dgrad(p + ".conv2.dgrad", p + ".conv2.weight", map_conv_dgrad(u2.wshape), [_src_dense(dz2, N, oH, oW, planes)],
+                                       [(0, kh - 1, kw - 1, planes // 64) for kh in range(3) for kw in range(3)], planes, 1, (oW, oH, N), dy1,
+                                       dense(curH, curW, planes))
+                else:
+                    ops += self._dgrad(p + ".conv2.dgrad", p + ".conv2.weight", map_s2_dgrad(u2.wshape), [_src_dense(dz2, N, oH, oW, planes)],
+                                       [(0, th - 1, tw - 1, planes // 64) for th in range(2) for tw in range(2)], planes, 4, (oW, oH, N), dy1,
+                                       dense(curH, curW, planes), out_scale=(2, 2))
+                dz1 = self._buf(N, curH, curW, planes)
+                ops.append(("bn_bwd", b1, dy1, y1, dz1, None))
+                ops += self._wgrad_ops(u1, dz1)
+                if has_ds:
+                    dzd = self._buf(N, oH, oW, outC)
+                    ops.append(("bn_bwd", bd, g, None, dzd, None))
+                    ops += self._wgrad_ops(ud, dzd)
+                    # the downsample's input gradient lands on the (even) pixels of d_cur IN PLACE, on top of whatever the
+                    # decoder's skip connection already accumulated there (residual = the buffer itself)
+                    # (layer1.0 has no skip gradient underneath: plain write)
+                    ops += self._dgrad(p + ".downsample.dgrad", p + ".downsample.0.weight", map_conv_dgrad(ud.wshape),
+                                       [_src_dense(dzd, N, oH, oW, outC)], [(0, 0, 0, outC // 64)], curC, 1, (oW, oH, N), d_cur,
+                                       dense(curH, curW, curC), out_scale=(stride, stride), residual=d_cur if li > 1 else None)
+                    fan_in = d_cur
+                else:
+                    fan_in = g
+                # d_cur = conv1 input gradient + identity / downsample gradient (in place when fan_in is d_cur itself)
+                ops += self._dgrad(p + ".conv1.dgrad", p + ".conv1.weight", map_conv_dgrad(u1.wshape), [_src_dense(dz1, N, curH, curW, planes)],
+                                   [(0, 0, 0, planes // 64)], curC, 1, (curW, curH, N), d_cur, dense(curH, curW, curC), residual=fan_in)
+                bwd.append(ops)
+                cur, curC, curH, curW, d_cur = out, outC, oH, oW, d_out
+            encs.append((cur, curC, curH, curW, d_cur))
+            self.feats["enc%d" % li] = (cur, (N, curH, curW, curC))
+        (enc1, c1, h1, w1, d_enc1), (enc2, c2, h2, w2, d_enc2), (enc3, c3, h3, w3, d_enc3), (enc4, c4, h4, w4, d_enc4) = encs
+        self._skip_grads = [d_enc1, d_enc2, d_enc3, d_enc4]
+
+        # ---- center + decoder
+        hp, wpx = h4 // 2, w4 // 2
+        pool4 = self._buf(N, hp, wpx, c4)
+        self.fwd_ops.append(("maxpool", enc4, pool4, N, h4, w4, c4, 2, 2, 0))
+        d_pool4 = self._buf(N, hp, wpx, c4)
+
+        dec_bwd = []
+
+        def decoder(name, sources, lh, lw, cout, out, out_pitches, d_out, d_out_pitches, d_sources, out_offset=0, first_into=None):
+            """sources: [(tensor, C)]; d_sources: [(grad tensor, accumulate?)] receiving the input gradients"""
+            wname = name + ".block.block.weight"
+            wshape = tuple(P[wname].shape)
+            srcs = [_src_dense(t, N, lh, lw, c) for t, c in sources]
+            segs = [(si, th - 1, tw - 1, c // 64) for th in range(2) for tw in range(2) for si, (_, c) in enumerate(sources)]
+            u = self._add_unit(name, wname, map_up_fwd(wshape), srcs, segs, cout, 4, (lw, lh, N), out, out_pitches, out_scale=(2, 2), relu=True,
+                               out_offset=out_offset)
+            # backward: g = d_out * (out > 0) in place over the whole buffer, wgrad, then one dgrad launch per source
+            ops = [("relu_bwd", d_out, None, out, d_out)]
+            ops += self._wgrad_ops(u, d_out)
+            pad_co = -(-cout // 64) * 64
+            oH, oW = 2 * lh, 2 * lw
+            pw_, ph_, pn_ = d_out_pitches
+            views = [ConvSrc(d_out.data_ptr() + 2 * (out_offset + a * ph_ + b * pw_), 2 * pw_, 2 * ph_, pn_, cout, lw, lh, N) for a in (0, 1) for b in (0, 1)]
+            dsegs = [(2 * a + b, 1 - th - a, 1 - tw - b, pad_co // 64) for a in (0, 1) for b in (0, 1) for th in (0, 1) for tw in (0, 1)]
+            lo = 0
+            for (t, c), (dt, acc) in zip(sources, d_sources):
+                ops += self._dgrad("%s.dgrad%d" % (name, lo), wname, map_up_dgrad(wshape, lo, lo + c, pad_co), views, dsegs, c, 1, (lw, lh, N), dt,
+                                   dense(lh, lw, c), residual=dt if acc else None)
+                lo += c
+            dec_bwd.append(ops)
+            return u
+
+        center = self._buf(N, h4, w4, 256)
+        d_center = self._buf(N, h4, w4, 256)
+        decoder("center", [(pool4, c4)], hp, wpx, 256, center, dense(h4, w4, 256), d_center, dense(h4, w4, 256), [(d_pool4, False)])
+        dec0 = self._buf(N, h3, w3, 256)
+        d_dec0 = self._buf(N, h3, w3, 256)
+        # d_enc4 receives the dec0 skip gradient first (plain write), then the max-pool gradient from center is added
+        decoder("dec0", [(enc4, c4), (center, 256)], h4, w4, 256, dec0, dense(h3, w3, 256), d_dec0, dense(h3, w3, 256), [(d_enc4, False), (d_center, False)])
+        dec1 = self._buf(N, h2, w2, 256)
+        d_dec1 = self._buf(N, h2, w2, 256)
+        decoder("dec1", [(enc3, c3), (dec0, 256)], h3, w3, 256, dec1, dense(h2, w2, 256), d_dec1, dense(h2, w2, 256), [(d_enc3, False), (d_dec0, False)])
+        dec2 = self._buf(N, h1, w1, 64)
+        d_dec2 = self._buf(N, h1, w1, 64)
+        decoder("dec2", [(enc2, c2), (dec1, 256)], h2, w2, 64, dec2, dense(h1, w1, 64), d_dec2, dense(h1, w1, 64), [(d_enc2, False), (d_dec1, False)])
+        dec3 = self._buf(N, H2, W2, 128)
+        d_dec3 = self._buf(N, H2, W2, 128)
+        decoder("dec3", [(enc1, c1), (dec2, 64)], h1, w1, 128, dec3, dense(H2, W2, 128), d_dec3, dense(H2, W2, 128), [(d_enc1, False), (d_dec2, False)])
+        Wq = W + 4
+        dec4 = self._buf(N, H, Wq, 32)
+        d_dec4 = self._buf(N, H, Wq, 32)
+        padded = (32, Wq * 32, H * Wq * 32)
+        decoder("dec4", [(dec3, 128)], H2, W2, 32, dec4, padded, d_dec4, padded, [(d_dec3, False)], out_offset=32)
+        for nm, t, shp in (("center", center, (N, h4, w4, 256)), ("dec0", dec0, (N, h3, w3, 256)), ("dec1", dec1, (N, h2, w2, 256)),
+                           ("dec2", dec2, (N, h1, w1, 64)), ("dec3", dec3, (N, H2, W2, 128)), ("dec4", dec4, (N, H, Wq, 32))):
+            self.feats[nm] = (t, shp)
+            self.relu_outs[nm] = (t, shp)
+
+        # dec5: plain 3x3 on the W-padded dec4 buffer (window view), relu in the epilogue
+        y5 = self._buf(N, H, W, 32)
+        d_y5 = self._buf(N, H, W, 32)
+        src5 = ConvSrc(dec4.data_ptr(), 32, Wq * 32, H * Wq * 32, 128, W, H, N)
+        u5 = self._add_unit("dec5", "dec5.block.weight", map_window3_fwd(tuple(P["dec5.block.weight"].shape)), [src5],
+                            [(0, kh - 1, 0, 2) for kh in range(3)], 32, 1, (W, H, N), y5, dense(H, W, 32), relu=True)
+        self.feats["dec5"] = (y5, (N, H, W, 32))
+        self.relu_outs["dec5"] = (y5, (N, H, W, 32))
+        self.logits = self._buf(N, self.C, H, W, dtype=torch.float32)
+        self.fwd_ops.append(("final_fwd", y5, self.logits))
+        self.final_acc = self._buf(self.C * 32 + 8, dtype=torch.float64)
+
+        ops5 = [("final_bwd", y5, d_y5), ("relu_bwd", d_y5, None, y5, d_y5)]
+        ops5 += self._wgrad_ops(u5, d_y5)
+        ops5 += self._dgrad("dec5.dgrad", "dec5.block.weight", map_conv_dgrad(u5.wshape, pad_co_to=64), [_src_dense(d_y5, N, H, W, 32)],
+                            [(0, kh - 1, kw - 1, 1) for kh in range(3) for kw in range(3)], 32, 1, (W, H, N), d_dec4, padded, out_offset=32)
+
+        # ---- backward program: head, decoder (reverse), pool4 fan-in, encoder (reverse)
+        self.bwd_ops = [("zero_grads",)] + ops5
+        for ops in reversed(dec_bwd):
+            self.bwd_ops += ops
+        # enc4's gradient = dec0 skip gradient (already in d_enc4) + max-pool backward of the center branch
+        d_enc4_pool = self._buf(N, h4, w4, c4)
+        self.bwd_ops.append(("maxpool_bwd", enc4, d_pool4, d_enc4_pool, N, h4, w4, c4, 2, 2, 0))
+        self.bwd_ops.append(("relu_bwd", d_enc4, d_enc4_pool, None, d_enc4))  # plain sum (no mask)
+        for ops in reversed(bwd):
+            self.bwd_ops += ops
+        self._mean = (ctypes.c_float * 3)(0.485, 0.456, 0.406)
+        self._std = (ctypes.c_float * 3)(0.229, 0.224, 0.225)
+
+    # ---------------------------------------------------------------- GPU executor
+    def _run(self, ops, x=None, dlogits=None):
+        lib = _lib.load()
+        st = _lib.current_stream_ptr()
+        P = self.params
+        for op in ops:
+            k = op[0]
+            if k == "conv":
+                op[1].run(st)
+            elif k == "pack":
+                _, wname, m, dst = op
+                _lib.check(lib.rsb_pack_weights(P[wname].data_ptr(), m.data_ptr(), dst.data_ptr(), dst.numel(), st), "rsb_pack_weights")
+            elif k == "bn_stats":
+                b = op[1]
+                _lib.check(lib.rsb_bn_stats(b.z.data_ptr(), b.sums.data_ptr(), b.M, b.C, st), "rsb_bn_stats")
+            elif k == "bn_finalize":
+                b = op[1]
+                pf = b.prefix
+                _lib.check(lib.rsb_bn_finalize(b.sums.data_ptr(), P[pf + ".weight"].data_ptr(), P[pf + ".bias"].data_ptr(), P[pf + ".running_mean"].data_ptr(),
+                                               P[pf + ".running_var"].data_ptr(), P[pf + ".num_batches_tracked"].data_ptr(), b.mean.data_ptr(),
+                                               b.invstd.data_ptr(), b.scale.data_ptr(), b.shift.data_ptr(), b.C, b.M, BN_EPS, BN_MOMENTUM, st), "rsb_bn_finalize")
+            elif k == "bn_apply":
+                _, b, res, y, relu = op
+                _lib.check(lib.rsb_bn_apply(b.z.data_ptr(), b.scale.data_ptr(), b.shift.data_ptr(), res.data_ptr() if res is not None else None,
+                                            y.data_ptr(), b.M, b.C, 1 if relu else 0, st), "rsb_bn_apply")
+            elif k == "bn_bwd":
+                _, b, dy, y, dz, g = op
+                pf = b.prefix
+                _lib.check(lib.rsb_bn_backward(dy.data_ptr(), y.data_ptr() if y is not None else None, b.z.data_ptr(), b.mean.data_ptr(), b.invstd.data_ptr(),
+                                               P[pf + ".weight"].data_ptr(), b.sums.data_ptr(), dz.data_ptr(), g.data_ptr() if g is not None else None,
+                                               self._grad(pf + ".weight").data_ptr(), self._grad(pf + ".bias").data_ptr(), 1.0 / self.loss_scale,
+                                               b.M, b.C, st), "rsb_bn_backward")
+            elif k == "relu_bwd":
+                _, a, b2, y, out = op
+                _lib.check(lib.rsb_relu_backward(a.data_ptr(), b2.data_ptr() if b2 is not None else None, y.data_ptr() if y is not None else None,
+                                                 out.data_ptr(), a.numel(), st), "rsb_relu_backward")
+            elif k == "maxpool":
+                _, src, dst, n, h, w, c, kk, s, p = op
+                _lib.check(lib.rsb_maxpool_nhwc(src.data_ptr(), dst.data_ptr(), n, h, w, c, kk, s, p, st), "rsb_maxpool_nhwc")
+            elif k == "maxpool_bwd":
+                _, xx, dy, dx, n, h, w, c, kk, s, p = op
+                _lib.check(lib.rsb_maxpool_backward(xx.data_ptr(), dy.data_ptr(), dx.data_ptr(), n, h, w, c, kk, s, p, st), "rsb_maxpool_backward")
+            elif k == "wgrad":
+                _, u, dy = op
+                if not hasattr(u, "wgrad_plan"):
+                    u.wgrad_plan = ctypes.c_void_p()
+                    _lib.check(lib.rsb_wgrad_plan_create(ctypes.byref(u.desc), dy.data_ptr() + 2 * u.out_offset, u.dw_packed.data_ptr(),
+                                                         ctypes.byref(u.wgrad_plan)), "rsb_wgrad_plan_create[%s]" % u.name)
+                _lib.check(lib.rsb_wgrad_run(u.wgrad_plan, st), "rsb_wgrad_run[%s]" % u.name)
+            elif k == "unpack":
+                _, dwp, m, wname, mul = op
+                _lib.check(lib.rsb_unpack_grads(dwp.data_ptr(), m.data_ptr(), self._grad(wname).data_ptr(), dwp.numel(), mul, st), "rsb_unpack_grads")
+            elif k == "prepass":
+                kind = 0 if x.dtype == torch.float32 else 1
+                _lib.check(lib.rsb_prepass_s2d(x.data_ptr(), kind, self.s2d.data_ptr(), self.N, self.H, self.W, self._mean, self._std, st), "rsb_prepass_s2d")
+            elif k == "final_fwd":
+                _, y5, logits = op
+                _lib.check(lib.rsb_final_forward(y5.data_ptr(), P["final.weight"].data_ptr(), P["final.bias"].data_ptr(), logits.data_ptr(),
+                                                 self.N, self.H * self.W, self.C, st), "rsb_final_forward")
+            elif k == "final_bwd":
+                _, y5, d_y5 = op
+                _lib.check(lib.rsb_final_backward(dlogits.data_ptr(), y5.data_ptr(), P["final.weight"].data_ptr(), d_y5.data_ptr(), self.final_acc.data_ptr(),
+                                                  self._grad("final.weight").data_ptr(), self._grad("final.bias").data_ptr(), self.loss_scale,
+                                                  self.N, self.H * self.W, self.C, st), "rsb_final_backward")
+            elif k == "zero_grads":
+                for g in self.grads.values():
+                    g.zero_()
+            else:  # pragma: no cover
+                raise AssertionError(k)
+
+    def forward(self, x):
+        if self.plan_only:
+            raise _lib.RsbError("UNetTrainEngine was built with plan_only=True; there is no CPU execution path")
+        assert x.is_cuda and x.is_contiguous()
+        self._run(self.fwd_ops, x=x)
+        return self.logits
+
+    def backward(self, dlogits):
+        """dlogits: fp32 [N, C, H, W] gradient of the loss w.r.t. the logits (unscaled). Fills self.grads."""
+        if self.plan_only:
+            raise _lib.RsbError("UNetTrainEngine was built with plan_only=True; there is no CPU execution path")
+        assert dlogits.is_cuda and dlogits.is_contiguous() and dlogits.dtype == torch.float32
+        for name in self.params:
+            if self.params[name].dtype == torch.float32 and not (name.endswith("running_mean") or name.endswith("running_var")) and not name.startswith("resnet.fc."):
+                self._grad(name)
+        self._run(self.bwd_ops, dlogits=dlogits)
+        return self.grads

@@ -98,3 +98,145 @@ def run_engine(engine, x):
         else:
             run_desc(op[1].desc)
     return engine.logits.clone()
+
+
+# --------------------------------------------------------------------------------------------------
+# training plan emulation (robosat_b200/train_engine.py op lists on CPU buffers)
+# --------------------------------------------------------------------------------------------------
+def _gather_segment(d, seg, phase):
+    """A operand of one segment for all tile-space pixels: float32 [Nt, Ht, Wt, 64*cblocks] (zero outside the view)"""
+    pa, pb = phase >> 1, phase & 1
+    src = d.srcs[seg.src]
+    width = seg.cblocks * 64
+    sv = _view(src.ptr, (src.N, src.H, src.W, min(width, src.C)), (src.pitch_n, src.pitch_h, src.pitch_w, 1))
+    hh = np.arange(d.Ht)[:, None] + seg.dh + pa
+    ww = np.arange(d.Wt)[None, :] + seg.dw + pb
+    inb = (hh >= 0) & (hh < src.H) & (ww >= 0) & (ww < src.W)
+    g = sv[:, np.clip(hh, 0, src.H - 1), np.clip(ww, 0, src.W - 1), :].astype(np.float32) * inb[None, :, :, None]
+    a = np.zeros((d.Nt, d.Ht, d.Wt, width), dtype=np.float32)
+    nn = min(d.Nt, src.N)
+    a[:nn, :, :, :g.shape[-1]] = g[:nn]
+    return a
+
+
+def run_wgrad(d, dy_ptr, dw):
+    """dw[phase*Cout + co][k] = sum_pixels dy_phase[p][co] * A_segment(k)[p]  (what rsb_wgrad_run accumulates); dw: torch fp32"""
+    K = 64 * sum(d.segs[i].cblocks for i in range(d.nseg))
+    out = dw.numpy().reshape(d.phases * d.Cout, K)
+    out[...] = 0
+    for phase in range(d.phases):
+        pa, pb = phase >> 1, phase & 1
+        base = dy_ptr + 2 * (pa * d.out_pitch_h + pb * d.out_pitch_w)
+        dyv = _view(base, (d.Nt, d.Ht, d.Wt, d.Cout), (d.out_pitch_n, d.out_sy * d.out_pitch_h, d.out_sx * d.out_pitch_w, 1)).astype(np.float32)
+        k0 = 0
+        for si in range(d.nseg):
+            a = _gather_segment(d, d.segs[si], phase)
+            out[phase * d.Cout:(phase + 1) * d.Cout, k0:k0 + a.shape[-1]] = np.tensordot(dyv, a, axes=([0, 1, 2], [0, 1, 2]))
+            k0 += a.shape[-1]
+
+
+def run_train_ops(eng, ops, x=None, dlogits=None):
+    """Replay a UNetTrainEngine op list (plan_only, CPU buffers) with torch / numpy semantics of the C ABI entry points."""
+    import torch
+    import torch.nn.functional as F
+
+    P = eng.params
+    for op in ops:
+        k = op[0]
+        if k == "conv":
+            run_desc(op[1].desc)
+        elif k == "pack":
+            _, wname, m, dst = op
+            src = P[wname].reshape(-1)
+            mm = m.long()
+            vals = torch.where(mm >= 0, src[mm.clamp_min(0)], torch.zeros(()))
+            dst.copy_(vals.sum(1).half())
+        elif k == "bn_stats":
+            b = op[1]
+            z = b.z.reshape(b.M, b.C).double()
+            b.sums[:b.C] = z.sum(0)
+            b.sums[b.C:] = (z * z).sum(0)
+        elif k == "bn_finalize":
+            b = op[1]
+            pf = b.prefix
+            mean = b.sums[:b.C] / b.M
+            var = (b.sums[b.C:] / b.M - mean * mean).clamp_min(0)
+            invstd = (1.0 / torch.sqrt(var + eng_eps())).float()
+            b.mean.copy_(mean.float())
+            b.invstd.copy_(invstd)
+            b.scale.copy_(P[pf + ".weight"] * invstd)
+            b.shift.copy_(P[pf + ".bias"] - mean.float() * b.scale)
+            P[pf + ".running_mean"].mul_(0.9).add_(0.1 * mean.float())
+            P[pf + ".running_var"].mul_(0.9).add_(0.1 * (var * b.M / (b.M - 1)).float())
+            P[pf + ".num_batches_tracked"].add_(1)
+        elif k == "bn_apply":
+            _, b, res, y, relu = op
+            o = b.z.reshape(b.M, b.C).float() * b.scale + b.shift
+            if res is not None:
+                o = o + res.reshape(b.M, b.C).float()
+            y.copy_((F.relu(o) if relu else o).half().reshape(y.shape))
+        elif k == "bn_bwd":
+            _, b, dy, y, dz, g_out = op
+            pf = b.prefix
+            g = dy.reshape(b.M, b.C).float()
+            if y is not None:
+                g = g * (y.reshape(b.M, b.C).float() > 0)
+            zhat = (b.z.reshape(b.M, b.C).float() - b.mean) * b.invstd
+            s0 = g.double().sum(0)
+            s1 = (g * zhat).double().sum(0)
+            if g_out is not None:
+                g_out.copy_(g.half().reshape(g_out.shape))
+            o = P[pf + ".weight"] * b.invstd * (g - (s0 / b.M).float() - zhat * (s1 / b.M).float())
+            dz.copy_(o.half().reshape(dz.shape))
+            eng._grad(pf + ".weight").copy_((s1 / eng.loss_scale).float())
+            eng._grad(pf + ".bias").copy_((s0 / eng.loss_scale).float())
+        elif k == "relu_bwd":
+            _, a, b2, y, out = op
+            g = a.float()
+            if b2 is not None:
+                g = g + b2.float()
+            if y is not None:
+                g = g * (y.float() > 0)
+            out.copy_(g.half())
+        elif k == "maxpool":
+            _, src, dst, n, h, w, c, kk, s, p = op
+            yy = F.max_pool2d(src.float().reshape(n, h, w, c).permute(0, 3, 1, 2), kk, s, p)
+            dst.copy_(yy.permute(0, 2, 3, 1).half())
+        elif k == "maxpool_bwd":
+            _, xx, dy, dx, n, h, w, c, kk, s, p = op
+            xin = xx.float().reshape(n, h, w, c).permute(0, 3, 1, 2).clone().requires_grad_(True)
+            yy = F.max_pool2d(xin, kk, s, p)
+            yy.backward(dy.float().reshape(n, yy.shape[2], yy.shape[3], c).permute(0, 3, 1, 2))
+            dx.copy_(xin.grad.permute(0, 2, 3, 1).half())
+        elif k == "wgrad":
+            _, u, dy = op
+            run_wgrad(u.desc, dy.data_ptr() + 2 * u.out_offset, u.dw_packed)
+        elif k == "unpack":
+            _, dwp, m, wname, mul = op
+            flat = eng._grad(wname).reshape(-1)
+            mm = m.long()
+            for j in range(4):
+                sel = mm[:, j] >= 0
+                flat.index_add_(0, mm[sel, j], dwp[sel] * mul)
+        elif k == "prepass":
+            eng.s2d.copy_(prepass_s2d_cpu(x))
+        elif k == "final_fwd":
+            _, y5, logits = op
+            yv = y5.float().permute(0, 3, 1, 2)
+            logits.copy_(F.conv2d(yv, P["final.weight"], P["final.bias"]))
+        elif k == "final_bwd":
+            _, y5, d_y5 = op
+            w = P["final.weight"].reshape(eng.C, 32)
+            d = torch.einsum("nkhw,kc->nhwc", dlogits, w) * eng.loss_scale
+            d_y5.copy_(d.half())
+            eng._grad("final.weight").copy_(torch.einsum("nkhw,nhwc->kc", dlogits, y5.float()).reshape(eng.C, 32, 1, 1))
+            eng._grad("final.bias").copy_(dlogits.sum((0, 2, 3)))
+        elif k == "zero_grads":
+            for g in eng.grads.values():
+                g.zero_()
+        else:
+            raise AssertionError(k)
+
+
+def eng_eps():
+    return 1e-5

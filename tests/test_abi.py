@@ -32,6 +32,7 @@ def test_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.ConvSrc) == 48
     assert ctypes.sizeof(_lib.ConvSeg) == 16
     assert _lib.ConvDesc.srcs.offset == 8 and _lib.ConvDesc.segs.offset == 8 + 4 * 48 + 4
+    assert _lib.RSB_MAX_SEGS == 16 and _lib.RSB_MAX_SRCS == 4  # keep in sync with include/rsb200.h
     assert ctypes.sizeof(_lib.ConvDesc) % 8 == 0
 
 

@@ -65,3 +65,33 @@ def test_engine_graph_matches_oracle(size, batch, classes):
         r = ((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt()).item()
         assert r < 3e-3, (name, r)
     assert len(eng.ops) == 59  # 1 pre-pass + 2 max pools + 56 conv launches (downsample fused into conv3, final into dec5)
+
+
+def test_train_engine_plan_matches_autograd_on_cpu():
+    """The whole training plan (forward in train mode + backward op lists) replayed by the CPU emulator:
+    forward vs the oracle's train-mode forward, parameter gradients vs autograd through the mask-frozen fp32 network."""
+    import linearized
+    from robosat_b200.train_engine import UNetTrainEngine
+
+    C, B, S = 2, 2, 64
+    sd0 = {k[7:]: v.clone() for k, v in synth.make_state_dict(C, seed=0).items()}
+    x = synth.normalize_tiles(synth.make_tiles_u8(B, S, seed=1))
+    dlogits = torch.randn((B, C, S, S), generator=torch.Generator().manual_seed(3)) * 1e-3
+    params = {k: v.clone() for k, v in sd0.items()}
+    eng = UNetTrainEngine(params, C, B, S, S, device="cpu", plan_only=True, loss_scale=1024.0)
+    emulate.run_train_ops(eng, eng.fwd_ops, x=x)
+    sd = {k: v.clone() for k, v in sd0.items()}
+    with torch.no_grad():
+        ref = unet_oracle.unet_forward_train(sd, x)
+    assert ((eng.logits - ref).pow(2).sum().sqrt() / ref.pow(2).sum().sqrt()).item() < 5e-3
+    assert torch.allclose(params["resnet.bn1.running_mean"], sd["resnet.bn1.running_mean"], atol=1e-3)
+    assert int(params["resnet.bn1.num_batches_tracked"]) == int(sd0["resnet.bn1.num_batches_tracked"]) + 1
+    emulate.run_train_ops(eng, eng.bwd_ops, dlogits=dlogits)
+    sdg = {k: v.clone() for k, v in sd0.items()}
+    for k, v in sdg.items():
+        if v.dtype == torch.float32 and "running" not in k:
+            v.requires_grad_(True)
+    (linearized.forward(eng, sdg, x) * dlogits).sum().backward()
+    rels = [((eng.grads[k] - v.grad).pow(2).sum().sqrt() / v.grad.pow(2).sum().sqrt().clamp_min(1e-30)).item()
+            for k, v in sdg.items() if v.requires_grad and not k.startswith("resnet.fc")]
+    assert len(rels) == 168 and max(rels) < 6e-2 and sorted(rels)[len(rels) // 2] < 3e-2, (max(rels), sorted(rels)[len(rels) // 2])

@@ -1,0 +1,200 @@
+"""GPU parity of the training path: helper kernels vs torch, the tcgen05 weight-gradient kernel vs its CPU emulation,
+and the whole UNetTrainEngine (train-mode forward + backward) vs (a) the fp32 oracle forward and (b) autograd through the
+mask-frozen fp32 network (tests/linearized.py).
+
+Tolerances: activations / activation gradients are fp16, so single kernels agree to fp16 rounding of their outputs;
+whole-network gradients are compared in relative L2 per parameter tensor (<= 6e-2, median <= 3e-2: ~100 chained fp16
+roundings, batch statistics over as few as 8 pixels in layer4 at this test size)."""
+
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import conv_cases
+import emulate
+import linearized
+from oracle import unet_oracle
+from robosat_b200 import _lib, synth
+from robosat_b200.train_engine import UNetTrainEngine
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a - b).pow(2).sum().sqrt() / b.pow(2).sum().sqrt().clamp_min(1e-30)).item()
+
+
+def test_batchnorm_train_kernels(cuda_device):
+    lib, st = _lib.load(), _lib.current_stream_ptr()
+    g = torch.Generator().manual_seed(0)
+    for (M, C) in [(2 * 16 * 16, 64), (3 * 8 * 8, 2048), (5 * 7 * 9, 256)]:
+        z = (torch.randn((M, C), generator=g) * 1.5 + 0.3).half()
+        res = torch.randn((M, C), generator=g).half()
+        gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+        rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+        # torch reference on the same fp16 values
+        zt = z.float().t().reshape(1, C, M, 1).clone().requires_grad_(True)
+        gt, bt = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+        rm_ref, rv_ref = rm.clone(), rv.clone()
+        y_ref = F.relu(F.batch_norm(zt, rm_ref, rv_ref, gt, bt, training=True, momentum=0.1, eps=1e-5) + res.float().t().reshape(1, C, M, 1))
+        dy = torch.randn((M, C), generator=g).half()
+        y_ref.backward(dy.float().t().reshape(1, C, M, 1))
+        d = cuda_device
+        zd, resd, dyd = z.to(d), res.to(d), dy.to(d)
+        gd, bd, rmd, rvd = gamma.to(d), beta.to(d), rm.to(d), rv.to(d)
+        nb = torch.zeros((), dtype=torch.int64, device=d)
+        sums = torch.zeros(2 * C, dtype=torch.float64, device=d)
+        mean, invstd, scale, shift = (torch.zeros(C, device=d) for _ in range(4))
+        y = torch.zeros((M, C), dtype=torch.float16, device=d)
+        _lib.check(lib.rsb_bn_stats(zd.data_ptr(), sums.data_ptr(), M, C, st), "stats")
+        _lib.check(lib.rsb_bn_finalize(sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), rmd.data_ptr(), rvd.data_ptr(), nb.data_ptr(), mean.data_ptr(),
+                                       invstd.data_ptr(), scale.data_ptr(), shift.data_ptr(), C, M, 1e-5, 0.1, st), "finalize")
+        _lib.check(lib.rsb_bn_apply(zd.data_ptr(), scale.data_ptr(), shift.data_ptr(), resd.data_ptr(), y.data_ptr(), M, C, 1, st), "apply")
+        dz, gout = torch.zeros_like(y), torch.zeros_like(y)
+        dg, db = torch.zeros(C, device=d), torch.zeros(C, device=d)
+        _lib.check(lib.rsb_bn_backward(dyd.data_ptr(), y.data_ptr(), zd.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gd.data_ptr(), sums.data_ptr(),
+                                       dz.data_ptr(), gout.data_ptr(), dg.data_ptr(), db.data_ptr(), 0.5, M, C, st), "bwd")
+        torch.cuda.synchronize()
+        yr = y_ref.detach().reshape(C, M).t()
+        assert (y.float().cpu() - yr).abs().max().item() <= 4e-3 * max(1.0, yr.abs().max().item() / 4)
+        assert torch.allclose(rmd.cpu(), rm_ref, atol=1e-5) and torch.allclose(rvd.cpu(), rv_ref, rtol=1e-4, atol=1e-5) and int(nb.item()) == 1
+        assert _rel(dz.float().cpu(), zt.grad.reshape(C, M).t()) < 3e-3
+        assert _rel(dg.cpu() * 2, gt.grad) < 2e-3 and _rel(db.cpu() * 2, bt.grad) < 2e-3
+        mask = (yr > 0).float()
+        assert _rel(gout.float().cpu(), dy.float() * mask) < 1e-3
+
+
+def test_relu_maxpool_final_pack_kernels(cuda_device):
+    lib, st, d = _lib.load(), _lib.current_stream_ptr(), cuda_device
+    g = torch.Generator().manual_seed(1)
+    # relu backward with fan-in
+    a, b, y = (torch.randn((4096,), generator=g).half() for _ in range(3))
+    out = torch.zeros(4096, dtype=torch.float16, device=d)
+    _lib.check(lib.rsb_relu_backward(a.to(d).data_ptr(), b.to(d).data_ptr(), y.to(d).data_ptr(), out.data_ptr(), 4096, st), "relu_bwd")
+    torch.cuda.synchronize()
+    assert torch.equal(out.cpu(), ((a.float() + b.float()) * (y.float() > 0)).half())
+    # max-pool backward (both pools of the network)
+    for (N, H, W, C, k, s, p) in [(2, 16, 16, 64, 3, 2, 1), (2, 4, 4, 128, 2, 2, 0)]:
+        x = torch.randn((N, C, H, W), generator=g).half().float().requires_grad_(True)
+        yy = F.max_pool2d(x, k, s, p)
+        dy = torch.randn(yy.shape, generator=g).half()
+        yy.backward(dy.float())
+        xd = x.detach().permute(0, 2, 3, 1).contiguous().half().to(d)
+        dyd = dy.permute(0, 2, 3, 1).contiguous().to(d)
+        dx = torch.zeros_like(xd)
+        _lib.check(lib.rsb_maxpool_backward(xd.data_ptr(), dyd.data_ptr(), dx.data_ptr(), N, H, W, C, k, s, p, st), "maxpool_bwd")
+        torch.cuda.synchronize()
+        assert (dx.float().cpu().permute(0, 3, 1, 2) - x.grad).abs().max().item() <= 2e-3
+    # final 1x1 forward / backward
+    N, H, W, C = 2, 16, 24, 6
+    y5 = torch.randn((N, H, W, 32), generator=g).half()
+    w = (torch.randn((C, 32), generator=g) * 0.3).requires_grad_(True)
+    bb = (torch.randn(C, generator=g) * 0.1).requires_grad_(True)
+    y5t = y5.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    ref = F.conv2d(y5t, w.reshape(C, 32, 1, 1), bb)
+    dl = torch.randn(ref.shape, generator=g) * 1e-2
+    ref.backward(dl)
+    logits = torch.zeros((N, C, H, W), device=d)
+    y5d, wd, bd = y5.to(d), w.detach().to(d), bb.detach().to(d)
+    _lib.check(lib.rsb_final_forward(y5d.data_ptr(), wd.data_ptr(), bd.data_ptr(), logits.data_ptr(), N, H * W, C, st), "final_fwd")
+    dy5 = torch.zeros_like(y5d)
+    acc = torch.zeros(C * 32 + 8, dtype=torch.float64, device=d)
+    dw, dbv = torch.zeros((C, 32), device=d), torch.zeros(C, device=d)
+    _lib.check(lib.rsb_final_backward(dl.to(d).data_ptr(), y5d.data_ptr(), wd.data_ptr(), dy5.data_ptr(), acc.data_ptr(), dw.data_ptr(), dbv.data_ptr(), 256.0,
+                                      N, H * W, C, st), "final_bwd")
+    torch.cuda.synchronize()
+    assert torch.allclose(logits.cpu(), ref.detach(), atol=1e-4)
+    assert _rel(dy5.float().cpu() / 256.0, y5t.grad.permute(0, 2, 3, 1)) < 2e-3
+    assert _rel(dw.cpu(), w.grad) < 1e-4 and _rel(dbv.cpu(), bb.grad) < 1e-5
+    # pack / unpack with the upsample-phase map (sums of up to 4 taps)
+    from robosat_b200.train_engine import map_up_fwd
+    from robosat_b200.engine import pack_upsample_phases
+
+    wt = torch.randn((8, 64, 3, 3), generator=g)
+    m = torch.from_numpy(map_up_fwd(tuple(wt.shape))).to(d)
+    dst = torch.zeros(m.shape[0], dtype=torch.float16, device=d)
+    _lib.check(lib.rsb_pack_weights(wt.to(d).data_ptr(), m.data_ptr(), dst.data_ptr(), m.shape[0], st), "pack")
+    torch.cuda.synchronize()
+    assert torch.equal(dst.cpu().reshape(32, 256), pack_upsample_phases(wt).half())
+    gp = torch.randn(m.shape[0], generator=g)
+    grad = torch.zeros_like(wt).to(d)
+    _lib.check(lib.rsb_unpack_grads(gp.to(d).data_ptr(), m.data_ptr(), grad.data_ptr(), m.shape[0], 0.5, st), "unpack")
+    torch.cuda.synchronize()
+    wref = wt.clone().requires_grad_(True)
+    (pack_upsample_phases(wref).reshape(-1) * gp * 0.5).sum().backward()
+    assert torch.allclose(grad.cpu(), wref.grad, atol=1e-5)
+
+
+@pytest.mark.parametrize("i", range(len(conv_cases.default_cases(None)) - 2))  # head cases have no packed fp16 output
+def test_wgrad_matches_cpu_emulation(i, cuda_device):
+    lib, st = _lib.load(), _lib.current_stream_ptr()
+    case = conv_cases.default_cases(cuda_device)[i]()
+    cpu = conv_cases.default_cases("cpu")[i]()
+    d = case.desc
+    g = torch.Generator().manual_seed(100 + i)
+    dy = (torch.randn(tuple(case.out.shape), generator=g) * 0.5).half()
+    K = 64 * sum(d.segs[j].cblocks for j in range(d.nseg))
+    dw = torch.zeros(d.phases * d.Cout * K, dtype=torch.float32, device=cuda_device)
+    dyd = dy.to(cuda_device)
+    plan = ctypes.c_void_p()
+    _lib.check(lib.rsb_wgrad_plan_create(ctypes.byref(d), dyd.data_ptr(), dw.data_ptr(), ctypes.byref(plan)), "wgrad_plan")
+    for _ in range(2):
+        _lib.check(lib.rsb_wgrad_run(plan, st), "wgrad_run")
+    torch.cuda.synchronize()
+    ref = torch.zeros(d.phases * d.Cout * K, dtype=torch.float32)
+    emulate.run_wgrad(cpu.desc, dy.data_ptr(), ref)
+    lib.rsb_wgrad_plan_destroy(plan)
+    assert _rel(dw.cpu(), ref) < 2e-3, case.name
+    assert (dw.cpu() - ref).abs().max().item() <= 2e-3 * ref.abs().max().item() + 1e-3
+
+
+def _engine_pair(C, B, S, device, loss_scale=1024.0):
+    sd0 = {k[7:]: v.clone() for k, v in synth.make_state_dict(C, seed=0).items()}
+    x = synth.normalize_tiles(synth.make_tiles_u8(B, S, seed=1))
+    params = {k: v.clone().to(device) for k, v in sd0.items()}
+    eng = UNetTrainEngine(params, C, B, S, S, device=device, loss_scale=loss_scale)
+    return sd0, x, params, eng
+
+
+def test_train_forward_matches_oracle_train_mode(cuda_device):
+    sd0, x, params, eng = _engine_pair(2, 2, 128, cuda_device)
+    logits = eng.forward(x.to(cuda_device)).float().cpu()
+    sd = {k: v.clone() for k, v in sd0.items()}
+    with torch.no_grad():
+        ref, feats = unet_oracle.unet_forward_train(sd, x, return_features=True)
+    assert _rel(logits, ref) < 5e-3
+    for name in ("stem", "enc1", "enc2", "enc3", "enc4", "dec1", "dec3", "dec5"):
+        t, (n, h, w, c) = eng.feats[name]
+        assert _rel(t.float().cpu().reshape(n, h, w, c).permute(0, 3, 1, 2), feats[name]) < 2e-2, name
+    # running statistics follow torch's momentum / unbiased-variance update
+    for k in ("resnet.bn1", "resnet.layer2.0.downsample.1", "resnet.layer4.2.bn3"):
+        assert torch.allclose(params[k + ".running_mean"].cpu(), sd[k + ".running_mean"], atol=3e-3)
+        assert _rel(params[k + ".running_var"].cpu(), sd[k + ".running_var"]) < 1e-2
+        assert int(params[k + ".num_batches_tracked"].item()) == int(sd0[k + ".num_batches_tracked"].item()) + 1
+
+
+@pytest.mark.parametrize("classes,size", [(2, 128), (6, 64)])
+def test_train_backward_matches_mask_frozen_autograd(classes, size, cuda_device):
+    sd0, x, params, eng = _engine_pair(classes, 2, size, cuda_device)
+    g = torch.Generator().manual_seed(3)
+    dlogits = torch.randn((2, classes, size, size), generator=g) * 1e-3
+    eng.forward(x.to(cuda_device))
+    grads = eng.backward(dlogits.to(cuda_device))
+    torch.cuda.synchronize()
+    sd = {k: v.clone() for k, v in sd0.items()}
+    for k, v in sd.items():
+        if v.dtype == torch.float32 and "running" not in k:
+            v.requires_grad_(True)
+    lo = linearized.forward(eng, sd, x)
+    (lo * dlogits).sum().backward()
+    rels = {}
+    for k, v in sd.items():
+        if v.requires_grad and not k.startswith("resnet.fc"):
+            rels[k] = _rel(grads[k].cpu(), v.grad)
+    worst = sorted(rels.items(), key=lambda kv: -kv[1])[:5]
+    print("worst parameter-gradient rel-L2:", worst, "median", float(np.median(list(rels.values()))))
+    assert len(rels) == 168  # every trainable tensor except the unused resnet.fc
+    assert worst[0][1] < 6e-2 and np.median(list(rels.values())) < 3e-2
