@@ -186,7 +186,7 @@ class UNetTrainEngine:
 
     def _grad(self, name):
         if name not in self.grads:
-            self.grads[name] = torch.zeros_like(self.params[name], dtype=torch.float32)
+            self.grads[name] = torch.zeros(tuple(self.params[name].shape), dtype=torch.float32, device=self.device)
         return self.grads[name]
 
     def _conv_op(self, name, desc):

@@ -6,8 +6,9 @@ so checkpoints written by either implementation load into the other (`module.`-p
 `nn.DataParallel`, train.py:69). `forward` (eval mode) builds -- and caches per input shape -- a `UNetEngine`
 plan from the current parameters and replays it; nothing in it is executed by torch ops.
 
-Training-mode forward/backward (batch-statistics BatchNorm, dgrad/wgrad) is not part of this round: calling the
-module in training mode raises instead of silently running elsewhere.
+In training mode (`net.train()`, robosat/tools/train.py:168) the forward runs the train-mode plan (`UNetTrainEngine`:
+batch-statistics BatchNorm with running-stat updates, activations saved in fp16) and `loss.backward()` runs its backward
+plan (BN / ReLU / max-pool backward kernels, tcgen05 dgrad and wgrad); gradients arrive in `param.grad` as fp32.
 """
 
 import torch
@@ -15,6 +16,23 @@ import torch.nn as nn
 
 from robosat_b200 import _lib
 from robosat_b200.engine import UNetEngine
+
+
+class _TrainStep(torch.autograd.Function):
+    """logits = net(images) in train mode; backward = the engine's backward plan. Parameters are passed only so that
+    autograd routes their gradients (the engine reads the live parameter storage itself)."""
+
+    @staticmethod
+    def forward(ctx, x, module, names, *params):
+        eng = module._train_engine_for(x)
+        logits = eng.forward(x.contiguous())
+        ctx.eng, ctx.names = eng, names
+        return logits.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grads = ctx.eng.backward(grad_out.contiguous().float())
+        return (None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
 class ConvRelu(nn.Module):
@@ -61,7 +79,8 @@ class UNet(nn.Module):
         self.dec5 = ConvRelu(num_filters, num_filters)
         self.final = nn.Conv2d(num_filters, num_classes, kernel_size=1)
         self._engines = {}
-        self._weights_version = 0
+        self._train_engines = {}
+        self.loss_scale = 4096.0  # activation gradients are fp16: scaled by this inside the backward plan, unscaled in param.grad
 
     # any weight change invalidates the packed plans
     def load_state_dict(self, *args, **kwargs):
@@ -71,6 +90,24 @@ class UNet(nn.Module):
 
     def invalidate_plans(self):
         self._engines.clear()
+
+    def train(self, mode=True):
+        if mode:
+            self._engines.clear()  # inference plans hold folded copies of the weights: stale once training updates them
+        return super().train(mode)
+
+    def _train_engine_for(self, x):
+        from robosat_b200.train_engine import UNetTrainEngine
+
+        key = (tuple(x.shape), x.device.index)
+        eng = self._train_engines.get(key)
+        if eng is None:
+            # live references: the plan reads the current storage of every parameter / buffer at each step
+            params = dict(self.named_parameters())
+            params.update(dict(self.named_buffers()))
+            eng = UNetTrainEngine(params, self.num_classes, x.shape[0], x.shape[2], x.shape[3], device=x.device, loss_scale=self.loss_scale)
+            self._train_engines[key] = eng
+        return eng
 
     def _engine_for(self, x):
         key = (tuple(x.shape), x.dtype, x.device.index)
@@ -87,8 +124,10 @@ class UNet(nn.Module):
         """x: fp32 [N, 3, H, W] normalised (reference API) or uint8 [N, H, W, 3] raw RGB -> fp32 [N, C, H, W] logits."""
         if x.dtype == torch.float32:
             assert x.size(-1) % 32 == 0 and x.size(-2) % 32 == 0, "image resolution has to be divisible by 32 for resnet"
-        if self.training or torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and x.requires_grad:
-            raise NotImplementedError("robosat_b200.UNet: the training forward/backward kernels are not built yet; call .eval() under torch.no_grad()")
         if not x.is_cuda:
             raise _lib.RsbError("robosat_b200.UNet runs on sm_100a kernels only (no CPU fallback); move the input to a CUDA device")
+        if self.training:
+            assert x.dtype == torch.float32, "training takes the reference's normalised fp32 NCHW tensors"
+            named = [(n, p) for n, p in self.named_parameters()]
+            return _TrainStep.apply(x, self, tuple(n for n, _ in named), *[p for _, p in named])
         return self._engine_for(x).forward(x.contiguous()).clone()

@@ -67,7 +67,8 @@ def test_prepass_u8_matches_reference_transform(cuda_device):
     dst = torch.zeros(2, 32, 36, 16, dtype=torch.float16, device=cuda_device)
     mean = (ctypes.c_float * 3)(*synth.IMAGENET_MEAN)
     std = (ctypes.c_float * 3)(*synth.IMAGENET_STD)
-    _lib.check(lib.rsb_prepass_s2d(u8.to(cuda_device).data_ptr(), 1, dst.data_ptr(), 2, 64, 64, mean, std, _lib.current_stream_ptr()), "prepass")
+    u8d = u8.to(cuda_device)
+    _lib.check(lib.rsb_prepass_s2d(u8d.data_ptr(), 1, dst.data_ptr(), 2, 64, 64, mean, std, _lib.current_stream_ptr()), "prepass")
     torch.cuda.synchronize()
     assert torch.equal(dst.cpu(), ref)
 

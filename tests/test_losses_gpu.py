@@ -98,7 +98,8 @@ def test_head_quantize_matches_numpy_digitize(cuda_device):
     o = 8
     q = torch.zeros((2, 64 - 2 * o, 96 - 2 * o), dtype=torch.uint8, device=cuda_device)
     pf = torch.zeros((2, 64 - 2 * o, 96 - 2 * o), dtype=torch.float32, device=cuda_device)
-    _lib.check(lib.rsb_head_quantize(logits.to(cuda_device).data_ptr(), q.data_ptr(), pf.data_ptr(), 2, 64, 96, o, _lib.current_stream_ptr()), "head")
+    logits_d = logits.to(cuda_device)
+    _lib.check(lib.rsb_head_quantize(logits_d.data_ptr(), q.data_ptr(), pf.data_ptr(), 2, 64, 96, o, _lib.current_stream_ptr()), "head")
     torch.cuda.synchronize()
     probs = torch.softmax(logits, dim=1).numpy()[:, 1, o:-o, o:-o]
     ref = np.digitize(probs, np.linspace(0, 1, 256)).astype(np.uint8)
@@ -111,6 +112,7 @@ def test_head_quantize_matches_numpy_digitize(cuda_device):
     # saturated probability 1.0 wraps to bin 0 exactly like .astype(np.uint8) on 256
     sat = torch.tensor([[[[-200.0]], [[200.0]]]])
     q1 = torch.zeros((1, 1, 1), dtype=torch.uint8, device=cuda_device)
-    _lib.check(lib.rsb_head_quantize(sat.to(cuda_device).data_ptr(), q1.data_ptr(), None, 1, 1, 1, 0, _lib.current_stream_ptr()), "head")
+    sat_d = sat.to(cuda_device)
+    _lib.check(lib.rsb_head_quantize(sat_d.data_ptr(), q1.data_ptr(), None, 1, 1, 1, 0, _lib.current_stream_ptr()), "head")
     torch.cuda.synchronize()
     assert int(q1.item()) == int(np.digitize(np.float32(1.0), np.linspace(0, 1, 256)).astype(np.uint8))

@@ -73,7 +73,8 @@ def test_relu_maxpool_final_pack_kernels(cuda_device):
     # relu backward with fan-in
     a, b, y = (torch.randn((4096,), generator=g).half() for _ in range(3))
     out = torch.zeros(4096, dtype=torch.float16, device=d)
-    _lib.check(lib.rsb_relu_backward(a.to(d).data_ptr(), b.to(d).data_ptr(), y.to(d).data_ptr(), out.data_ptr(), 4096, st), "relu_bwd")
+    ad, bd_, yd = a.to(d), b.to(d), y.to(d)  # keep the device copies alive until the kernel has run
+    _lib.check(lib.rsb_relu_backward(ad.data_ptr(), bd_.data_ptr(), yd.data_ptr(), out.data_ptr(), 4096, st), "relu_bwd")
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), ((a.float() + b.float()) * (y.float() > 0)).half())
     # max-pool backward (both pools of the network)
@@ -103,7 +104,8 @@ def test_relu_maxpool_final_pack_kernels(cuda_device):
     dy5 = torch.zeros_like(y5d)
     acc = torch.zeros(C * 32 + 8, dtype=torch.float64, device=d)
     dw, dbv = torch.zeros((C, 32), device=d), torch.zeros(C, device=d)
-    _lib.check(lib.rsb_final_backward(dl.to(d).data_ptr(), y5d.data_ptr(), wd.data_ptr(), dy5.data_ptr(), acc.data_ptr(), dw.data_ptr(), dbv.data_ptr(), 256.0,
+    dld = dl.to(d)
+    _lib.check(lib.rsb_final_backward(dld.data_ptr(), y5d.data_ptr(), wd.data_ptr(), dy5.data_ptr(), acc.data_ptr(), dw.data_ptr(), dbv.data_ptr(), 256.0,
                                       N, H * W, C, st), "final_bwd")
     torch.cuda.synchronize()
     assert torch.allclose(logits.cpu(), ref.detach(), atol=1e-4)
@@ -116,12 +118,14 @@ def test_relu_maxpool_final_pack_kernels(cuda_device):
     wt = torch.randn((8, 64, 3, 3), generator=g)
     m = torch.from_numpy(map_up_fwd(tuple(wt.shape))).to(d)
     dst = torch.zeros(m.shape[0], dtype=torch.float16, device=d)
-    _lib.check(lib.rsb_pack_weights(wt.to(d).data_ptr(), m.data_ptr(), dst.data_ptr(), m.shape[0], st), "pack")
+    wtd = wt.to(d)
+    _lib.check(lib.rsb_pack_weights(wtd.data_ptr(), m.data_ptr(), dst.data_ptr(), m.shape[0], st), "pack")
     torch.cuda.synchronize()
     assert torch.equal(dst.cpu().reshape(32, 256), pack_upsample_phases(wt).half())
     gp = torch.randn(m.shape[0], generator=g)
     grad = torch.zeros_like(wt).to(d)
-    _lib.check(lib.rsb_unpack_grads(gp.to(d).data_ptr(), m.data_ptr(), grad.data_ptr(), m.shape[0], 0.5, st), "unpack")
+    gpd = gp.to(d)
+    _lib.check(lib.rsb_unpack_grads(gpd.data_ptr(), m.data_ptr(), grad.data_ptr(), m.shape[0], 0.5, st), "unpack")
     torch.cuda.synchronize()
     wref = wt.clone().requires_grad_(True)
     (pack_upsample_phases(wref).reshape(-1) * gp * 0.5).sum().backward()
@@ -198,3 +202,55 @@ def test_train_backward_matches_mask_frozen_autograd(classes, size, cuda_device)
     print("worst parameter-gradient rel-L2:", worst, "median", float(np.median(list(rels.values()))))
     assert len(rels) == 168  # every trainable tensor except the unused resnet.fc
     assert worst[0][1] < 6e-2 and np.median(list(rels.values())) < 3e-2
+
+
+def test_unet_module_train_step_with_lovasz_and_adam(cuda_device):
+    """The `rs train` inner loop (train.py:172-194) on the B200 path: net.train(); outputs = net(images);
+    loss = LovaszLoss2d()(outputs, masks); loss.backward(); optimizer.step() -- loss matches the fp32 oracle at step 0,
+    gradients reach every parameter, BN buffers move, the loss goes down on a fixed batch, checkpoint layout is kept."""
+    from oracle import losses_oracle
+    from robosat_b200.losses import LovaszLoss2d
+    from robosat_b200.metrics import Metrics
+    from robosat_b200.optim import Adam
+    from robosat_b200.unet import UNet
+
+    sd = synth.make_state_dict(2, seed=0)
+    net = torch.nn.DataParallel(UNet(2, pretrained=False), device_ids=[0]).to(cuda_device)
+    net.load_state_dict(sd)
+    opt = Adam(net.parameters(), lr=1e-3)
+    opt.mark_used([not n.startswith("module.resnet.fc.") for n, _ in net.named_parameters()])
+    crit = LovaszLoss2d().to(cuda_device)
+    x = synth.normalize_tiles(synth.make_tiles_u8(2, 128, seed=1)).to(cuda_device)
+    masks = synth.make_masks(2, 128, 2, seed=3).to(cuda_device)
+    with torch.no_grad():
+        ref_logits = unet_oracle.unet_forward_train({k: v.clone() for k, v in sd.items()}, x.cpu())
+    ref_loss = float(losses_oracle.lovasz_loss(ref_logits, masks.cpu()))
+    net.train()
+    losses = []
+    metrics = Metrics(range(2))
+    rm0 = net.module.resnet.bn1.running_mean.clone()
+    for step in range(4):
+        opt.zero_grad()
+        out = net(x)
+        loss = crit(out, masks)
+        loss.backward()
+        if step == 0:
+            gnorm = {n: float(p.grad.abs().sum()) for n, p in net.named_parameters()}
+            assert all(v > 0 for n, v in gnorm.items() if not n.startswith("module.resnet.fc.")), [n for n, v in gnorm.items() if v == 0][:5]
+            assert all(gnorm[n] == 0 for n in gnorm if n.startswith("module.resnet.fc."))
+        opt.step()
+        losses.append(loss.item())
+        metrics.add_batch(masks, out.detach())
+    print("lovasz losses", losses, "oracle step-0", ref_loss)
+    assert abs(losses[0] - ref_loss) <= 5e-3 * abs(ref_loss)
+    assert losses[-1] < losses[0]
+    assert not torch.equal(net.module.resnet.bn1.running_mean, rm0)
+    assert 0.0 <= metrics.get_miou() <= 1.0
+    ckpt = {"epoch": 1, "state_dict": net.state_dict(), "optimizer": opt.state_dict()}
+    assert list(ckpt["state_dict"].keys()) == list(sd.keys()) and len(ckpt["optimizer"]["state"]) == 168
+    # eval after training uses freshly folded weights (plans invalidated by train())
+    net.eval()
+    with torch.no_grad():
+        ev = net(x)
+    ref_eval = unet_oracle.unet_forward({k: v.detach().cpu() for k, v in net.state_dict().items()}, x.cpu())
+    assert _rel(ev.float().cpu(), ref_eval) < 1e-2
