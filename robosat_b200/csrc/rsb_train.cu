@@ -15,7 +15,7 @@
 
 namespace rsb {
 
-static inline unsigned tr_blocks(int64_t total, int block, int cap = 148 * 8) {
+static inline unsigned tr_blocks(int64_t total, int block, int cap = 148 * 16) {
     int64_t b = (total + block - 1) / block;
     if (b > cap) b = cap;
     if (b < 1) b = 1;
@@ -130,19 +130,27 @@ __global__ void bn_finalize_kernel(const double* __restrict__ s0, const double* 
     }
 }
 
-// y = relu?(z * scale + shift (+ res))
+// y = relu?(z * scale + shift (+ res)). The grid stride (blocks * 256) is a multiple of C/8 (C/8 divides 256), so every
+// thread keeps the same 8 channels for its whole loop and holds their coefficients in registers.
 __global__ void bn_apply_kernel(const __half* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                                 const __half* __restrict__ res, __half* __restrict__ y, int64_t M, int C, int relu) {
     const int C8 = C / 8;
     const int64_t total = M * C8;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int col = static_cast<int>(i % C8) * 8;
+    const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int col = static_cast<int>(i0 % C8) * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        sc[e] = scale[col + e];
+        sh[e] = shift[col + e];
+    }
+    for (int64_t i = i0; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         float v[8], r[8];
         load8(z + i * 8, v);
         if (res) load8(res + i * 8, r);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            float o = v[e] * scale[col + e] + shift[col + e];
+            float o = fmaf(v[e], sc[e], sh[e]);
             if (res) o += r[e];
             v[e] = relu ? fmaxf(o, 0.f) : o;
         }
@@ -150,7 +158,8 @@ __global__ void bn_apply_kernel(const __half* __restrict__ z, const float* __res
     }
 }
 
-// dz = gamma*invstd * (g - sum_g/M - zhat * sum_gz/M), g = dy * (y > 0); optionally also writes g (identity-branch gradient)
+// dz = gamma*invstd * (g - sum_g/M - zhat * sum_gz/M) = A*g + B*z + D per channel, g = dy * (y > 0);
+// optionally also writes g (identity-branch gradient). Per-channel coefficients live in registers (see bn_apply_kernel).
 __global__ void bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, const __half* __restrict__ z,
                                     const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
                                     const double* __restrict__ s0, const double* __restrict__ s1, __half* __restrict__ dz,
@@ -158,7 +167,7 @@ __global__ void bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half*
                                     int64_t M, int C) {
     const int C8 = C / 8;
     const int64_t total = M * C8;
-    const float invM = 1.0f / static_cast<float>(M);
+    const double invM = 1.0 / static_cast<double>(M);
     if (blockIdx.x == 0) {
         // parameter gradients (unscaled fp32); written once
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -166,8 +175,19 @@ __global__ void bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half*
             dbeta[c] = static_cast<float>(s0[c]) * inv_scale;
         }
     }
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const int col = static_cast<int>(i % C8) * 8;
+    const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const int col = static_cast<int>(i0 % C8) * 8;
+    float A[8], B[8], D[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int c = col + e;
+        const float is = invstd[c], ga = gamma[c], mu = mean[c];
+        const float mg = static_cast<float>(s0[c] * invM), mgz = static_cast<float>(s1[c] * invM);
+        A[e] = ga * is;
+        B[e] = -ga * is * is * mgz;
+        D[e] = -ga * is * mg + ga * is * is * mu * mgz;
+    }
+    for (int64_t i = i0; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         float g[8], zz[8];
         load8(dy + i * 8, g);
         load8(z + i * 8, zz);
@@ -180,11 +200,7 @@ __global__ void bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half*
         if (g_out) store8(g_out + i * 8, g);
         float o[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int c = col + e;
-            const float zhat = (zz[e] - mean[c]) * invstd[c];
-            o[e] = gamma[c] * invstd[c] * (g[e] - static_cast<float>(s0[c]) * invM - zhat * static_cast<float>(s1[c]) * invM);
-        }
+        for (int e = 0; e < 8; ++e) o[e] = fmaf(A[e], g[e], fmaf(B[e], zz[e], D[e]));
         store8(dz + i * 8, o);
     }
 }
@@ -392,7 +408,7 @@ extern "C" int rsb_bn_stats(const void* z, double* sums, int64_t M, int32_t C, v
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
     if (e != cudaSuccess) return set_cuda_error(e, "bn_stats memset");
     const int rows_per_iter = 256 / (C / 8);
-    channel_reduce_kernel<0><<<tr_blocks((M + rows_per_iter - 1) / rows_per_iter, 1, 148 * 4), 256, 0, st>>>(
+    channel_reduce_kernel<0><<<tr_blocks((M + rows_per_iter - 1) / rows_per_iter, 1, 148 * 8), 256, 0, st>>>(
         static_cast<const __half*>(z), nullptr, nullptr, nullptr, nullptr, sums, sums + C, M, C);
     RSB_LAUNCH_CHECK("bn_stats launch");
     return RSB_OK;
@@ -427,7 +443,7 @@ extern "C" int rsb_bn_backward(const void* dy, const void* y, const void* z, con
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
     if (e != cudaSuccess) return set_cuda_error(e, "bn_backward memset");
     const int rows_per_iter = 256 / (C / 8);
-    channel_reduce_kernel<1><<<tr_blocks((M + rows_per_iter - 1) / rows_per_iter, 1, 148 * 4), 256, 0, st>>>(
+    channel_reduce_kernel<1><<<tr_blocks((M + rows_per_iter - 1) / rows_per_iter, 1, 148 * 8), 256, 0, st>>>(
         static_cast<const __half*>(dy), static_cast<const __half*>(y), static_cast<const __half*>(z), mean, invstd, sums, sums + C, M, C);
     bn_bwd_apply_kernel<<<tr_blocks(M * (C / 8), 256), 256, 0, st>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
                                                                    static_cast<const __half*>(z), mean, invstd, gamma, sums, sums + C,

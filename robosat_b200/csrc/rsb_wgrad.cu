@@ -207,8 +207,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
                 tmem_ld_32x32(taddr + c, r);
                 tmem_ld_wait();
                 if (valid) {
+                    // split-K reduction: 16-byte vector reductions (no return value) into the packed fp32 gradient
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) atomicAdd(drow + c + j, __uint_as_float(r[j]));
+                    for (int j = 0; j < 32; j += 4) {
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c + j), "f"(__uint_as_float(r[j])),
+                                     "f"(__uint_as_float(r[j + 1])), "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                                     : "memory");
+                    }
                 }
             }
             tc_fence_before();
@@ -304,7 +309,8 @@ extern "C" int rsb_wgrad_plan_create(const rsb_conv_desc* d, const void* dy, flo
     // split the pixel tiles so that there are a few work items per SM (each item ends with 128 x 256 fp32 atomics)
     const int sms = num_sms();
     const int base_items = kp.co_blocks * kp.phases * kp.kgroups;
-    int slices = (3 * sms + base_items - 1) / base_items;
+    // (every slice adds a full copy of the gradient tile to the reduction traffic: one wave of items is enough)
+    int slices = (sms + base_items - 1) / base_items;
     if (slices > kp.ptiles) slices = kp.ptiles;
     if (slices < 1) slices = 1;
     kp.tiles_per_slice = (kp.ptiles + slices - 1) / slices;

@@ -1,0 +1,40 @@
+"""Per-op device time of one training step (CUDA events around every op of the train engine's two op lists)."""
+import collections
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from robosat_b200 import synth  # noqa: E402
+from robosat_b200.train_engine import UNetTrainEngine  # noqa: E402
+
+B, S = int(sys.argv[1]) if len(sys.argv) > 1 else 16, 512
+dev = torch.device("cuda:0")
+params = {k[7:]: v.to(dev) for k, v in synth.make_state_dict(2, seed=0).items()}
+eng = UNetTrainEngine(params, 2, B, S, S, device=dev)
+x = synth.normalize_tiles(synth.make_tiles_u8(B, S, seed=1)).to(dev)
+dl = (torch.randn((B, 2, S, S), generator=torch.Generator().manual_seed(0)) * 1e-6).to(dev)
+for _ in range(2):
+    eng.forward(x)
+    eng.backward(dl)
+torch.cuda.synchronize()
+agg = collections.defaultdict(float)
+rows = []
+for phase, ops, kw in (("fwd", eng.fwd_ops, {"x": x}), ("bwd", eng.bwd_ops, {"dlogits": dl})):
+    for op in ops:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        eng._run([op], **kw)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        name = op[1].name if op[0] in ("conv", "wgrad") else ""
+        agg[phase + ":" + op[0]] += ms
+        if op[0] in ("conv", "wgrad"):
+            rows.append((ms, phase, op[0], name))
+print(json.dumps({k: round(v, 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}))
+rows.sort(reverse=True)
+for ms, phase, kind, name in rows[:40]:
+    print("%8.3f ms  %s %-6s %s" % (ms, phase, kind, name))
