@@ -146,6 +146,49 @@ def layer_profile(engine, x, reps=3):
     return rows
 
 
+def train_leg(dev, steps=8, warmup=3, batch=16):
+    """BASELINE.json configs[2] (rs train: 2-class, Lovasz, 3x512x512, batch 16, 1 GPU): one step = zero_grad + train-mode forward
+    + Lovasz loss + backward + Adam through the public module API. Reported beside the headline, never instead of it."""
+    import torch
+
+    from robosat_b200 import synth
+    from robosat_b200.losses import LovaszLoss2d
+    from robosat_b200.optim import Adam
+    from robosat_b200.unet import UNet
+
+    net = torch.nn.DataParallel(UNet(CLASSES, pretrained=False), device_ids=[dev.index]).to(dev)
+    net.load_state_dict(synth.make_state_dict(CLASSES, seed=0))
+    opt = Adam(net.parameters(), lr=1e-4)
+    opt.mark_used([not n.startswith("module.resnet.fc.") for n, _ in net.named_parameters()])
+    crit = LovaszLoss2d().to(dev)
+    xs = [synth.normalize_tiles(synth.make_tiles_u8(batch, TILE, seed=300 + i)).to(dev) for i in range(2)]
+    ms = [synth.make_masks(batch, TILE, CLASSES, seed=310 + i).to(dev) for i in range(2)]
+    net.train()
+
+    def step(i):
+        opt.zero_grad()
+        loss = crit(net(xs[i % 2]), ms[i % 2])
+        loss.backward()
+        opt.step()
+        return loss
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    del net, opt
+    torch.cuda.empty_cache()
+    return {"metric": "512x512 tiles/sec (train fwd+bwd, Lovasz, Adam)", "value": batch * steps / (ms_total / 1e3), "unit": "tiles/s",
+            "ms_per_step": ms_total / steps, "steps": steps, "warmup": warmup, "batch": batch, "dense_equiv_tflops": batch * steps * 500.246 / ms_total,
+            "config": "rs train: ResNet50-UNet, 2-class, Lovasz loss, 3x512x512 synthetic tiles+masks, batch=16, 1xB200", "last_loss": float(loss.detach())}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,6 +196,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary training-step measurement (configs[2])")
     ap.add_argument("--layers-out", default=None, help="write the per-layer timing table (JSON) here")
     args = ap.parse_args()
 
@@ -270,6 +314,13 @@ def main():
         if not args.no_cpu_baseline:
             cb, _ = cpu_reference_leg(steps=2, warmup=1, tiles_per_step=2)
             line["cpu_baseline"] = cb
+        if world == 1 and not args.no_train:
+            del pred
+            torch.cuda.empty_cache()
+            try:
+                line["train"] = train_leg(dev)
+            except Exception as exc:  # the headline must survive a failure of the secondary measurement
+                line["train"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

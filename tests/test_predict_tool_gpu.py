@@ -1,0 +1,58 @@
+"""`rs predict` end to end on the GPU: synthetic slippy-map directory + checkpoint + TOML configs in, paletted PNGs out,
+compared with the reference pipeline restated on the CPU (buffer_tile_image -> ToTensor/Normalize -> oracle forward ->
+softmax -> unbuffer -> np.digitize, robosat/tools/predict.py:71-113)."""
+
+import argparse
+import os
+
+import numpy as np
+import pytest
+import torch
+from PIL import Image
+
+from oracle import unet_oracle
+from robosat_b200 import colors, synth
+from robosat_b200.datasets import BufferedSlippyMapDirectory
+from robosat_b200.transforms import ImageToUint8Tensor
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rs_predict_end_to_end(tmp_path, cuda_device, monkeypatch):
+    from robosat_b200.tools import predict
+
+    tiles_dir, probs_dir = tmp_path / "tiles", tmp_path / "probs"
+    u8 = synth.make_tiles_u8(5, 256, seed=9).numpy()
+    coords = [(100, 200), (101, 200), (100, 201), (101, 201), (103, 205)]  # a 2x2 block with neighbours + one isolated tile
+    for (x, y), arr in zip(coords, u8):
+        os.makedirs(tiles_dir / "17" / str(x), exist_ok=True)
+        Image.fromarray(arr).save(tiles_dir / "17" / str(x) / ("%d.png" % y))
+    sd = synth.make_state_dict(2, seed=0)
+    ckpt = tmp_path / "checkpoint-00001-of-00001.pth"
+    torch.save({"epoch": 1, "state_dict": sd, "optimizer": {}}, ckpt)
+    (tmp_path / "model.toml").write_text("[common]\ncuda = true\nbatch_size = 2\nimage_size = 256\ncheckpoint = '%s'\n[opt]\nepochs = 1\nlr = 0.0001\nloss = 'Lovasz'\n" % tmp_path)
+    (tmp_path / "dataset.toml").write_text("[common]\ndataset = '%s'\nclasses = ['background', 'parking']\ncolors = ['denim', 'orange']\n" % tmp_path)
+    monkeypatch.setenv("RSB_GPUS", "1")
+    args = argparse.Namespace(batch_size=2, checkpoint=str(ckpt), overlap=32, tile_size=256, workers=0, tiles=str(tiles_dir), probs=str(probs_dir),
+                              model=str(tmp_path / "model.toml"), dataset=str(tmp_path / "dataset.toml"))
+    predict.main(args)
+
+    directory = BufferedSlippyMapDirectory(str(tiles_dir), transform=ImageToUint8Tensor(), size=256, overlap=32)
+    palette = colors.continuous_palette_for_color("pink", 256)
+    worst, total_diff, total_px = 0, 0, 0
+    for i in range(len(directory)):
+        image, xyz = directory[i]
+        x, y, z = (int(v) for v in xyz)
+        out = Image.open(probs_dir / str(z) / str(x) / ("%d.png" % y))
+        assert out.mode == "P" and out.size == (256, 256) and out.getpalette()[: 3 * 256] == palette
+        with torch.no_grad():
+            probs = unet_oracle.predict_probs(sd, synth.normalize_tiles(image.unsqueeze(0))).numpy()[0]
+        fg = directory.unbuffer(probs)[1]
+        ref = np.digitize(fg, np.linspace(0, 1, 256)).astype(np.uint8)
+        diff = np.abs(np.array(out).astype(np.int32) - ref.astype(np.int32))
+        worst = max(worst, int(diff.max()))
+        total_diff += int((diff > 1).sum())
+        total_px += diff.size
+    print("rs predict vs reference pipeline: worst bin difference %d, pixels off by more than one bin %d / %d" % (worst, total_diff, total_px))
+    # fp16 logits move the foreground probability by <= ~1e-2, i.e. a couple of the 255 bins on a few pixels
+    assert worst <= 4 and total_diff <= 0.01 * total_px
