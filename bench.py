@@ -87,8 +87,9 @@ def cpu_reference_leg(steps, warmup, tiles_per_step=2, threads=None):
     from oracle import unet_oracle
     from robosat_b200 import synth
 
-    if threads:
-        torch.set_num_threads(threads)
+    # torchrun exports OMP_NUM_THREADS=1: ask for every core this process may run on, explicitly
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(threads or avail)
     cores = torch.get_num_threads()
     sd = synth.make_state_dict(CLASSES, seed=0)
     x = synth.normalize_tiles(synth.make_tiles_u8(tiles_per_step, TILE, seed=1))

@@ -225,7 +225,8 @@ class UNetEngine:
         self.ops = []  # ("conv", ConvOp) | ("prepass",) | ("maxpool", src, dst, N, H, W, C, k, s, p)
         self.feats = OrderedDict()  # name -> (tensor, (N, H, W, C) logical view) for layer-wise checks
         self._keep = []
-        self._build(_strip(state_dict))
+        # packing runs on the host: accept state_dicts living on any device (e.g. straight out of the NCCL broadcast)
+        self._build({k: v.detach().cpu() for k, v in _strip(state_dict).items()})
 
     # ---------------------------------------------------------------- helpers
     def _buf(self, *shape, dtype=torch.float16):
