@@ -311,7 +311,7 @@ def main():
                 "dense_equiv_tflops": value * FWD_GFLOP_DENSE / 1e3,
                 "e2e": {"value": tiles / (e2e_ms / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": pred.h2d_bytes, "d2h_bytes_per_step": pred.d2h_bytes,
                         "wall_ms": wall_ms, "api": "TilePredictor.submit/collect (pinned uint8 in, uint8 bins out)"},
-                "gpu_launches": args.steps * pred.num_launches(), "clocks": clocks, "roofline": roof}
+                "gpu_launches": world * args.steps * pred.num_launches(), "clocks": clocks, "roofline": roof}
         if not args.no_cpu_baseline:
             cb, _ = cpu_reference_leg(steps=2, warmup=1, tiles_per_step=2)
             line["cpu_baseline"] = cb

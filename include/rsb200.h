@@ -142,6 +142,15 @@ int rsb_softmax_nchw(const float* logits, float* probs, int32_t N, int32_t C, in
 int rsb_cross_entropy(const float* logits, const int64_t* targets, const float* weight, float* loss_out, float* grad,
                       double* scratch, int32_t N, int32_t C, int32_t HW, void* stream);
 
+/* FocalLoss2d.forward (losses.py:49-50): NLLLoss(weight)((1 - softmax)^gamma * log_softmax, targets) + gradient. scratch: 2 doubles. */
+int rsb_focal(const float* logits, const int64_t* targets, const float* weight, float gamma, float* loss_out, float* grad,
+              double* scratch, int32_t N, int32_t C, int32_t HW, void* stream);
+/* mIoULoss2d.forward (losses.py:71-83): max(1 - mean_{c,n} soft-IoU, weighted cross entropy); the gradient is the one of
+ * whichever term is larger (decided on the device, no host synchronisation). scratch: rsb_miou_scratch_doubles(N, C) doubles. */
+int64_t rsb_miou_scratch_doubles(int32_t N, int32_t C);
+int rsb_miou(const float* logits, const int64_t* targets, const float* weight, float* loss_out, float* grad, double* scratch,
+             int32_t N, int32_t C, int32_t HW, void* stream);
+
 /* LovaszLoss2d.forward (losses.py:96-119) and its closed-form gradient, per image:
  * errors e = 1 - (2*onehot-1)*x over the flattened C*H*W vector, descending sort, Jaccard gradient, dot(relu(e), J).
  * workspace: rsb_lovasz_workspace_bytes(N, C, HW) bytes. loss_out: fp32 scalar (mean over N). grad optional. */

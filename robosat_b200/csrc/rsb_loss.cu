@@ -80,6 +80,159 @@ __global__ void ce_finish_kernel(const float* __restrict__ logits, const int64_t
 }
 
 // =================================================================================================
+// FocalLoss2d (losses.py:49-50): NLLLoss(weight)((1 - softmax)^gamma * log_softmax, t), weighted mean.
+// d/dx_c of f = (1-p_t)^gamma * log p_t  is  (delta_tc - p_c) * [(1-p_t)^gamma - gamma (1-p_t)^(gamma-1) p_t log p_t]
+// =================================================================================================
+__global__ void focal_reduce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets, const float* __restrict__ weight,
+                                    double* __restrict__ scratch, float gamma, int N, int C, int64_t HW) {
+    const int64_t total = static_cast<int64_t>(N) * HW;
+    double num = 0.0, den = 0.0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t n = i / HW, pix = i % HW;
+        const float* l = logits + n * C * HW + pix;
+        float m = l[0];
+        for (int c = 1; c < C; ++c) m = fmaxf(m, l[c * HW]);
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s += expf(l[c * HW] - m);
+        const int t = static_cast<int>(targets[i]);
+        const float logp = (l[static_cast<int64_t>(t) * HW] - m) - logf(s);
+        const float pt = expf(l[static_cast<int64_t>(t) * HW] - m) / s;
+        const float w = weight ? weight[t] : 1.0f;
+        num += static_cast<double>(-powf(1.0f - pt, gamma) * logp * w);
+        den += static_cast<double>(w);
+    }
+    num = warp_sum(num);
+    den = warp_sum(den);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&scratch[0], num);
+        atomicAdd(&scratch[1], den);
+    }
+}
+
+__global__ void focal_finish_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets, const float* __restrict__ weight,
+                                    const double* __restrict__ scratch, float* __restrict__ loss_out, float* __restrict__ grad, float gamma,
+                                    int N, int C, int64_t HW) {
+    const double den = scratch[1];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *loss_out = static_cast<float>(scratch[0] / den);
+    if (!grad) return;
+    const float inv_den = static_cast<float>(1.0 / den);
+    const int64_t total = static_cast<int64_t>(N) * HW;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t n = i / HW, pix = i % HW;
+        const float* l = logits + n * C * HW + pix;
+        float* g = grad + n * C * HW + pix;
+        float m = l[0];
+        for (int c = 1; c < C; ++c) m = fmaxf(m, l[c * HW]);
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s += expf(l[c * HW] - m);
+        const int t = static_cast<int>(targets[i]);
+        const float logp = (l[static_cast<int64_t>(t) * HW] - m) - logf(s);
+        const float pt = expf(l[static_cast<int64_t>(t) * HW] - m) / s;
+        const float q = 1.0f - pt;
+        const float k = powf(q, gamma) - gamma * powf(q, gamma - 1.0f) * pt * logp;
+        const float w = -(weight ? weight[t] : 1.0f) * inv_den * k;
+        for (int c = 0; c < C; ++c) {
+            const float p = expf(l[c * HW] - m) / s;
+            g[c * HW] = w * ((c == t ? 1.0f : 0.0f) - p);
+        }
+    }
+}
+
+// =================================================================================================
+// mIoULoss2d (losses.py:71-83): miou = 1 - mean_{c,n}( sum_hw softs*masks / sum_hw (softs + masks - softs*masks) ),
+// returned value = max(miou, weighted cross entropy): both are computed on the device and the larger one selects
+// which gradient the final pass writes (the reference's Python max() picks one of the two tensors).
+// sums[(n*C + c)*2 + {0,1}] = {intersection, union}; scratch[0..1] = CE numerator / denominator
+// =================================================================================================
+__global__ void miou_reduce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets, const float* __restrict__ weight,
+                                   double* __restrict__ sums, double* __restrict__ scratch, int C, int64_t HW) {
+    const int n = blockIdx.y;
+    extern __shared__ double sh[];  // [C][2]
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sh[i] = 0.0;
+    __syncthreads();
+    double num = 0.0, den = 0.0;
+    for (int64_t pix = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; pix < HW; pix += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float* l = logits + static_cast<int64_t>(n) * C * HW + pix;
+        float m = l[0];
+        for (int c = 1; c < C; ++c) m = fmaxf(m, l[c * HW]);
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s += expf(l[c * HW] - m);
+        const int t = static_cast<int>(targets[static_cast<int64_t>(n) * HW + pix]);
+        for (int c = 0; c < C; ++c) {
+            const float p = expf(l[c * HW] - m) / s;
+            if (c == t) {
+                atomicAdd(&sh[2 * c], static_cast<double>(p));   // inters: softs * masks
+                atomicAdd(&sh[2 * c + 1], 1.0);                  // unions: softs + 1 - softs
+            } else {
+                atomicAdd(&sh[2 * c + 1], static_cast<double>(p));
+            }
+        }
+        const float logp = (l[static_cast<int64_t>(t) * HW] - m) - logf(s);
+        const float w = weight ? weight[t] : 1.0f;
+        num += static_cast<double>(-logp * w);
+        den += static_cast<double>(w);
+    }
+    num = warp_sum(num);
+    den = warp_sum(den);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&scratch[0], num);
+        atomicAdd(&scratch[1], den);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&sums[static_cast<int64_t>(n) * C * 2 + i], sh[i]);
+}
+
+__global__ void miou_select_kernel(const double* __restrict__ sums, double* __restrict__ scratch, float* __restrict__ loss_out, int N, int C) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        // (inters.sum / unions.sum).mean() in fp32 like the reference
+        float acc = 0.f;
+        for (int i = 0; i < N * C; ++i) acc += static_cast<float>(sums[2 * i]) / static_cast<float>(sums[2 * i + 1]);
+        const float miou = 1.0f - acc / static_cast<float>(N * C);
+        const float ce = static_cast<float>(scratch[0] / scratch[1]);
+        // Python's max(miou, ce) returns ce only when ce > miou
+        scratch[2] = ce > miou ? 0.0 : 1.0;
+        *loss_out = ce > miou ? ce : miou;
+    }
+}
+
+__global__ void miou_grad_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets, const float* __restrict__ weight,
+                                 const double* __restrict__ sums, const double* __restrict__ scratch, float* __restrict__ grad, int N, int C,
+                                 int64_t HW) {
+    const bool use_miou = scratch[2] > 0.5;
+    const float inv_den = static_cast<float>(1.0 / scratch[1]);
+    const float inv_cn = 1.0f / static_cast<float>(N * C);
+    const int64_t total = static_cast<int64_t>(N) * HW;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t n = i / HW, pix = i % HW;
+        const float* l = logits + n * C * HW + pix;
+        float* g = grad + n * C * HW + pix;
+        float m = l[0];
+        for (int c = 1; c < C; ++c) m = fmaxf(m, l[c * HW]);
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s += expf(l[c * HW] - m);
+        const int t = static_cast<int>(targets[i]);
+        if (!use_miou) {
+            const float w = (weight ? weight[t] : 1.0f) * inv_den;
+            for (int c = 0; c < C; ++c) g[c * HW] = w * (expf(l[c * HW] - m) / s - (c == t ? 1.0f : 0.0f));
+        } else {
+            // d miou / d s_c = -(1/CN) * [ m_c / U - I (1 - m_c) / U^2 ];  dx_k = s_k (ds_k - sum_c ds_c s_c)
+            float dot = 0.f;
+            for (int c = 0; c < C; ++c) {
+                const float I = static_cast<float>(sums[(n * C + c) * 2]), U = static_cast<float>(sums[(n * C + c) * 2 + 1]);
+                const float ds = -inv_cn * (c == t ? 1.0f / U : -I / (U * U));
+                dot += ds * (expf(l[c * HW] - m) / s);
+            }
+            for (int c = 0; c < C; ++c) {
+                const float I = static_cast<float>(sums[(n * C + c) * 2]), U = static_cast<float>(sums[(n * C + c) * 2 + 1]);
+                const float ds = -inv_cn * (c == t ? 1.0f / U : -I / (U * U));
+                const float p = expf(l[c * HW] - m) / s;
+                g[c * HW] = p * (ds - dot);
+            }
+        }
+    }
+}
+
+// =================================================================================================
 // Metrics.add (metrics.py:27-41) over a batch
 // =================================================================================================
 __global__ void metrics_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets,
@@ -448,6 +601,35 @@ extern "C" int rsb_cross_entropy(const float* logits, const int64_t* targets, co
     ce_finish_kernel<<<grad ? blocks_for(total, 256) : 1, 256, 0, st>>>(logits, targets, weight, scratch, loss_out, grad, N, C, HW);
     e = cudaGetLastError();
     return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "cross_entropy launch");
+}
+
+extern "C" int rsb_focal(const float* logits, const int64_t* targets, const float* weight, float gamma, float* loss_out, float* grad,
+                         double* scratch, int32_t N, int32_t C, int32_t HW, void* stream) {
+    if (!logits || !targets || !loss_out || !scratch || N <= 0 || C <= 0 || HW <= 0) return set_error(RSB_E_INVALID, "focal: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(scratch, 0, 2 * sizeof(double), st);
+    if (e != cudaSuccess) return set_cuda_error(e, "focal memset");
+    const int64_t total = static_cast<int64_t>(N) * HW;
+    focal_reduce_kernel<<<blocks_for(total, 256), 256, 0, st>>>(logits, targets, weight, scratch, gamma, N, C, HW);
+    focal_finish_kernel<<<grad ? blocks_for(total, 256) : 1, 256, 0, st>>>(logits, targets, weight, scratch, loss_out, grad, gamma, N, C, HW);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "focal launch");
+}
+
+extern "C" int64_t rsb_miou_scratch_doubles(int32_t N, int32_t C) { return (N <= 0 || C <= 0) ? 0 : 4 + 2LL * N * C; }
+
+extern "C" int rsb_miou(const float* logits, const int64_t* targets, const float* weight, float* loss_out, float* grad, double* scratch,
+                        int32_t N, int32_t C, int32_t HW, void* stream) {
+    if (!logits || !targets || !loss_out || !scratch || N <= 0 || C <= 0 || C > 64 || HW <= 0) return set_error(RSB_E_INVALID, "miou: bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(scratch, 0, (4 + 2LL * N * C) * sizeof(double), st);
+    if (e != cudaSuccess) return set_cuda_error(e, "miou memset");
+    double* sums = scratch + 4;
+    miou_reduce_kernel<<<dim3(blocks_for(HW, 256, 64), N), 256, 2 * C * sizeof(double), st>>>(logits, targets, weight, sums, scratch, C, HW);
+    miou_select_kernel<<<1, 32, 0, st>>>(sums, scratch, loss_out, N, C);
+    if (grad) miou_grad_kernel<<<blocks_for(static_cast<int64_t>(N) * HW, 256), 256, 0, st>>>(logits, targets, weight, sums, scratch, grad, N, C, HW);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "miou launch");
 }
 
 extern "C" int rsb_metrics_count(const float* logits, const int64_t* targets, int64_t* counts, int32_t N, int32_t C, int32_t HW, void* stream) {

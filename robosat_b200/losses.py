@@ -1,9 +1,8 @@
 """Loss modules with the reference's class names and call signature (robosat/losses.py:8-119):
 `forward(inputs fp32 [N, C, H, W], targets int64 [N, H, W]) -> 0-dim tensor` supporting `.backward()` / `.item()`.
 
-LovaszLoss2d and CrossEntropyLoss2d run entirely in librsb200.so: the forward kernel pipeline also produces the
-closed-form gradient, which `backward` just scales by the incoming gradient. FocalLoss2d / mIoULoss2d stay
-selectable (train.py:97-102) but are NOT accelerated yet: they raise instead of silently running elsewhere.
+All four losses selectable in `rs train` (train.py:97-102) run entirely in librsb200.so: the forward kernel pipeline also
+produces the closed-form gradient, which `backward` just scales by the incoming gradient.
 """
 
 import torch
@@ -81,22 +80,72 @@ class LovaszLoss2d(nn.Module):
         return _LovaszFn.apply(inputs, targets)
 
 
+class _FocalFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, targets, weight, gamma):
+        if not inputs.is_cuda:
+            raise _lib.RsbError("FocalLoss2d runs on the GPU kernels only (no CPU fallback)")
+        lib = _lib.load()
+        n, c, h, w = inputs.shape
+        x = inputs.detach().contiguous().float()
+        t = targets.contiguous().long()
+        wt = weight.to(x.device).contiguous().float() if weight is not None else None
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x)
+        scratch = torch.empty(2, dtype=torch.float64, device=x.device)
+        _lib.check(lib.rsb_focal(x.data_ptr(), t.data_ptr(), wt.data_ptr() if wt is not None else None, float(gamma), loss.data_ptr(), grad.data_ptr(),
+                                 scratch.data_ptr(), n, c, h * w, _lib.current_stream_ptr()), "rsb_focal")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        return grad * grad_out, None, None, None
+
+
+class _MIoUFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, inputs, targets, weight):
+        if not inputs.is_cuda:
+            raise _lib.RsbError("mIoULoss2d runs on the GPU kernels only (no CPU fallback)")
+        lib = _lib.load()
+        n, c, h, w = inputs.shape
+        x = inputs.detach().contiguous().float()
+        t = targets.contiguous().long()
+        wt = weight.to(x.device).contiguous().float() if weight is not None else None
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        grad = torch.empty_like(x)
+        scratch = torch.empty(lib.rsb_miou_scratch_doubles(n, c), dtype=torch.float64, device=x.device)
+        _lib.check(lib.rsb_miou(x.data_ptr(), t.data_ptr(), wt.data_ptr() if wt is not None else None, loss.data_ptr(), grad.data_ptr(),
+                                scratch.data_ptr(), n, c, h * w, _lib.current_stream_ptr()), "rsb_miou")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (grad,) = ctx.saved_tensors
+        return grad * grad_out, None, None
+
+
 class FocalLoss2d(nn.Module):
-    """Kept selectable like the reference (losses.py:28-50); no B200 kernel yet -> explicit error."""
+    """Focal loss (losses.py:28-50): class-weighted NLL of (1 - softmax)^gamma * log_softmax."""
 
     def __init__(self, gamma=2, weight=None):
         super().__init__()
         self.gamma = gamma
+        self.register_buffer("weight", weight if weight is None else torch.as_tensor(weight, dtype=torch.float32))
 
     def forward(self, inputs, targets):
-        raise NotImplementedError("FocalLoss2d has no sm_100a kernel yet; use 'Lovasz' or 'CrossEntropy' in [opt].loss")
+        return _FocalFn.apply(inputs, targets, self.weight, self.gamma)
 
 
 class mIoULoss2d(nn.Module):
-    """Kept selectable like the reference (losses.py:53-83); no B200 kernel yet -> explicit error."""
+    """max(soft mIoU loss, class-weighted cross entropy) (losses.py:53-83); the larger term also provides the gradient."""
 
     def __init__(self, weight=None):
         super().__init__()
+        self.register_buffer("weight", weight if weight is None else torch.as_tensor(weight, dtype=torch.float32))
 
     def forward(self, inputs, targets):
-        raise NotImplementedError("mIoULoss2d has no sm_100a kernel yet; use 'Lovasz' or 'CrossEntropy' in [opt].loss")
+        return _MIoUFn.apply(inputs, targets, self.weight)

@@ -30,7 +30,7 @@ sys.modules["mercantile"] = shim
 sys.path.insert(0, "/root/reference")
 
 import robosat.unet as ref_unet  # noqa: E402
-from robosat.losses import CrossEntropyLoss2d, LovaszLoss2d  # noqa: E402
+from robosat.losses import CrossEntropyLoss2d, FocalLoss2d, LovaszLoss2d, mIoULoss2d  # noqa: E402
 from robosat.metrics import Metrics  # noqa: E402
 
 from robosat_b200 import synth  # noqa: E402
@@ -89,6 +89,20 @@ def main():
         res["ce_%s_weight" % tag] = w.numpy()
         res["ce_%s_loss" % tag] = np.float32(loss.item())
         res["ce_%s_grad" % tag] = logits.grad.numpy().copy()
+        logits.grad = None
+        loss = FocalLoss2d(gamma=2, weight=w)(logits, targets)
+        loss.backward()
+        res["focal_%s_loss" % tag] = np.float32(loss.item())
+        res["focal_%s_grad" % tag] = logits.grad.numpy().copy()
+        # mIoU loss: once with the logits as they are and once scaled up (confident predictions make the CE term win / lose)
+        onehot = torch.zeros(N, C, S, S).scatter_(1, targets.view(N, 1, S, S), 1.0)
+        res["miou_aligned_%s_logits" % tag] = (logits.detach() * 0.15 + onehot * 1.2).numpy()
+        for sub, scale in (("", 1.0), ("_sharp", 4.0), ("_aligned", None)):
+            lg = (logits.detach() * scale if scale is not None else torch.from_numpy(res["miou_aligned_%s_logits" % tag])).requires_grad_(True)
+            loss = mIoULoss2d(weight=w)(lg, targets)
+            loss.backward()
+            res["miou%s_%s_loss" % (sub, tag)] = np.float32(loss.item())
+            res["miou%s_%s_grad" % (sub, tag)] = lg.grad.numpy().copy()
         m = Metrics(range(C))
         for mask, output in zip(targets, logits.detach()):
             m.add(mask, output)

@@ -116,3 +116,31 @@ def test_head_quantize_matches_numpy_digitize(cuda_device):
     _lib.check(lib.rsb_head_quantize(sat_d.data_ptr(), q1.data_ptr(), None, 1, 1, 1, 0, _lib.current_stream_ptr()), "head")
     torch.cuda.synchronize()
     assert int(q1.item()) == int(np.digitize(np.float32(1.0), np.linspace(0, 1, 256)).astype(np.uint8))
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_focal_and_miou_match_reference_fixture(tag, cuda_device):
+    """FocalLoss2d (losses.py:49-50) and mIoULoss2d (losses.py:71-83, both branches of its max()) through the module API."""
+    from robosat_b200.losses import FocalLoss2d, mIoULoss2d
+
+    gold = np.load(os.path.join(GOLD, "losses.npz"))
+    targets = torch.from_numpy(gold["lovasz_%s_targets" % tag]).to(cuda_device)
+    w = torch.from_numpy(gold["ce_%s_weight" % tag])
+    logits = torch.from_numpy(gold["lovasz_%s_logits" % tag]).to(cuda_device).requires_grad_(True)
+    loss = FocalLoss2d(gamma=2, weight=w).to(cuda_device)(logits, targets)
+    loss.backward()
+    ref = float(gold["focal_%s_loss" % tag])
+    assert abs(loss.item() - ref) <= 1e-5 * abs(ref)
+    np.testing.assert_allclose(logits.grad.cpu().numpy(), gold["focal_%s_grad" % tag], rtol=1e-3, atol=2e-9)
+    branches = set()
+    for sub, scale in (("", 1.0), ("_sharp", 4.0), ("_aligned", None)):
+        base = torch.from_numpy(gold["lovasz_%s_logits" % tag]) * scale if scale is not None else torch.from_numpy(gold["miou_aligned_%s_logits" % tag])
+        lg = base.to(cuda_device).requires_grad_(True)
+        loss = mIoULoss2d(weight=w).to(cuda_device)(lg, targets)
+        loss.backward()
+        ref = float(gold["miou%s_%s_loss" % (sub, tag)])
+        assert abs(loss.item() - ref) <= 1e-5 * abs(ref)
+        np.testing.assert_allclose(lg.grad.cpu().numpy(), gold["miou%s_%s_grad" % (sub, tag)], rtol=2e-3, atol=2e-9)
+        branches.add(abs(ref - float(losses_oracle.cross_entropy_loss(lg.detach().cpu(), targets.cpu(), w))) < 1e-5 * abs(ref))
+    print("mIoU loss branches exercised for", tag, branches)
+    assert branches == {True, False}  # both the cross-entropy and the soft-IoU branch of max() occur

@@ -87,3 +87,20 @@ def test_adam_oracle_matches_reference():
     for s in range(3):
         p, m, v = losses_oracle.adam_step(p, gold["adam_grads"][s], m, v, lr=1e-4, step=s + 1)
         np.testing.assert_allclose(p, gold["adam_p%d" % (s + 1)], rtol=2e-7, atol=1e-9)
+
+
+def test_focal_and_miou_oracles_match_reference():
+    gold = np.load(os.path.join(GOLD, "losses.npz"))
+    for tag in "abc":
+        logits = torch.from_numpy(gold["lovasz_%s_logits" % tag])
+        targets = torch.from_numpy(gold["lovasz_%s_targets" % tag])
+        w = torch.from_numpy(gold["ce_%s_weight" % tag])
+        loss, grad = losses_oracle.focal_loss(logits, targets, w, gamma=2, with_grad=True)
+        assert abs(float(loss) - float(gold["focal_%s_loss" % tag])) <= 5e-6 * abs(float(gold["focal_%s_loss" % tag]))
+        np.testing.assert_allclose(grad.numpy(), gold["focal_%s_grad" % tag], rtol=2e-4, atol=1e-9)
+        for sub, scale in (("", 1.0), ("_sharp", 4.0), ("_aligned", None)):
+            lg = logits * scale if scale is not None else torch.from_numpy(gold["miou_aligned_%s_logits" % tag])
+            loss, grad = losses_oracle.miou_loss(lg, targets, w, with_grad=True)
+            ref = float(gold["miou%s_%s_loss" % (sub, tag)])
+            assert abs(float(loss) - ref) <= 5e-6 * abs(ref)
+            np.testing.assert_allclose(grad.numpy(), gold["miou%s_%s_grad" % (sub, tag)], rtol=5e-4, atol=1e-9)
