@@ -111,6 +111,40 @@ int rsb_conv_run(const rsb_conv_plan* plan, void* stream);
 int rsb_conv_run_simt_check(const rsb_conv_desc* desc, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Line-buffer variant of the same convolution for stride-1 layers with few output channels at high resolution
+ * (dec5 + final, dec4, layer1 3x3; unet.py:127, 138-141): a tile is 128 pixels of one output row, input rows live in a
+ * shared-memory ring and are fetched once for all filter taps. Same arithmetic and packed weight layout
+ * ([phase*Cout + co][(tap_h, tap_w)][ci]) as rsb_conv_*; see csrc/rsb_conv_row.cu.
+ */
+typedef struct rsb_rowconv_desc {
+    rsb_conv_src src;        /* dense NHWC view of the input (TMA zero-fills outside = padding) */
+    int32_t cin;             /* 32, 64 or 128 */
+    int32_t taps_h, taps_w;  /* 3x3, or 2x2 for the fused upsample */
+    int32_t dh0, dw0;        /* displacement of tap (0,0) for phase (0,0): -1, -1 */
+    int32_t nsub;            /* 1, or 2 column phases b (phase b adds b to dw) computed per tile */
+    int32_t nphase_a;        /* 1, or 2 row phases a (phase a adds a to dh), one per work unit */
+    const void* weights;     /* fp16 [(a*nsub + b)*Cout + co][taps_h*taps_w*cin] */
+    const float* bias;       /* fp32 [Cout] or NULL */
+    int32_t Cout;            /* 32 or 64 */
+    int32_t Wt, Ht, Nt;      /* tile-space extents */
+    void* out;               /* fp16, addressed like rsb_conv_desc.out (mode 0) */
+    int64_t out_pitch_w, out_pitch_h, out_pitch_n;
+    int32_t out_sy, out_sx;
+    int32_t relu;
+    int32_t mode;            /* 0: fp16 NHWC output; 1: head (Cout 32 -> fp32 NCHW logits through head_w / head_b) */
+    int32_t head_classes;
+    const float* head_w;
+    const float* head_b;
+    float* head_out;
+    int32_t rows_per_unit;   /* output rows per work unit (0 = default 32) */
+} rsb_rowconv_desc;
+
+typedef struct rsb_rowconv_plan rsb_rowconv_plan;
+int rsb_rowconv_plan_create(const rsb_rowconv_desc* desc, rsb_rowconv_plan** out_plan);
+void rsb_rowconv_plan_destroy(rsb_rowconv_plan* plan);
+int rsb_rowconv_run(const rsb_rowconv_plan* plan, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Input pre-pass. Replaces `images.to(device)` + the stem's NCHW read (predict.py:83, train.py:172) and,
  * for uint8 input, ToTensor + Normalize (predict.py:71-73). Writes the space-to-depth view the stem
  * convolution consumes: fp16 [N][H/2][W/2 + 4][16], pixel (hh, ww) at column ww + 2, channel

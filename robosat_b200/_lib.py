@@ -69,6 +69,38 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class RowConvDesc(ctypes.Structure):
+    _fields_ = [
+        ("src", ConvSrc),
+        ("cin", ctypes.c_int32),
+        ("taps_h", ctypes.c_int32),
+        ("taps_w", ctypes.c_int32),
+        ("dh0", ctypes.c_int32),
+        ("dw0", ctypes.c_int32),
+        ("nsub", ctypes.c_int32),
+        ("nphase_a", ctypes.c_int32),
+        ("weights", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p),
+        ("Cout", ctypes.c_int32),
+        ("Wt", ctypes.c_int32),
+        ("Ht", ctypes.c_int32),
+        ("Nt", ctypes.c_int32),
+        ("out", ctypes.c_void_p),
+        ("out_pitch_w", ctypes.c_int64),
+        ("out_pitch_h", ctypes.c_int64),
+        ("out_pitch_n", ctypes.c_int64),
+        ("out_sy", ctypes.c_int32),
+        ("out_sx", ctypes.c_int32),
+        ("relu", ctypes.c_int32),
+        ("mode", ctypes.c_int32),
+        ("head_classes", ctypes.c_int32),
+        ("head_w", ctypes.c_void_p),
+        ("head_b", ctypes.c_void_p),
+        ("head_out", ctypes.c_void_p),
+        ("rows_per_unit", ctypes.c_int32),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/rsb200.h one to one (tests/test_abi.py checks both sides)
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 SIGNATURES = {
@@ -80,6 +112,9 @@ SIGNATURES = {
     "rsb_conv_plan_info": (ctypes.c_int, [_vp] + [ctypes.POINTER(_i32)] * 4),
     "rsb_conv_run": (ctypes.c_int, [_vp, _vp]),
     "rsb_conv_run_simt_check": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp]),
+    "rsb_rowconv_plan_create": (ctypes.c_int, [ctypes.POINTER(RowConvDesc), ctypes.POINTER(_vp)]),
+    "rsb_rowconv_plan_destroy": (None, [_vp]),
+    "rsb_rowconv_run": (ctypes.c_int, [_vp, _vp]),
     "rsb_prepass_s2d": (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, ctypes.POINTER(_f32), ctypes.POINTER(_f32), _vp]),
     "rsb_maxpool_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rsb_head_quantize": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -17,7 +17,7 @@ from collections import OrderedDict
 import torch
 
 from robosat_b200 import _lib
-from robosat_b200._lib import ConvDesc, ConvSeg, ConvSrc
+from robosat_b200._lib import ConvDesc, ConvSeg, ConvSrc, RowConvDesc
 
 RESNET50_BLOCKS = (3, 4, 6, 3)
 BN_EPS = 1e-5
@@ -159,6 +159,61 @@ class ConvOp:
             pass
 
 
+class RowConvOp:
+    """Line-buffer convolution plan (csrc/rsb_conv_row.cu) with the ConvOp interface."""
+
+    def __init__(self, name, desc, keep=(), create_plan=True):
+        self.name, self.desc, self.keep = name, desc, keep
+        self.plan = ctypes.c_void_p()
+        if create_plan:
+            _lib.check(_lib.load().rsb_rowconv_plan_create(ctypes.byref(desc), ctypes.byref(self.plan)), "rsb_rowconv_plan_create[%s]" % name)
+
+    def run(self, stream):
+        _lib.check(_lib.load().rsb_rowconv_run(self.plan, stream), "rsb_rowconv_run[%s]" % self.name)
+
+    def info(self):
+        return {"grid": 0, "tiles": -(-self.desc.Wt // 128) * self.desc.Ht * self.desc.Nt * self.desc.nsub * self.desc.nphase_a, "kblocks": 0, "smem": 0}
+
+    def __del__(self):
+        try:
+            if self.plan:
+                _lib.load().rsb_rowconv_plan_destroy(self.plan)
+                self.plan = ctypes.c_void_p()
+        except Exception:
+            pass
+
+
+def make_rowconv_desc(src, cin, weights, bias, cout, tile_space, out, out_pitches, upsample=False, relu=True, head=None,
+                      out_offset_elems=0, rows_per_unit=0):
+    """3x3 stride-1 conv (upsample=False) or the fused nearest-x2 + 3x3 (upsample=True: 2x2 taps, 4 phases) on the
+    line-buffer kernel. weights: fp16 [phases*Cout][taps*cin] in the packed layout of pack_conv / pack_upsample_phases."""
+    d = RowConvDesc()
+    d.src = src
+    d.cin = cin
+    d.taps_h = d.taps_w = 2 if upsample else 3
+    d.dh0 = d.dw0 = -1
+    d.nsub = d.nphase_a = 2 if upsample else 1
+    phases = 4 if upsample else 1
+    assert weights.dtype == torch.float16 and tuple(weights.shape) == (phases * cout, d.taps_h * d.taps_w * cin), tuple(weights.shape)
+    d.weights = weights.data_ptr()
+    d.bias = bias.data_ptr() if bias is not None else None
+    d.Cout = cout
+    d.Wt, d.Ht, d.Nt = tile_space
+    d.relu = 1 if relu else 0
+    d.rows_per_unit = rows_per_unit
+    if head is None:
+        d.mode = 0
+        d.out = out.data_ptr() + 2 * out_offset_elems
+        d.out_pitch_w, d.out_pitch_h, d.out_pitch_n = out_pitches
+        d.out_sy = d.out_sx = 2 if upsample else 1
+    else:
+        head_w, head_b, head_out, classes = head
+        d.mode = 1
+        d.head_classes = classes
+        d.head_w, d.head_b, d.head_out = head_w.data_ptr(), head_b.data_ptr(), head_out.data_ptr()
+    return d
+
+
 def _src_dense(t, N, H, W, C):
     return ConvSrc(t.data_ptr(), C, W * C, H * W * C, C, W, H, N)
 
@@ -211,13 +266,14 @@ def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out
 class UNetEngine:
     """Static-shape inference plan for `UNet(num_classes)` on one GPU."""
 
-    def __init__(self, state_dict, num_classes, batch, height, width, device="cuda", plan_only=False):
+    def __init__(self, state_dict, num_classes, batch, height, width, device="cuda", plan_only=False, use_row=True):
         """plan_only=True builds buffers and descriptors on `device` without touching the GPU library
         (used by the CPU tests, which execute the descriptors with tests/emulate.py)."""
         assert height % 32 == 0 and width % 32 == 0, "image resolution has to be divisible by 32 for resnet"
         # the reference's torch.cat([enc4, center]) (unet.py:134) only works when enc4's extent is even
         assert height % 64 == 0 and width % 64 == 0, "enc4 must have even extents (input divisible by 64), as in the reference"
         self.plan_only = plan_only
+        self.use_row = use_row  # line-buffer kernel for the >= 128-pixel-wide, small-Cout layers (layer1 3x3, dec4, dec5 + final)
         if not plan_only:
             _lib.require_device()
         self.device = torch.device(device)
@@ -241,6 +297,11 @@ class UNetEngine:
 
     def _add_conv(self, name, desc, keep=()):
         op = ConvOp(name, desc, keep, create_plan=not self.plan_only)
+        self.ops.append(("conv", op))
+        return op
+
+    def _add_row(self, name, desc):
+        op = RowConvOp(name, desc, (), create_plan=not self.plan_only)
         self.ops.append(("conv", op))
         return op
 
@@ -288,7 +349,11 @@ class UNetEngine:
                 # conv2 3x3 (stride) + bn2 + relu
                 w, b = fold_bn(sd, p + ".conv2.weight", p + ".bn2")
                 t2 = self._buf(N, oH, oW, planes)
-                if stride == 1:
+                if stride == 1 and planes == 64 and self.use_row and curW >= 128:
+                    self._add_row(p + ".conv2", make_rowconv_desc(_src_dense(t1, N, curH, curW, planes), planes, dev(pack_conv(w), torch.float16),
+                                                                  dev(b, torch.float32), planes, (oW, oH, N), t2, (planes, oW * planes, oH * oW * planes)))
+                    srcs = None
+                elif stride == 1:
                     srcs = [_src_dense(t1, N, curH, curW, planes)]
                     segs = [(0, kh - 1, kw - 1, planes // 64) for kh in range(3) for kw in range(3)]
                 else:
@@ -299,9 +364,10 @@ class UNetEngine:
                             ph, dh = (kh - 1) % 2, (kh - 1) // 2
                             pw, dw = (kw - 1) % 2, (kw - 1) // 2
                             segs.append((ph * 2 + pw, dh, dw, planes // 64))
-                self._add_conv(p + ".conv2", make_conv_desc(
-                    srcs, segs, dev(pack_conv(w), torch.float16), dev(b, torch.float32), planes, 1, (oW, oH, N), t2,
-                    (planes, oW * planes, oH * oW * planes)))
+                if srcs is not None:
+                    self._add_conv(p + ".conv2", make_conv_desc(
+                        srcs, segs, dev(pack_conv(w), torch.float16), dev(b, torch.float32), planes, 1, (oW, oH, N), t2,
+                        (planes, oW * planes, oH * oW * planes)))
                 outC = planes * 4
                 w3, b3 = fold_bn(sd, p + ".conv3.weight", p + ".bn3")
                 out = self._buf(N, oH, oW, outC)
@@ -364,7 +430,12 @@ class UNetEngine:
         # dec4 writes into a W-padded buffer [N, H, W+4, 32] (pixel w at column w+1) so dec5 can read 4-pixel windows
         Wq = W + 4
         self.dec4 = self._buf(N, H, Wq, 32)
-        decoder("dec4", [(dec3, 128)], H2, W2, 32, self.dec4, (32, Wq * 32, H * Wq * 32), out_offset=32)
+        if self.use_row and W2 >= 128:
+            w4 = sd["dec4.block.block.weight"].float()
+            self._add_row("dec4", make_rowconv_desc(_src_dense(dec3, N, H2, W2, 128), 128, dev(pack_upsample_phases(w4), torch.float16), None, 32,
+                                                    (W2, H2, N), self.dec4, (32, Wq * 32, H * Wq * 32), upsample=True, out_offset_elems=32))
+        else:
+            decoder("dec4", [(dec3, 128)], H2, W2, 32, self.dec4, (32, Wq * 32, H * Wq * 32), out_offset=32)
         self.feats["dec4"] = (self.dec4, (N, H, Wq, 32))
 
         # dec5 (3x3 32->32 + relu, unet.py:139) fused with final (1x1 32->C + bias, unet.py:141) -> fp32 NCHW logits
@@ -372,11 +443,17 @@ class UNetEngine:
         self.logits = self._buf(N, self.C, H, W, dtype=torch.float32)
         head_w = dev(sd["final.weight"].float().reshape(self.C, 32), torch.float32)
         head_b = dev(sd["final.bias"].float(), torch.float32)
-        src = ConvSrc(self.dec4.data_ptr(), 32, Wq * 32, H * Wq * 32, 128, W, H, N)
-        segs = [(0, kh - 1, 0, 2) for kh in range(3)]
-        self._add_conv("dec5+final", make_conv_desc(
-            [src], segs, dev(pack_window3(w5), torch.float16), None, 32, 1, (W, H, N), None, None,
-            head=(head_w, head_b, self.logits, self.C)))
+        if self.use_row and W >= 128:
+            # the real pixels of the W-padded dec4 buffer as a dense view: column -1 / W are outside the view (zero fill)
+            src = ConvSrc(self.dec4.data_ptr() + 2 * 32, 32, Wq * 32, H * Wq * 32, 32, W, H, N)
+            self._add_row("dec5+final", make_rowconv_desc(src, 32, dev(pack_conv(w5), torch.float16), None, 32, (W, H, N), None, None,
+                                                          head=(head_w, head_b, self.logits, self.C)))
+        else:
+            src = ConvSrc(self.dec4.data_ptr(), 32, Wq * 32, H * Wq * 32, 128, W, H, N)
+            segs = [(0, kh - 1, 0, 2) for kh in range(3)]
+            self._add_conv("dec5+final", make_conv_desc(
+                [src], segs, dev(pack_window3(w5), torch.float16), None, 32, 1, (W, H, N), None, None,
+                head=(head_w, head_b, self.logits, self.C)))
 
         self._mean = (ctypes.c_float * 3)(*IMAGENET_MEAN)
         self._std = (ctypes.c_float * 3)(*IMAGENET_STD)

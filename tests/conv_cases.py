@@ -170,3 +170,74 @@ def default_cases(device):
         lambda: head_case(2, 32, 32, 2, device, seed=12),
         lambda: head_case(1, 32, 64, 6, device, seed=13),
     ]
+
+
+# --------------------------------------------------------------------------------------------------
+# line-buffer kernel cases (csrc/rsb_conv_row.cu): same arithmetic, different operand staging
+# --------------------------------------------------------------------------------------------------
+def row_conv_case(N, H, W, cin, cout, device, seed=0, bias=True, relu=True, rows_per_unit=0):
+    g = torch.Generator().manual_seed(seed)
+    x = _rand((N, cin, H, W), g).half().float()
+    w = _rand((cout, cin, 3, 3), g, (2.0 / (cin * 9)) ** 0.5)
+    b = _rand((cout,), g, 0.1) if bias else None
+    xd = _nhwc_half(x, device)
+    wp = E.pack_conv(w).half().to(device)
+    bd = b.to(device) if bias else None
+    out = torch.zeros(N, H, W, cout, dtype=torch.float16, device=device)
+    desc = E.make_rowconv_desc(E._src_dense(xd, N, H, W, cin), cin, wp, bd, cout, (W, H, N), out, (cout, W * cout, H * W * cout), relu=relu,
+                               rows_per_unit=rows_per_unit)
+
+    def ref():
+        y = F.conv2d(x, w.half().float(), b, padding=1)
+        return F.relu(y) if relu else y
+
+    return Case("row3x3_%dx%dx%d_%d-%d" % (N, H, W, cin, cout), desc, (xd, wp, bd), out, lambda t: _out_nchw(t, (N, H, W, cout)), ref)
+
+
+def row_up_case(N, lh, lw, cin, cout, device, seed=0, rows_per_unit=0):
+    g = torch.Generator().manual_seed(seed)
+    x = _rand((N, cin, lh, lw), g).half().float()
+    w = _rand((cout, cin, 3, 3), g, (2.0 / (cin * 9)) ** 0.5)
+    xd = _nhwc_half(x, device)
+    wp = E.pack_upsample_phases(w).half().to(device)
+    oH, oW = 2 * lh, 2 * lw
+    out = torch.zeros(N, oH, oW, cout, dtype=torch.float16, device=device)
+    desc = E.make_rowconv_desc(E._src_dense(xd, N, lh, lw, cin), cin, wp, None, cout, (lw, lh, N), out, (cout, oW * cout, oH * oW * cout), upsample=True,
+                               rows_per_unit=rows_per_unit)
+
+    def ref():
+        return F.relu(F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, None, padding=1))
+
+    return Case("rowup_%dx%dx%d_%d-%d" % (N, lh, lw, cin, cout), desc, (xd, wp), out, lambda t: _out_nchw(t, (N, oH, oW, cout)), ref)
+
+
+def row_head_case(N, H, W, classes, device, seed=0, rows_per_unit=0):
+    g = torch.Generator().manual_seed(seed)
+    x = _rand((N, 32, H, W), g).half().float()
+    w5 = _rand((32, 32, 3, 3), g, (2.0 / 288) ** 0.5)
+    wf = _rand((classes, 32, 1, 1), g, 0.3)
+    bf = _rand((classes,), g, 0.1)
+    xd = _nhwc_half(x, device)
+    wp = E.pack_conv(w5).half().to(device)
+    hw, hb = wf.reshape(classes, 32).contiguous().to(device), bf.to(device)
+    logits = torch.zeros(N, classes, H, W, dtype=torch.float32, device=device)
+    desc = E.make_rowconv_desc(E._src_dense(xd, N, H, W, 32), 32, wp, None, 32, (W, H, N), None, None, head=(hw, hb, logits, classes),
+                               rows_per_unit=rows_per_unit)
+
+    def ref():
+        return F.conv2d(F.relu(F.conv2d(x, w5.half().float(), None, padding=1)), wf, bf)
+
+    return Case("rowhead_%dx%dx%d_c%d" % (N, H, W, classes), desc, (xd, wp, hw, hb), logits, lambda t: t.float().cpu(), ref)
+
+
+def row_cases(device):
+    return [
+        lambda: row_conv_case(2, 40, 160, 64, 64, device, seed=31),                    # partial strip + unit boundary (32-row units)
+        lambda: row_conv_case(1, 9, 128, 64, 64, device, seed=32, rows_per_unit=4),    # several short units: ring wrap-around
+        lambda: row_conv_case(2, 20, 256, 32, 32, device, seed=33, bias=False),        # 64-byte pixel rows (SWIZZLE_64B)
+        lambda: row_conv_case(1, 12, 128, 128, 64, device, seed=34),                   # two channel blocks
+        lambda: row_up_case(2, 24, 160, 128, 32, device, seed=35, rows_per_unit=8),    # dec4: fused upsample, 2 sub-tiles, 2 row phases
+        lambda: row_up_case(1, 8, 128, 64, 64, device, seed=36),
+        lambda: row_head_case(2, 36, 192, 2, device, seed=37),                         # dec5 + final
+        lambda: row_head_case(1, 16, 128, 6, device, seed=38, rows_per_unit=5),
+    ]

@@ -82,6 +82,42 @@ def run_desc(d):
             ov[...] = np.transpose(logits, (0, 3, 1, 2))
 
 
+def run_rowdesc(d):
+    """CPU semantics of rsb_rowconv_run (line-buffer kernel): same arithmetic as run_desc, described by taps instead of segments"""
+    nph = d.nphase_a * d.nsub
+    K = d.taps_h * d.taps_w * d.cin
+    wts = _view(d.weights, (nph * d.Cout, K), (K, 1)).astype(np.float32)
+    bias = _view(d.bias, (d.Cout,), (1,), np.float32) if d.bias else None
+    src = d.src
+    sv = _view(src.ptr, (src.N, src.H, src.W, d.cin), (src.pitch_n, src.pitch_h, src.pitch_w, 1))
+    for a in range(d.nphase_a):
+        for s_ in range(d.nsub):
+            acc = np.zeros((d.Nt, d.Ht, d.Wt, d.Cout), dtype=np.float32)
+            for th in range(d.taps_h):
+                for tw in range(d.taps_w):
+                    hh = np.arange(d.Ht)[:, None] + d.dh0 + a + th
+                    ww = np.arange(d.Wt)[None, :] + d.dw0 + s_ + tw
+                    inb = (hh >= 0) & (hh < src.H) & (ww >= 0) & (ww < src.W)
+                    g = sv[:, np.clip(hh, 0, src.H - 1), np.clip(ww, 0, src.W - 1), :].astype(np.float32) * inb[None, :, :, None]
+                    k0 = (th * d.taps_w + tw) * d.cin
+                    wseg = wts[(a * d.nsub + s_) * d.Cout:(a * d.nsub + s_ + 1) * d.Cout, k0:k0 + d.cin]
+                    acc += np.tensordot(g[:d.Nt], wseg, axes=([3], [1]))
+            if bias is not None:
+                acc += bias
+            if d.relu:
+                acc = np.maximum(acc, 0)
+            if d.mode == 0:
+                base = d.out + 2 * (a * d.out_pitch_h + s_ * d.out_pitch_w)
+                ov = _view(base, (d.Nt, d.Ht, d.Wt, d.Cout), (d.out_pitch_n, d.out_sy * d.out_pitch_h, d.out_sx * d.out_pitch_w, 1), writable=True)
+                ov[...] = acc.astype(np.float16)
+            else:
+                hw = _view(d.head_w, (d.head_classes, 32), (32, 1), np.float32)
+                hb = _view(d.head_b, (d.head_classes,), (1,), np.float32)
+                logits = np.tensordot(acc, hw, axes=([3], [1])) + hb
+                ov = _view(d.head_out, (d.Nt, d.head_classes, d.Ht, d.Wt), (d.head_classes * d.Ht * d.Wt, d.Ht * d.Wt, d.Wt, 1), np.float32, writable=True)
+                ov[...] = np.transpose(logits, (0, 3, 1, 2))
+
+
 def run_engine(engine, x):
     """Execute a plan_only UNetEngine (CPU buffers) op by op; returns fp32 NCHW logits (torch)."""
     import torch
@@ -95,6 +131,8 @@ def run_engine(engine, x):
             _, src, dst, n, h, w, c, k, s, p = op
             y = F.max_pool2d(src.float().reshape(n, h, w, c).permute(0, 3, 1, 2), kernel_size=k, stride=s, padding=p)
             dst.copy_(y.permute(0, 2, 3, 1).half())
+        elif hasattr(op[1].desc, "taps_h"):
+            run_rowdesc(op[1].desc)
         else:
             run_desc(op[1].desc)
     return engine.logits.clone()

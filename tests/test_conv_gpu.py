@@ -84,3 +84,19 @@ def test_maxpool_matches_torch(cuda_device):
         _lib.check(lib.rsb_maxpool_nhwc(src.data_ptr(), dst.data_ptr(), N, H, W, C, k, s, p, _lib.current_stream_ptr()), "maxpool")
         torch.cuda.synchronize()
         assert torch.equal(dst.cpu().permute(0, 3, 1, 2), ref)
+
+
+@pytest.mark.parametrize("i", range(len(conv_cases.row_cases(None))))
+def test_row_conv_case_matches_cpu_reference(i, cuda_device):
+    """line-buffer kernel (shared-memory row ring, shifted operand windows) against the same CPU references"""
+    from robosat_b200.engine import RowConvOp
+
+    case = conv_cases.row_cases(cuda_device)[i]()
+    ref = case.ref()
+    op = RowConvOp(case.name, case.desc)
+    tol = 6e-3 * max(1.0, ref.abs().max().item() / 8)
+    for _ in range(2):
+        case.out.zero_()
+        op.run(_lib.current_stream_ptr())
+        torch.cuda.synchronize()
+        assert (case.result() - ref).abs().max().item() <= tol, case.name

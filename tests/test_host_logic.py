@@ -22,6 +22,27 @@ def test_single_conv_descriptor_semantics(i):
     assert err <= 6e-3 * max(1.0, ref.abs().max().item() / 8), (case.name, err)
 
 
+@pytest.mark.parametrize("i", range(len(conv_cases.row_cases("cpu"))))
+def test_row_conv_descriptor_semantics(i):
+    case = conv_cases.row_cases("cpu")[i]()
+    emulate.run_rowdesc(case.desc)
+    got, ref = case.result(), case.ref()
+    assert (got - ref).abs().max().item() <= 6e-3 * max(1.0, ref.abs().max().item() / 8), case.name
+
+
+def test_engine_graph_with_line_buffer_layers_matches_oracle():
+    """512-wide input: layer1 3x3, dec4 and dec5 + final take the line-buffer plan; same result as the oracle"""
+    sd = synth.make_state_dict(2, seed=0)
+    x = synth.normalize_tiles(synth.make_tiles_u8(1, 512, seed=1)[:, :64].contiguous())  # 64 x 512 strip keeps the CPU run short
+    eng = UNetEngine(sd, 2, 1, 64, 512, device="cpu", plan_only=True)
+    kinds = [type(op[1]).__name__ for op in eng.ops if op[0] == "conv"]
+    assert kinds.count("RowConvOp") == 5  # layer1.{0,1,2}.conv2, dec4, dec5+final
+    got = emulate.run_engine(eng, x)
+    with torch.no_grad():
+        ref = unet_oracle.unet_forward(sd, x)
+    assert ((got - ref).pow(2).sum().sqrt() / ref.pow(2).sum().sqrt()).item() < 5e-3
+
+
 def test_upsample_phase_decomposition_is_exact_in_fp64():
     g = torch.Generator().manual_seed(0)
     w = torch.randn(8, 5, 3, 3, generator=g, dtype=torch.float64)
