@@ -131,10 +131,13 @@ def layer_profile(engine, x, reps=3):
             continue
         c = op[1]
         d = c.desc
-        K = 64 * sum(d.segs[i].cblocks for i in range(d.nseg))
         # executed MACs: every output pixel-phase x Cout x K (padded K blocks and tile padding are executed too,
         # but only the algorithmic part is counted as useful work)
-        flops = 2.0 * d.Nt * d.Ht * d.Wt * d.phases * d.Cout * K
+        if hasattr(d, "taps_h"):  # line-buffer plan
+            K, phases, kern = d.taps_h * d.taps_w * d.cin, d.nsub * d.nphase_a, "conv_row_kernel<%d,%d,%d>" % (32 if d.cin == 32 else 64, d.Cout, d.mode)
+        else:
+            K, phases, kern = 64 * sum(d.segs[i].cblocks for i in range(d.nseg)), d.phases, "conv_tc_kernel<%d,%d>" % (d.block_n, d.mode)
+        flops = 2.0 * d.Nt * d.Ht * d.Wt * phases * d.Cout * K
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         for a, b in evs:
             a.record()
@@ -142,8 +145,8 @@ def layer_profile(engine, x, reps=3):
             b.record()
         torch.cuda.synchronize()
         ms = min(a.elapsed_time(b) for a, b in evs)
-        rows.append({"name": c.name, "block_n": d.block_n, "mode": d.mode, "ms": ms, "gflop": flops / 1e9, "tflops": flops / ms / 1e9,
-                     "tiles": c.info()["tiles"], "kblocks": c.info()["kblocks"]})
+        rows.append({"name": c.name, "kernel": kern, "block_n": getattr(d, "block_n", d.Cout), "mode": d.mode, "ms": ms, "gflop": flops / 1e9,
+                     "tflops": flops / ms / 1e9, "tiles": c.info()["tiles"], "kblocks": c.info()["kblocks"]})
     return rows
 
 
@@ -285,7 +288,7 @@ def main():
         rows = layer_profile(pred.engine, inputs[0])
         by_kernel = {}
         for r in rows:
-            k = "conv_tc_kernel<%d,%d>" % (r["block_n"], r["mode"])
+            k = r["kernel"]
             a = by_kernel.setdefault(k, {"ms": 0.0, "gflop": 0.0, "launches": 0})
             a["ms"] += r["ms"]
             a["gflop"] += r["gflop"]

@@ -64,3 +64,12 @@ def shard_range(n_items, rank, world):
     base, rem = divmod(n_items, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def allreduce_sum_(flat, world=None):
+    """In-place sum of one flat tensor over all ranks: the single data-path collective of data-parallel training
+    (replaces DataParallel's per-step reduce-add of gradients to GPU 0). The caller scales the loss by
+    1 / world beforehand, so the summed gradient is the global mean and no extra elementwise pass is needed."""
+    if dist.is_available() and dist.is_initialized() and (world or dist.get_world_size()) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    return flat

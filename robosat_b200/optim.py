@@ -37,6 +37,11 @@ class Adam(torch.optim.Optimizer):
         self._touched = [False] * len(ps)
         self._step = 0
 
+    @property
+    def flat_grad(self):
+        """all gradients as ONE contiguous fp32 tensor (what data-parallel training all-reduces in a single call)"""
+        return self._flat_g
+
     def zero_grad(self, set_to_none=False):
         self._flat_g.zero_()
         for p, (off, k) in zip(self._params, self._spans):

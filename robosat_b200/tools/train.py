@@ -1,11 +1,14 @@
 """`rs train`: same flags, configuration keys, log lines and checkpoint layout as robosat/tools/train.py:42-276.
 
-What is B200-native today: the losses (`LovaszLoss2d`, `CrossEntropyLoss2d`: sort/scan + closed-form gradient
-kernels), the metrics (one counting kernel per batch, one read-back per epoch instead of 4 syncs per sample), and
-Adam (one fused kernel over a flat arena). The network's training forward/backward (batch-statistics BatchNorm,
-dgrad, wgrad) is the next row of SURVEY.md §8 and is NOT built yet: `UNet.forward` raises in training mode, so this
-tool exits with that message instead of silently training on another implementation. Validation (eval mode, no
-grad) already runs on the B200 inference plan.
+Everything in the inner loop (train.py:163-201) runs on librsb200.so: the train-mode forward and the backward of the
+network (`UNet` -> `UNetTrainEngine`), the losses (sort/scan + closed-form gradient kernels), the metrics (one counting
+kernel per batch, one read-back per epoch instead of 4 syncs per sample) and Adam (one fused kernel over a flat arena).
+Validation runs on the inference plan.
+
+With several GPUs the tool spawns one process per GPU (the command line is unchanged; `RSB_GPUS` overrides the count):
+rank 0's weights are broadcast once, every rank trains on its shard of each epoch (DistributedSampler), the flat fp32
+gradient arena is summed with ONE NCCL all-reduce per step (loss pre-scaled by 1/world), BatchNorm statistics stay per
+rank like DataParallel's replicas, rank 0 logs and writes the checkpoints (replaces `nn.DataParallel`, train.py:69).
 """
 
 import argparse
@@ -78,8 +81,9 @@ class _ResizeCrop:
         return image
 
 
-def get_dataset_loaders(model, dataset, workers):
+def get_dataset_loaders(model, dataset, workers, rank=0, world=1):
     from torch.utils.data import DataLoader
+    from torch.utils.data.distributed import DistributedSampler
 
     target_size = (model["common"]["image_size"],) * 2
     batch_size = model["common"]["batch_size"]
@@ -99,13 +103,21 @@ def get_dataset_loaders(model, dataset, workers):
     val_dataset = SlippyMapTilesConcatenation([os.path.join(path, "validation", "images")], os.path.join(path, "validation", "labels"), transform)
     assert len(train_dataset) > 0, "at least one tile in training dataset"
     assert len(val_dataset) > 0, "at least one tile in validation dataset"
-    train_loader = DataLoader(train_dataset, batch_size=batch_size, shuffle=True, drop_last=True, num_workers=workers)
-    val_loader = DataLoader(val_dataset, batch_size=batch_size, shuffle=False, drop_last=True, num_workers=workers)
+    if world > 1:
+        ts = DistributedSampler(train_dataset, num_replicas=world, rank=rank, shuffle=True, drop_last=True)
+        vs = DistributedSampler(val_dataset, num_replicas=world, rank=rank, shuffle=False, drop_last=True)
+        train_loader = DataLoader(train_dataset, batch_size=batch_size, sampler=ts, drop_last=True, num_workers=workers)
+        val_loader = DataLoader(val_dataset, batch_size=batch_size, sampler=vs, drop_last=True, num_workers=workers)
+    else:
+        train_loader = DataLoader(train_dataset, batch_size=batch_size, shuffle=True, drop_last=True, num_workers=workers)
+        val_loader = DataLoader(val_dataset, batch_size=batch_size, shuffle=False, drop_last=True, num_workers=workers)
     return train_loader, val_loader
 
 
-def _epoch(loader, num_classes, device, net, criterion, optimizer=None):
+def _epoch(loader, num_classes, device, net, criterion, optimizer=None, world=1):
     """One pass of train() (train.py:163-201) or validate() (train.py:204-238): same bookkeeping, batched metrics."""
+    from robosat_b200.dist import allreduce_sum_
+
     training = optimizer is not None
     num_samples, running_loss = 0, torch.zeros((), dtype=torch.float32, device=device)
     metrics = Metrics(range(num_classes))
@@ -125,25 +137,60 @@ def _epoch(loader, num_classes, device, net, criterion, optimizer=None):
         assert outputs.size()[1] == num_classes, "classes for predictions and dataset are in sync"
         loss = criterion(outputs, masks)
         if training:
-            loss.backward()
+            (loss / world if world > 1 else loss).backward()
+            allreduce_sum_(optimizer.flat_grad, world)  # no-op on one GPU
             optimizer.step()
         running_loss += loss.detach()  # stays on the device: one read-back per epoch instead of one per batch
         metrics.add_batch(masks, outputs.detach())
+    if world > 1:
+        import torch.distributed as dist
+
+        # epoch totals over all ranks: 4 confusion counts + loss sum + sample count, one small all-reduce per epoch
+        counts = torch.tensor(metrics._counts(), dtype=torch.float64, device=device)
+        extra = torch.stack([running_loss.double(), torch.tensor(float(num_samples), dtype=torch.float64, device=device)])
+        both = torch.cat([counts, extra])
+        dist.all_reduce(both)
+        metrics._host = [int(v) for v in both[:4].tolist()]
+        return {"loss": both[4].item() / both[5].item(), "miou": metrics.get_miou(), "fg_iou": metrics.get_fg_iou(), "mcc": metrics.get_mcc()}
     return {"loss": running_loss.item() / num_samples, "miou": metrics.get_miou(), "fg_iou": metrics.get_fg_iou(), "mcc": metrics.get_mcc()}
 
 
 def main(args):
     model = load_config(args.model)
-    dataset = load_config(args.dataset)
     if not model["common"]["cuda"]:
         sys.exit("Error: robosat_b200 runs on CUDA devices only; set cuda = true in the model configuration")
     if not torch.cuda.is_available():
         sys.exit("Error: CUDA requested but not available")
-    device = torch.device("cuda")
+    world = int(os.environ.get("RSB_GPUS", torch.cuda.device_count()))
+    world = max(1, min(world, torch.cuda.device_count()))
+    if world == 1:
+        _run(0, 1, args, 0)
+    else:
+        import socket
+
+        import torch.multiprocessing as mp
+
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        mp.spawn(_run, args=(world, args, port), nprocs=world, join=True)
+
+
+def _run(rank, world, args, port):
+    model = load_config(args.model)
+    dataset = load_config(args.dataset)
+    torch.cuda.set_device(rank)
+    device = torch.device("cuda", rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", str(port))
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
     os.makedirs(model["common"]["checkpoint"], exist_ok=True)
 
     num_classes = len(dataset["common"]["classes"])
-    net = torch.nn.DataParallel(UNet(num_classes), device_ids=[0])  # keeps the `module.` checkpoint prefix (train.py:69)
+    net = torch.nn.DataParallel(UNet(num_classes), device_ids=[rank])  # keeps the `module.` checkpoint prefix (train.py:69)
     net = net.to(device)
 
     try:
@@ -162,6 +209,15 @@ def main(args):
         if args.resume:
             optimizer.load_state_dict(chkpt["optimizer"])
             resume = chkpt["epoch"]
+    if world > 1:
+        # every rank starts from rank 0's weights and buffers: one broadcast of the flat state (the reference re-broadcasts
+        # them on every forward through DataParallel.replicate)
+        from robosat_b200.dist import broadcast_state_dict
+
+        synced = broadcast_state_dict(net.state_dict() if rank == 0 else None, net.state_dict(), device)
+        with torch.no_grad():
+            for k, v in net.state_dict().items():
+                v.copy_(synced[k])
 
     loss_name = model["opt"]["loss"]
     if loss_name == "CrossEntropy":
@@ -175,13 +231,13 @@ def main(args):
     else:
         sys.exit("Error: Unknown [opt][loss] value !")
 
-    train_loader, val_loader = get_dataset_loaders(model, dataset, args.workers)
+    train_loader, val_loader = get_dataset_loaders(model, dataset, args.workers, rank, world)
     num_epochs = model["opt"]["epochs"]
     if resume >= num_epochs:
         sys.exit("Error: Epoch {} set in {} already reached by the checkpoint provided".format(num_epochs, args.model))
 
     history = collections.defaultdict(list)
-    log = Log(os.path.join(model["common"]["checkpoint"], "log"))
+    log = Log(os.path.join(model["common"]["checkpoint"], "log" if rank == 0 else "log.rank%d" % rank), out=sys.stdout if rank == 0 else None)
     log.log("--- Hyper Parameters on Dataset: {} ---".format(dataset["common"]["dataset"]))
     log.log("Batch Size:\t {}".format(model["common"]["batch_size"]))
     log.log("Image Size:\t {}".format(model["common"]["image_size"]))
@@ -194,19 +250,24 @@ def main(args):
     fg = dataset["common"]["classes"][1]
     for epoch in range(resume, num_epochs):
         log.log("Epoch: {}/{}".format(epoch + 1, num_epochs))
-        try:
-            train_hist = _epoch(train_loader, num_classes, device, net, criterion, optimizer)
-        except NotImplementedError as exc:
-            sys.exit("Error: {}".format(exc))
+        if world > 1:
+            train_loader.sampler.set_epoch(epoch)
+        train_hist = _epoch(train_loader, num_classes, device, net, criterion, optimizer, world=world)
         log.log("Train    loss: {:.4f}, mIoU: {:.3f}, {} IoU: {:.3f}, MCC: {:.3f}".format(
             train_hist["loss"], train_hist["miou"], fg, train_hist["fg_iou"], train_hist["mcc"]))
         for k, v in train_hist.items():
             history["train " + k].append(v)
-        val_hist = _epoch(val_loader, num_classes, device, net, criterion)
+        val_hist = _epoch(val_loader, num_classes, device, net, criterion, world=world)
         log.log("Validate loss: {:.4f}, mIoU: {:.3f}, {} IoU: {:.3f}, MCC: {:.3f}".format(
             val_hist["loss"], val_hist["miou"], fg, val_hist["fg_iou"], val_hist["mcc"]))
         for k, v in val_hist.items():
             history["val " + k].append(v)
-        _plot(os.path.join(model["common"]["checkpoint"], "history-{:05d}-of-{:05d}.png".format(epoch + 1, num_epochs)), history)
-        states = {"epoch": epoch + 1, "state_dict": net.state_dict(), "optimizer": optimizer.state_dict()}
-        torch.save(states, os.path.join(model["common"]["checkpoint"], "checkpoint-{:05d}-of-{:05d}.pth".format(epoch + 1, num_epochs)))
+        if rank == 0:
+            _plot(os.path.join(model["common"]["checkpoint"], "history-{:05d}-of-{:05d}.png".format(epoch + 1, num_epochs)), history)
+            states = {"epoch": epoch + 1, "state_dict": net.state_dict(), "optimizer": optimizer.state_dict()}
+            torch.save(states, os.path.join(model["common"]["checkpoint"], "checkpoint-{:05d}-of-{:05d}.pth".format(epoch + 1, num_epochs)))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+        dist.destroy_process_group()

@@ -50,3 +50,31 @@ def test_shard_range_covers_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def _ar_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from robosat_b200.dist import allreduce_sum_
+
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1) / world  # gradient of the loss pre-scaled by 1/world
+    allreduce_sum_(flat, world)
+    q.put((rank, flat.tolist()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_is_the_global_mean_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_ar_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    expect = [(i * 1 + i * 2) / 2 for i in range(10)]  # mean over ranks of rank-local gradients i*(rank+1)
+    assert res[0][1] == expect and res[1][1] == expect
