@@ -27,7 +27,7 @@
 namespace rsb {
 
 static constexpr int kRowTile = 128;      // output pixels per tile (one row segment)
-static constexpr int kRowSlots = 4;       // ring depth in input rows
+static constexpr int kRowMaxSlots = 16;   // ring depth in input rows is chosen per plan (latency hiding vs shared memory)
 static constexpr int kRowThreads = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 static constexpr int kRowMaxW = 16;       // weight blocks: nsub * taps * cblocks <= 16
 
@@ -39,6 +39,7 @@ struct alignas(64) RowKParams {
     int32_t dh0, dw0;
     int32_t buf_w;        // pixels per ring row = 128 + taps_w + nsub - 2
     int32_t slot_bytes;   // bytes of one (row, cblock) buffer, multiple of 1024
+    int32_t slots;        // ring depth (rows)
     int32_t wblock_bytes; // BLOCK_N * CBLK * 2
     int32_t Wt, Ht, Nt, Cout;
     int32_t wstrips, rchunks, rows_per_unit, total_units;
@@ -86,7 +87,7 @@ struct RowCfg {
     static constexpr int kChunk = BLOCK_N >= 64 ? 64 : 32;     // epilogue staging chunk (channels)
     static constexpr int kWarpChunkBytes = 32 * kChunk * 2;
     static constexpr int kStageBytes = MODE == 0 ? 4 * 2 * kWarpChunkBytes : 0;  // 4 warps x 2 store slices
-    static constexpr int kBarBytes = 256;
+    static constexpr int kBarBytes = 512;
 };
 
 template <int CBLK, int BLOCK_N, int MODE>
@@ -96,12 +97,12 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int row_bytes = p.slot_bytes * p.cblocks;            // one ring slot = all channel blocks of a row
     uint8_t* smem_rows = smem;
-    uint8_t* smem_w = smem_rows + kRowSlots * row_bytes;
+    uint8_t* smem_w = smem_rows + p.slots * row_bytes;
     const int nwblocks = p.nsub * p.taps_h * p.taps_w * p.cblocks;
     uint8_t* smem_c = smem_w + nwblocks * p.wblock_bytes;      // epilogue staging (mode 0), 1024-aligned by construction
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + Cfg::kStageBytes);
-    uint64_t* empty_bar = full_bar + kRowSlots;
-    uint64_t* wfull_bar = empty_bar + kRowSlots;
+    uint64_t* empty_bar = full_bar + kRowMaxSlots;
+    uint64_t* wfull_bar = empty_bar + kRowMaxSlots;
     uint64_t* wempty_bar = wfull_bar + 1;
     uint64_t* tmem_full_bar = wempty_bar + 1;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
         for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.tmC[i]);
-        for (int i = 0; i < kRowSlots; ++i) {
+        for (int i = 0; i < kRowMaxSlots; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
@@ -158,8 +159,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                 const int r_first = u.h_lo + p.dh0 + u.a;
                 const int r_last = u.h_hi - 1 + p.dh0 + u.a + p.taps_h - 1;
                 for (int r = r_first; r <= r_last; ++r, ++q) {
-                    const int slot = q % kRowSlots;
-                    mbar_wait(&empty_bar[slot], ((q / kRowSlots) & 1) ^ 1);
+                    const int slot = q % p.slots;
+                    mbar_wait(&empty_bar[slot], ((q / p.slots) & 1) ^ 1);
                     mbar_expect_tx(&full_bar[slot], p.cblocks * p.buf_w * Cfg::kPB);
                     for (int cb = 0; cb < p.cblocks; ++cb)
                         tma_load_4d(smem_rows + slot * row_bytes + cb * p.slot_bytes, &p.tmA, &full_bar[slot], cb * CBLK, u.w0 + p.dw0, r, u.n);
@@ -184,14 +185,14 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                     const uint32_t qrow = qbase + (h - u.h_lo);  // ring position of input row (h + dh0 + a)
                     for (int th = 0; th < p.taps_h; ++th) {
                         const uint32_t qq = qrow + th;
-                        mbar_wait(&full_bar[qq % kRowSlots], (qq / kRowSlots) & 1);
+                        mbar_wait(&full_bar[qq % p.slots], (qq / p.slots) & 1);
                     }
                     tc_fence_after();
                     for (int s = 0; s < p.nsub; ++s) {
                         const uint32_t d_tmem = tmem_base + (acc * p.nsub + s) * BLOCK_N;
                         bool first = true;
                         for (int th = 0; th < p.taps_h; ++th) {
-                            const uint32_t slot = (qrow + th) % kRowSlots;
+                            const uint32_t slot = (qrow + th) % p.slots;
                             for (int tw = 0; tw < p.taps_w; ++tw) {
                                 for (int cb = 0; cb < p.cblocks; ++cb) {
                                     const uint32_t a_addr = smem_u32(smem_rows + slot * row_bytes + cb * p.slot_bytes) + (tw + s) * Cfg::kPB;
@@ -208,9 +209,9 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                         }
                     }
                     // the oldest ring row is not needed by later output rows of this strip
-                    umma_commit(&empty_bar[qrow % kRowSlots]);
+                    umma_commit(&empty_bar[qrow % p.slots]);
                     if (h == u.h_hi - 1) {
-                        for (int th = 1; th < p.taps_h; ++th) umma_commit(&empty_bar[(qrow + th) % kRowSlots]);
+                        for (int th = 1; th < p.taps_h; ++th) umma_commit(&empty_bar[(qrow + th) % p.slots]);
                         umma_commit(wempty_bar);
                     }
                     umma_commit(&tmem_full_bar[acc]);
@@ -358,7 +359,6 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     if (!(d->Cout == 32 || d->Cout == 64)) return set_error(RSB_E_INVALID, "rowconv: Cout must be 32 or 64");
     if (d->taps_h < 1 || d->taps_h > 3 || d->taps_w < 1 || d->taps_w > 3) return set_error(RSB_E_INVALID, "rowconv: taps must be 1..3");
     if (d->nsub < 1 || d->nsub > 2 || d->nphase_a < 1 || d->nphase_a > 2) return set_error(RSB_E_INVALID, "rowconv: nsub / nphase_a must be 1 or 2");
-    if (d->taps_h + 1 > kRowSlots) return set_error(RSB_E_INVALID, "rowconv: ring too small for taps_h");
     const int cblk = d->cin == 32 ? 32 : 64;
     const int cblocks = d->cin / cblk;
     if (d->nsub * d->taps_h * d->taps_w * cblocks > kRowMaxW) return set_error(RSB_E_INVALID, "rowconv: too many weight blocks");
@@ -389,7 +389,7 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     kp.Nt = d->Nt;
     kp.Cout = d->Cout;
     kp.wstrips = (d->Wt + kRowTile - 1) / kRowTile;
-    kp.rows_per_unit = d->rows_per_unit > 0 ? d->rows_per_unit : 32;
+    kp.rows_per_unit = d->rows_per_unit > 0 ? d->rows_per_unit : 64;
     kp.rchunks = (d->Ht + kp.rows_per_unit - 1) / kp.rows_per_unit;
     kp.total_units = d->Nt * kp.wstrips * kp.rchunks * d->nphase_a;
     kp.relu = d->relu;
@@ -435,14 +435,29 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     plan->cblk = cblk;
     plan->block_n = d->Cout;
     plan->mode = d->mode;
+    // shared memory: weights + epilogue staging are fixed; the ring takes the rest. Small layers run several CTAs per SM
+    // (each with its own ring) so that TMA latency and the single MMA-issuing thread of one CTA are hidden by the others.
     const int stage = d->mode == 0 ? 4 * 2 * 32 * (d->Cout >= 64 ? 64 : 32) * 2 : 0;
-    plan->smem = kRowSlots * kp.slot_bytes * cblocks + d->nsub * d->taps_h * d->taps_w * cblocks * kp.wblock_bytes + stage + 256 + 1024;
-    if (plan->smem > 232448) {
-        delete plan;
-        return set_error(RSB_E_INVALID, "rowconv: needs %d bytes of shared memory", plan->smem);
+    const int fixed = d->nsub * d->taps_h * d->taps_w * cblocks * kp.wblock_bytes + stage + 512 + 1024;
+    const int row_bytes = kp.slot_bytes * cblocks;
+    const int tmem_cols = 4 * d->Cout <= 128 ? 128 : 256;
+    int ctas = 1;
+    for (int c = 3; c >= 2; --c) {
+        if (c * tmem_cols <= 512 && fixed + (d->taps_h + 3) * row_bytes <= 232448 / c - 1024) {
+            ctas = c;
+            break;
+        }
     }
+    int slots = (232448 / ctas - 1024 - fixed) / row_bytes;
+    if (slots > kRowMaxSlots) slots = kRowMaxSlots;
+    if (slots < d->taps_h + 1) {
+        delete plan;
+        return set_error(RSB_E_INVALID, "rowconv: needs %d bytes of shared memory for a %d-row ring", fixed + (d->taps_h + 1) * row_bytes, d->taps_h + 1);
+    }
+    kp.slots = slots;
+    plan->smem = slots * row_bytes + fixed;
     const int sms = num_sms();
-    plan->grid = kp.total_units < sms ? kp.total_units : sms;
+    plan->grid = kp.total_units < ctas * sms ? kp.total_units : ctas * sms;
     *out_plan = plan;
     return RSB_OK;
 }
