@@ -56,13 +56,14 @@ struct RowUnit {
 };
 
 __device__ __forceinline__ RowUnit row_decode(const RowKParams& p, int id) {
+    // the row phase is the slowest index: a CTA's consecutive units share their resident weights
     RowUnit u;
-    u.a = id % p.nphase_a;
-    id /= p.nphase_a;
     const int ws = id % p.wstrips;
     id /= p.wstrips;
     const int rc = id % p.rchunks;
-    u.n = id / p.rchunks;
+    id /= p.rchunks;
+    u.n = id % p.Nt;
+    u.a = id / p.Nt;
     u.w0 = ws * kRowTile;
     u.h_lo = rc * p.rows_per_unit;
     u.h_hi = min(p.Ht, u.h_lo + p.rows_per_unit);
@@ -140,20 +141,25 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         // ------------------------------------------------------------------ TMA producer
         if (elect_one()) {
             uint32_t q = 0;  // rows loaded so far (ring position)
-            uint32_t wq = 0; // units whose weights have been loaded
-            for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++wq) {
+            uint32_t wq = 0; // weight sets loaded so far
+            int cur_a = -1;
+            for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
                 const RowUnit u = row_decode(p, unit);
-                // resident weights of this unit: nsub x taps x cblocks blocks of [BLOCK_N][CBLK]
-                mbar_wait(wempty_bar, (wq & 1) ^ 1);
-                mbar_expect_tx(wfull_bar, nwblocks * p.wblock_bytes);
-                for (int s = 0; s < p.nsub; ++s) {
-                    const int brow = (u.a * p.nsub + s) * p.Cout;
-                    for (int t = 0; t < p.taps_h * p.taps_w; ++t) {
-                        for (int cb = 0; cb < p.cblocks; ++cb) {
-                            const int blk = (s * p.taps_h * p.taps_w + t) * p.cblocks + cb;
-                            tma_load_2d(smem_w + blk * p.wblock_bytes, &p.tmB, wfull_bar, (t * p.cblocks + cb) * CBLK, brow);
+                if (u.a != cur_a) {
+                    // resident weights of this row phase: nsub x taps x cblocks blocks of [BLOCK_N][CBLK]
+                    cur_a = u.a;
+                    mbar_wait(wempty_bar, (wq & 1) ^ 1);
+                    mbar_expect_tx(wfull_bar, nwblocks * p.wblock_bytes);
+                    for (int s = 0; s < p.nsub; ++s) {
+                        const int brow = (u.a * p.nsub + s) * p.Cout;
+                        for (int t = 0; t < p.taps_h * p.taps_w; ++t) {
+                            for (int cb = 0; cb < p.cblocks; ++cb) {
+                                const int blk = (s * p.taps_h * p.taps_w + t) * p.cblocks + cb;
+                                tma_load_2d(smem_w + blk * p.wblock_bytes, &p.tmB, wfull_bar, (t * p.cblocks + cb) * CBLK, brow);
+                            }
                         }
                     }
+                    ++wq;
                 }
                 // input rows of the strip, in order; each row = cblocks boxes of buf_w pixels
                 const int r_first = u.h_lo + p.dh0 + u.a;
@@ -174,10 +180,17 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
             uint32_t qbase = 0, wq = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x, ++wq) {
+            int cur_a = -1;
+            for (int unit = blockIdx.x; unit < p.total_units; unit += gridDim.x) {
                 const RowUnit u = row_decode(p, unit);
-                mbar_wait(wfull_bar, wq & 1);
-                tc_fence_after();
+                if (u.a != cur_a) {
+                    cur_a = u.a;
+                    mbar_wait(wfull_bar, wq & 1);
+                    tc_fence_after();
+                    ++wq;
+                }
+                const int next_unit = unit + gridDim.x;
+                const bool last_of_set = next_unit >= p.total_units || row_decode(p, next_unit).a != u.a;
                 const int nrows_in = (u.h_hi - u.h_lo) + p.taps_h - 1;
                 for (int h = u.h_lo; h < u.h_hi; ++h) {
                     mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -212,7 +225,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                     umma_commit(&empty_bar[qrow % p.slots]);
                     if (h == u.h_hi - 1) {
                         for (int th = 1; th < p.taps_h; ++th) umma_commit(&empty_bar[(qrow + th) % p.slots]);
-                        umma_commit(wempty_bar);
+                        if (last_of_set) umma_commit(wempty_bar);  // the resident weights may be replaced
                     }
                     umma_commit(&tmem_full_bar[acc]);
                     if (++acc == 2) {
@@ -389,9 +402,7 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     kp.Nt = d->Nt;
     kp.Cout = d->Cout;
     kp.wstrips = (d->Wt + kRowTile - 1) / kRowTile;
-    kp.rows_per_unit = d->rows_per_unit > 0 ? d->rows_per_unit : 64;
-    kp.rchunks = (d->Ht + kp.rows_per_unit - 1) / kp.rows_per_unit;
-    kp.total_units = d->Nt * kp.wstrips * kp.rchunks * d->nphase_a;
+    kp.rows_per_unit = d->rows_per_unit;  // 0: chosen below, once the number of resident CTAs is known
     kp.relu = d->relu;
     kp.bias = d->bias;
     kp.head_classes = d->head_classes;
@@ -457,6 +468,19 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     kp.slots = slots;
     plan->smem = slots * row_bytes + fixed;
     const int sms = num_sms();
+    if (kp.rows_per_unit <= 0) {
+        // units of consecutive rows: long enough to amortise the (taps_h - 1)-row halo, short enough for ~6 waves of units
+        kp.rows_per_unit = 8;
+        for (int r = 32; r >= 8; r /= 2) {
+            const int units = d->Nt * kp.wstrips * ((d->Ht + r - 1) / r) * d->nphase_a;
+            if (units >= 6 * ctas * sms) {
+                kp.rows_per_unit = r;
+                break;
+            }
+        }
+    }
+    kp.rchunks = (d->Ht + kp.rows_per_unit - 1) / kp.rows_per_unit;
+    kp.total_units = d->Nt * kp.wstrips * kp.rchunks * d->nphase_a;
     plan->grid = kp.total_units < ctas * sms ? kp.total_units : ctas * sms;
     *out_plan = plan;
     return RSB_OK;
