@@ -56,14 +56,15 @@ struct RowUnit {
 };
 
 __device__ __forceinline__ RowUnit row_decode(const RowKParams& p, int id) {
-    // the row phase is the slowest index: a CTA's consecutive units share their resident weights
+    // the row phase is the FASTEST index: neighbouring CTAs work on the two row phases of the same strip at the same time
+    // (the input rows they share are served by L2), and with an even grid every CTA keeps one phase = one resident weight set
     RowUnit u;
+    u.a = id % p.nphase_a;
+    id /= p.nphase_a;
     const int ws = id % p.wstrips;
     id /= p.wstrips;
     const int rc = id % p.rchunks;
-    id /= p.rchunks;
-    u.n = id % p.Nt;
-    u.a = id / p.Nt;
+    u.n = id / p.rchunks;
     u.w0 = ws * kRowTile;
     u.h_lo = rc * p.rows_per_unit;
     u.h_hi = min(p.Ht, u.h_lo + p.rows_per_unit);
@@ -469,11 +470,11 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     plan->smem = slots * row_bytes + fixed;
     const int sms = num_sms();
     if (kp.rows_per_unit <= 0) {
-        // units of consecutive rows: long enough to amortise the (taps_h - 1)-row halo, short enough for ~6 waves of units
+        // units of consecutive rows: as long as possible (halo rows, ring refill) while still filling every resident CTA
         kp.rows_per_unit = 8;
         for (int r = 32; r >= 8; r /= 2) {
             const int units = d->Nt * kp.wstrips * ((d->Ht + r - 1) / r) * d->nphase_a;
-            if (units >= 6 * ctas * sms) {
+            if (units >= ctas * sms) {
                 kp.rows_per_unit = r;
                 break;
             }
@@ -482,6 +483,7 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     kp.rchunks = (d->Ht + kp.rows_per_unit - 1) / kp.rows_per_unit;
     kp.total_units = d->Nt * kp.wstrips * kp.rchunks * d->nphase_a;
     plan->grid = kp.total_units < ctas * sms ? kp.total_units : ctas * sms;
+    if (d->nphase_a == 2 && plan->grid > 1) plan->grid &= ~1;  // even grid: a CTA's units all have the same row phase
     *out_plan = plan;
     return RSB_OK;
 }
