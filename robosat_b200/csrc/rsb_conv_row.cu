@@ -474,7 +474,7 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
         kp.rows_per_unit = 8;
         for (int r = 32; r >= 8; r /= 2) {
             const int units = d->Nt * kp.wstrips * ((d->Ht + r - 1) / r) * d->nphase_a;
-            if (units >= ctas * sms) {
+            if (4 * units >= 3 * ctas * sms) {
                 kp.rows_per_unit = r;
                 break;
             }

@@ -1,6 +1,6 @@
 """One predict step (batch 32 of 3x512x512) after 3 warm-up steps: the target command for ncu captures.
 
-    ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'conv_tc|maxpool|prepass|head_quant' -s 192 -c 64 \
+    ncu --metrics gpu__time_duration.sum --clock-control none -k regex:'conv_tc|conv_row|maxpool|prepass|head_quant' -s 192 -c 64 \
         --csv --log-file gpurun_out/launches.csv python scripts/profile_step.py
 """
 import os
