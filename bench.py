@@ -297,8 +297,14 @@ def main():
         dk = by_kernel[dom]
         conv_ms = sum(r["ms"] for r in rows)
         conv_tf = sum(r["gflop"] for r in rows) / conv_ms
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+            ent = json.load(open(tpath)).get("kernels", {}).get(dom)
+            if ent:
+                traffic = {"value": ent["mb_per_launch"], "unit": "MB per launch (ncu dram read+write)", "source": "profiles/ncu_traffic.json"}
         roof = {"bound": "tensor", "kernel": dom, "achieved": dk["gflop"] / dk["ms"], "peak": pk["tflops"], "unit": "TFLOP/s",
-                "frac": dk["gflop"] / dk["ms"] / pk["tflops"], "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                "frac": dk["gflop"] / dk["ms"] / pk["tflops"], "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
                 "launches_per_step": dk["launches"], "ms_per_step": dk["ms"], "all_conv_tflops": conv_tf, "all_conv_ms": conv_ms,
                 "flops": "executed (sub-pixel decoder: 100.7 GFLOP/tile, not the 167.16 dense-equivalent)"}
         if args.layers_out:

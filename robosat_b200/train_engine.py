@@ -163,6 +163,11 @@ class UNetTrainEngine:
         self.params = params
         self.loss_scale = float(loss_scale)
         self.fwd_ops, self.bwd_ops = [], []
+        self.pack_list, self.unpack_list = [], []  # (wname, map, packed fp16) / (packed fp32 grad, map, wname)
+        self._pack_all = None
+        self._pack_chunks = []  # [fp16 arena tensor, elements used]
+        self._dw_chunks = []    # [fp32 arena tensor, elements used] packed weight gradients
+        self._grads_flat, self._grad_offset, self._unpack_all = None, {}, None
         self._keep = []
         self.grads = OrderedDict()
         self.units = OrderedDict()
@@ -185,17 +190,37 @@ class UNetTrainEngine:
         return t
 
     def _grad(self, name):
-        if name not in self.grads:
-            self.grads[name] = torch.zeros(tuple(self.params[name].shape), dtype=torch.float32, device=self.device)
+        """fp32 gradient of parameter `name`: a view of ONE flat buffer (zeroed with a single memset per backward)"""
+        if self._grads_flat is None:
+            names = [k for k, v in self.params.items()
+                     if v.dtype == torch.float32 and not k.endswith("running_mean") and not k.endswith("running_var") and not k.startswith("resnet.fc.")]
+            total = sum(self.params[k].numel() for k in names)
+            self._grads_flat = torch.zeros(total, dtype=torch.float32, device=self.device)
+            off = 0
+            for k in names:
+                n = self.params[k].numel()
+                self.grads[k] = self._grads_flat[off:off + n].view(tuple(self.params[k].shape))
+                self._grad_offset[k] = off
+                off += n
         return self.grads[name]
 
     def _conv_op(self, name, desc):
         return ConvOp(name, desc, (), create_plan=not self.plan_only)
 
     def _packed(self, wname, map4):
-        """(packed fp16 buffer, device map) for parameter `wname`; a ("pack", ...) op refreshes it every step"""
+        """(packed fp16 buffer, device map) for parameter `wname`; refreshed from the fp32 master weights once per step
+        by the ("pack_all",) op at the head of the forward program (one launch for every operand layout of every layer when
+        the parameters live in one arena, e.g. robosat_b200.optim.Adam's)"""
         m = self._dev(map4, torch.int32)
-        dst = self._buf(m.shape[0])
+        n = m.shape[0]
+        # bump-allocate the packed buffer inside a shared fp16 arena chunk (16-byte aligned for TMA)
+        chunk_elems = 48 * 1024 * 1024
+        if not self._pack_chunks or self._pack_chunks[-1][1] + n > self._pack_chunks[-1][0].numel():
+            self._pack_chunks.append([self._buf(max(chunk_elems, n)), 0])
+        chunk, used = self._pack_chunks[-1]
+        dst = chunk[used:used + n]
+        self._pack_chunks[-1][1] = used + ((n + 7) // 8) * 8
+        self.pack_list.append((wname, m, dst, len(self._pack_chunks) - 1, used))
         return dst, m
 
     # ---------------------------------------------------------------- unit construction
@@ -212,17 +237,23 @@ class UNetTrainEngine:
         u.desc = make_conv_desc(srcs, segs, wp, None, cout, phases, tile_space, out, out_pitches, out_scale=out_scale, relu=relu,
                                 out_offset_elems=out_offset, residual=residual)
         u.fwd = self._conv_op(name, u.desc)
-        u.dw_packed = self._buf(phases * cout * K, dtype=torch.float32)
+        nd = phases * cout * K
+        if not self._dw_chunks or self._dw_chunks[-1][1] + nd > self._dw_chunks[-1][0].numel():
+            self._dw_chunks.append([self._buf(max(32 * 1024 * 1024, nd), dtype=torch.float32), 0])
+        dchunk, dused = self._dw_chunks[-1]
+        u.dw_packed = dchunk[dused:dused + nd]
+        u.dw_chunk, u.dw_off = len(self._dw_chunks) - 1, dused
+        self._dw_chunks[-1][1] = dused + ((nd + 3) // 4) * 4
         u.out, u.out_offset = out, out_offset
         self.units[name] = u
-        self.fwd_ops.append(("pack", wname, u.fwd_map, u.w_packed))
         self.fwd_ops.append(("conv", u.fwd))
         return u
 
     def _wgrad_ops(self, u, dy):
         """weight gradient of unit u from dy (addressed like u's forward output), unpacked into the OIHW gradient"""
         self._grad(u.wname)
-        return [("wgrad", u, dy), ("unpack", u.dw_packed, u.fwd_map, u.wname, 1.0 / self.loss_scale)]
+        self.unpack_list.append((u.dw_packed, u.fwd_map, u.wname, u.dw_chunk, u.dw_off))
+        return [("wgrad", u, dy)]
 
     def _dgrad(self, name, wname, map4, srcs, segs, cout, phases, tile_space, out, out_pitches, out_scale=(1, 1), residual=None,
                out_offset=0):
@@ -232,7 +263,7 @@ class UNetTrainEngine:
         desc = make_conv_desc(srcs, segs, wp.view(phases * cout, K), None, cout, phases, tile_space, out, out_pitches, out_scale=out_scale,
                               relu=False, residual=residual, out_offset_elems=out_offset)
         op = self._conv_op(name, desc)
-        return [("pack", wname, m, wp), ("conv", op)]
+        return [("conv", op)]
 
     def _bn(self, prefix, z, M, C):
         b = Unit(prefix)
@@ -259,6 +290,7 @@ class UNetTrainEngine:
         # ---- stem
         self.x_in = None
         self.s2d = self._buf(N, H2, W2 + 4, 16)
+        self.fwd_ops.append(("pack_all",))
         self.fwd_ops.append(("prepass",))
         Wp = W2 + 4
         z0 = self._buf(N, H2, W2, 64)
@@ -460,6 +492,7 @@ class UNetTrainEngine:
         self.bwd_ops.append(("relu_bwd", d_enc4, d_enc4_pool, None, d_enc4))  # plain sum (no mask)
         for ops in reversed(bwd):
             self.bwd_ops += ops
+        self.bwd_ops.append(("unpack_all",))
         self._mean = (ctypes.c_float * 3)(0.485, 0.456, 0.406)
         self._std = (ctypes.c_float * 3)(0.229, 0.224, 0.225)
 
@@ -472,9 +505,21 @@ class UNetTrainEngine:
             k = op[0]
             if k == "conv":
                 op[1].run(st)
-            elif k == "pack":
-                _, wname, m, dst = op
-                _lib.check(lib.rsb_pack_weights(P[wname].data_ptr(), m.data_ptr(), dst.data_ptr(), dst.numel(), st), "rsb_pack_weights")
+            elif k == "pack_all":
+                self._run_pack_all(lib, st)
+            elif k == "unpack_all":
+                # packed weight gradients (fp32 arena chunks) -> the flat OIHW gradient buffer: one launch per chunk
+                if self._unpack_all is None:
+                    self._grad(self.unpack_list[0][2])
+                    self._unpack_all = []
+                    for ci, (chunk, used) in enumerate(self._dw_chunks):
+                        gmap = torch.full((used, 4), -1, dtype=torch.int32, device=self.device)
+                        for dwp, m, wname, c, off in self.unpack_list:
+                            if c == ci:
+                                gmap[off:off + m.shape[0]] = torch.where(m >= 0, m + self._grad_offset[wname], m)
+                        self._unpack_all.append((gmap, chunk, used))
+                for gmap, chunk, used in self._unpack_all:
+                    _lib.check(lib.rsb_unpack_grads(chunk.data_ptr(), gmap.data_ptr(), self._grads_flat.data_ptr(), used, 1.0 / self.loss_scale, st), "rsb_unpack_grads")
             elif k == "bn_stats":
                 b = op[1]
                 _lib.check(lib.rsb_bn_stats(b.z.data_ptr(), b.sums.data_ptr(), b.M, b.C, st), "rsb_bn_stats")
@@ -512,9 +557,6 @@ class UNetTrainEngine:
                     _lib.check(lib.rsb_wgrad_plan_create(ctypes.byref(u.desc), dy.data_ptr() + 2 * u.out_offset, u.dw_packed.data_ptr(),
                                                          ctypes.byref(u.wgrad_plan)), "rsb_wgrad_plan_create[%s]" % u.name)
                 _lib.check(lib.rsb_wgrad_run(u.wgrad_plan, st), "rsb_wgrad_run[%s]" % u.name)
-            elif k == "unpack":
-                _, dwp, m, wname, mul = op
-                _lib.check(lib.rsb_unpack_grads(dwp.data_ptr(), m.data_ptr(), self._grad(wname).data_ptr(), dwp.numel(), mul, st), "rsb_unpack_grads")
             elif k == "prepass":
                 kind = 0 if x.dtype == torch.float32 else 1
                 _lib.check(lib.rsb_prepass_s2d(x.data_ptr(), kind, self.s2d.data_ptr(), self.N, self.H, self.W, self._mean, self._std, st), "rsb_prepass_s2d")
@@ -528,10 +570,36 @@ class UNetTrainEngine:
                                                   self._grad("final.weight").data_ptr(), self._grad("final.bias").data_ptr(), self.loss_scale,
                                                   self.N, self.H * self.W, self.C, st), "rsb_final_backward")
             elif k == "zero_grads":
-                for g in self.grads.values():
-                    g.zero_()
+                self._grad("final.bias")
+                self._grads_flat.zero_()
             else:  # pragma: no cover
                 raise AssertionError(k)
+
+    def _run_pack_all(self, lib, st):
+        """fp32 master weights -> every fp16 operand layout of every layer. The packed buffers are slices of a few arena
+        chunks; when all weights sit in one parameter arena (offsets from the lowest address fit in int32, e.g. the flat arena
+        of robosat_b200.optim.Adam) ONE launch per chunk fills them through a combined map, else one launch per layout."""
+        P = self.params
+        ptrs = tuple(P[w].data_ptr() for w, _, _, _, _ in self.pack_list)
+        if self._pack_all is None or self._pack_all["ptrs"] != ptrs:
+            base = min(ptrs)
+            span = max((p - base) // 4 + P[e[0]].numel() for p, e in zip(ptrs, self.pack_list))
+            combined = None
+            if span < 2 ** 31 and all((p - base) % 4 == 0 for p in ptrs):
+                combined = []
+                for ci, (chunk, used) in enumerate(self._pack_chunks):
+                    gmap = torch.full((used, 4), -1, dtype=torch.int32, device=self.device)
+                    for p, (w, m, d, c, off) in zip(ptrs, self.pack_list):
+                        if c == ci:
+                            gmap[off:off + m.shape[0]] = torch.where(m >= 0, m + int((p - base) // 4), m)
+                    combined.append((gmap, chunk, used))
+            self._pack_all = {"ptrs": ptrs, "combined": combined, "base": base}
+        if self._pack_all["combined"] is None:
+            for w, m, d, _, _ in self.pack_list:
+                _lib.check(lib.rsb_pack_weights(P[w].data_ptr(), m.data_ptr(), d.data_ptr(), d.numel(), st), "rsb_pack_weights")
+            return
+        for gmap, chunk, used in self._pack_all["combined"]:
+            _lib.check(lib.rsb_pack_weights(self._pack_all["base"], gmap.data_ptr(), chunk.data_ptr(), used, st), "rsb_pack_weights")
 
     def forward(self, x):
         if self.plan_only:
@@ -545,8 +613,6 @@ class UNetTrainEngine:
         if self.plan_only:
             raise _lib.RsbError("UNetTrainEngine was built with plan_only=True; there is no CPU execution path")
         assert dlogits.is_cuda and dlogits.is_contiguous() and dlogits.dtype == torch.float32
-        for name in self.params:
-            if self.params[name].dtype == torch.float32 and not (name.endswith("running_mean") or name.endswith("running_var")) and not name.startswith("resnet.fc."):
-                self._grad(name)
+        self._grad("final.bias")
         self._run(self.bwd_ops, dlogits=dlogits)
         return self.grads

@@ -183,12 +183,19 @@ def run_train_ops(eng, ops, x=None, dlogits=None):
         k = op[0]
         if k == "conv":
             run_desc(op[1].desc)
-        elif k == "pack":
-            _, wname, m, dst = op
-            src = P[wname].reshape(-1)
-            mm = m.long()
-            vals = torch.where(mm >= 0, src[mm.clamp_min(0)], torch.zeros(()))
-            dst.copy_(vals.sum(1).half())
+        elif k == "pack_all":
+            for wname, m, dst, _c, _o in eng.pack_list:
+                src = P[wname].reshape(-1)
+                mm = m.long()
+                vals = torch.where(mm >= 0, src[mm.clamp_min(0)], torch.zeros(()))
+                dst.copy_(vals.sum(1).half())
+        elif k == "unpack_all":
+            for dwp, m, wname, _c, _o in eng.unpack_list:
+                flat = eng._grad(wname).reshape(-1)
+                mm = m.long()
+                for j in range(4):
+                    sel = mm[:, j] >= 0
+                    flat.index_add_(0, mm[sel, j], dwp[sel] / eng.loss_scale)
         elif k == "bn_stats":
             b = op[1]
             z = b.z.reshape(b.M, b.C).double()
@@ -249,13 +256,6 @@ def run_train_ops(eng, ops, x=None, dlogits=None):
         elif k == "wgrad":
             _, u, dy = op
             run_wgrad(u.desc, dy.data_ptr() + 2 * u.out_offset, u.dw_packed)
-        elif k == "unpack":
-            _, dwp, m, wname, mul = op
-            flat = eng._grad(wname).reshape(-1)
-            mm = m.long()
-            for j in range(4):
-                sel = mm[:, j] >= 0
-                flat.index_add_(0, mm[sel, j], dwp[sel] * mul)
         elif k == "prepass":
             eng.s2d.copy_(prepass_s2d_cpu(x))
         elif k == "final_fwd":
@@ -270,8 +270,8 @@ def run_train_ops(eng, ops, x=None, dlogits=None):
             eng._grad("final.weight").copy_(torch.einsum("nkhw,nhwc->kc", dlogits, y5.float()).reshape(eng.C, 32, 1, 1))
             eng._grad("final.bias").copy_(dlogits.sum((0, 2, 3)))
         elif k == "zero_grads":
-            for g in eng.grads.values():
-                g.zero_()
+            eng._grad("final.bias")
+            eng._grads_flat.zero_()
         else:
             raise AssertionError(k)
 
