@@ -89,10 +89,14 @@ struct RowCfg {
     static constexpr int kChunk = BLOCK_N >= 64 ? 64 : 32;     // epilogue staging chunk (channels)
     static constexpr int kWarpChunkBytes = 32 * kChunk * 2;
     static constexpr int kStageBytes = MODE == 0 ? 4 * 2 * kWarpChunkBytes : 0;  // 4 warps x 2 store slices
-    static constexpr int kBarBytes = 512;
+    static constexpr int kBarBytes = 512;   // mbarriers + TMEM pointer
+    static constexpr int kHeadBytes = 1088; // final 1x1 weights [8][32] + bias [8] as fp32 (mode 1)
 };
 
-template <int CBLK, int BLOCK_N, int MODE>
+// TAPS: 3 (3x3) or 2 (2x2 taps of the fused upsample); CBLOCKS: channel blocks per pixel; NSUB: column phases per tile.
+// They are compile-time so that the single MMA-issuing thread runs a fully unrolled instruction stream (its issue rate,
+// not the tensor pipe, bounds these small-N layers otherwise).
+template <int CBLK, int BLOCK_N, int MODE, int TAPS, int CBLOCKS, int NSUB>
 __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_constant__ RowKParams p) {
     using Cfg = RowCfg<CBLK, BLOCK_N, MODE>;
     extern __shared__ uint8_t smem_raw[];
@@ -109,9 +113,15 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
     uint64_t* tmem_full_bar = wempty_bar + 1;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    float* smem_head = reinterpret_cast<float*>(smem_c + Cfg::kStageBytes + Cfg::kBarBytes);  // [8][32] weights, then [8] bias
 
     const int warp_idx = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    if (MODE == 1) {
+        // the head's 1x1 weights are read once per pixel and class: keep them in shared memory (broadcast reads)
+        for (int i = threadIdx.x; i < p.head_classes * 32; i += blockDim.x) smem_head[i] = p.head_w[i];
+        if (threadIdx.x < p.head_classes) smem_head[256 + threadIdx.x] = p.head_b[threadIdx.x];
+    }
     constexpr int kTmemCols = 4 * BLOCK_N <= 32 ? 32 : (4 * BLOCK_N <= 64 ? 64 : (4 * BLOCK_N <= 128 ? 128 : 256));  // 2 stages x 2 subs
 
     if (warp_idx == 0 && lane == 0) {
@@ -178,6 +188,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         // ------------------------------------------------------------------ MMA issuer
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(kRowTile, BLOCK_N);
+            const uint64_t desc_hi = make_kmajor_desc<CBLK>(0);  // everything but the start address
+            const uint32_t rows_base = smem_u32(smem_rows), w_base = smem_u32(smem_w);
             uint32_t qbase = 0, wq = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
@@ -197,27 +209,30 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                     mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t qrow = qbase + (h - u.h_lo);  // ring position of input row (h + dh0 + a)
-                    for (int th = 0; th < p.taps_h; ++th) {
+                    // rows h-1 .. were already waited for by the previous output row of this strip: only the newest one can be missing
+                    for (int th = (h == u.h_lo ? 0 : TAPS - 1); th < TAPS; ++th) {
                         const uint32_t qq = qrow + th;
                         mbar_wait(&full_bar[qq % p.slots], (qq / p.slots) & 1);
                     }
                     tc_fence_after();
-                    for (int s = 0; s < p.nsub; ++s) {
-                        const uint32_t d_tmem = tmem_base + (acc * p.nsub + s) * BLOCK_N;
-                        bool first = true;
-                        for (int th = 0; th < p.taps_h; ++th) {
-                            const uint32_t slot = (qrow + th) % p.slots;
-                            for (int tw = 0; tw < p.taps_w; ++tw) {
-                                for (int cb = 0; cb < p.cblocks; ++cb) {
-                                    const uint32_t a_addr = smem_u32(smem_rows + slot * row_bytes + cb * p.slot_bytes) + (tw + s) * Cfg::kPB;
-                                    const int blk = (s * p.taps_h * p.taps_w + th * p.taps_w + tw) * p.cblocks + cb;
-                                    const uint64_t da = make_kmajor_desc<CBLK>(a_addr);
-                                    const uint64_t db = make_kmajor_desc<CBLK>(smem_u32(smem_w + blk * p.wblock_bytes));
+                    uint32_t slot_addr[TAPS];
 #pragma unroll
-                                    for (int k = 0; k < CBLK / 16; ++k) {
-                                        umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, first ? 0u : 1u);
-                                        first = false;
-                                    }
+                    for (int th = 0; th < TAPS; ++th) slot_addr[th] = rows_base + ((qrow + th) % p.slots) * row_bytes;
+#pragma unroll
+                    for (int s = 0; s < NSUB; ++s) {
+                        const uint32_t d_tmem = tmem_base + (acc * NSUB + s) * BLOCK_N;
+#pragma unroll
+                        for (int th = 0; th < TAPS; ++th) {
+#pragma unroll
+                            for (int tw = 0; tw < TAPS; ++tw) {
+#pragma unroll
+                                for (int cb = 0; cb < CBLOCKS; ++cb) {
+                                    constexpr int kPB = Cfg::kPB;
+                                    const int blk = ((s * TAPS + th) * TAPS + tw) * CBLOCKS + cb;
+                                    const uint64_t da = desc_hi | static_cast<uint64_t>(((slot_addr[th] + cb * p.slot_bytes + (tw + s) * kPB) & 0x3FFFF) >> 4);
+                                    const uint64_t db = desc_hi | static_cast<uint64_t>(((w_base + blk * p.wblock_bytes) & 0x3FFFF) >> 4);
+#pragma unroll
+                                    for (int k = 0; k < CBLK / 16; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (th | tw | cb | k) != 0 ? 1u : 0u);
                                 }
                             }
                         }
@@ -306,9 +321,16 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                             v[j] = p.relu ? fmaxf(a, 0.0f) : a;
                         }
                         for (int k = 0; k < p.head_classes; ++k) {
-                            float sum = __ldg(p.head_b + k);
+                            float sum = smem_head[256 + k];
+                            const float4* hw4 = reinterpret_cast<const float4*>(smem_head + k * 32);
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) sum = fmaf(__ldg(p.head_w + k * 32 + j), v[j], sum);
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 wv = hw4[j];
+                                sum = fmaf(wv.x, v[4 * j], sum);
+                                sum = fmaf(wv.y, v[4 * j + 1], sum);
+                                sum = fmaf(wv.z, v[4 * j + 2], sum);
+                                sum = fmaf(wv.w, v[4 * j + 3], sum);
+                            }
                             if (w < p.Wt) p.head_out[((static_cast<int64_t>(u.n) * p.head_classes + k) * p.Ht + h) * p.Wt + w] = sum;
                         }
                     }
@@ -342,9 +364,9 @@ struct rsb_rowconv_plan {
     int cblk, block_n, mode, grid, smem;
 };
 
-template <int CBLK, int BLOCK_N, int MODE>
+template <int CBLK, int BLOCK_N, int MODE, int TAPS, int CBLOCKS, int NSUB>
 static int launch_row(const rsb_rowconv_plan* plan, cudaStream_t stream) {
-    auto kern = conv_row_kernel<CBLK, BLOCK_N, MODE>;
+    auto kern = conv_row_kernel<CBLK, BLOCK_N, MODE, TAPS, CBLOCKS, NSUB>;
     static int attr_smem = 0;
     if (plan->smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem);
@@ -371,7 +393,7 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     *out_plan = nullptr;
     if (!(d->cin == 32 || d->cin == 64 || d->cin == 128)) return set_error(RSB_E_INVALID, "rowconv: cin must be 32, 64 or 128");
     if (!(d->Cout == 32 || d->Cout == 64)) return set_error(RSB_E_INVALID, "rowconv: Cout must be 32 or 64");
-    if (d->taps_h < 1 || d->taps_h > 3 || d->taps_w < 1 || d->taps_w > 3) return set_error(RSB_E_INVALID, "rowconv: taps must be 1..3");
+    if (d->taps_h != d->taps_w || (d->taps_h != 2 && d->taps_h != 3)) return set_error(RSB_E_INVALID, "rowconv: taps must be 3x3 or 2x2");
     if (d->nsub < 1 || d->nsub > 2 || d->nphase_a < 1 || d->nphase_a > 2) return set_error(RSB_E_INVALID, "rowconv: nsub / nphase_a must be 1 or 2");
     const int cblk = d->cin == 32 ? 32 : 64;
     const int cblocks = d->cin / cblk;
@@ -450,7 +472,7 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     // shared memory: weights + epilogue staging are fixed; the ring takes the rest. Small layers run several CTAs per SM
     // (each with its own ring) so that TMA latency and the single MMA-issuing thread of one CTA are hidden by the others.
     const int stage = d->mode == 0 ? 4 * 2 * 32 * (d->Cout >= 64 ? 64 : 32) * 2 : 0;
-    const int fixed = d->nsub * d->taps_h * d->taps_w * cblocks * kp.wblock_bytes + stage + 512 + 1024;
+    const int fixed = d->nsub * d->taps_h * d->taps_w * cblocks * kp.wblock_bytes + stage + 512 + 1088 + 1024;
     const int row_bytes = kp.slot_bytes * cblocks;
     const int tmem_cols = 4 * d->Cout <= 128 ? 128 : 256;
     int ctas = 1;
@@ -493,7 +515,19 @@ extern "C" void rsb_rowconv_plan_destroy(rsb_rowconv_plan* plan) { delete plan; 
 extern "C" int rsb_rowconv_run(const rsb_rowconv_plan* plan, void* stream_) {
     if (!plan) return set_error(RSB_E_INVALID, "rowconv: null plan");
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
-    if (plan->mode == 1) return plan->cblk == 32 ? launch_row<32, 32, 1>(plan, st) : launch_row<64, 32, 1>(plan, st);
-    if (plan->cblk == 32) return plan->block_n == 32 ? launch_row<32, 32, 0>(plan, st) : launch_row<32, 64, 0>(plan, st);
-    return plan->block_n == 32 ? launch_row<64, 32, 0>(plan, st) : launch_row<64, 64, 0>(plan, st);
+    const RowKParams& k = plan->kp;
+    const int key = ((((plan->cblk * 100 + plan->block_n) * 10 + plan->mode) * 10 + k.taps_h) * 10 + k.cblocks) * 10 + k.nsub;
+    switch (key) {  // CBLK BLOCK_N MODE TAPS CBLOCKS NSUB
+        case 32321311: return launch_row<32, 32, 1, 3, 1, 1>(plan, st);  // dec5 + final
+        case 64321311: return launch_row<64, 32, 1, 3, 1, 1>(plan, st);
+        case 32320311: return launch_row<32, 32, 0, 3, 1, 1>(plan, st);  // 3x3, 32 -> 32
+        case 64640311: return launch_row<64, 64, 0, 3, 1, 1>(plan, st);  // layer1 3x3
+        case 64320311: return launch_row<64, 32, 0, 3, 1, 1>(plan, st);
+        case 64320222: return launch_row<64, 32, 0, 2, 2, 2>(plan, st);  // dec4: fused upsample 128 -> 32
+        case 64640212: return launch_row<64, 64, 0, 2, 1, 2>(plan, st);  // fused upsample 64 -> 64
+        case 64320212: return launch_row<64, 32, 0, 2, 1, 2>(plan, st);
+        case 64640222: return launch_row<64, 64, 0, 2, 2, 2>(plan, st);
+    }
+    return set_error(RSB_E_INVALID, "rowconv: no kernel instance for cblk %d, Cout %d, mode %d, taps %d, cblocks %d, nsub %d", plan->cblk,
+                     plan->block_n, plan->mode, k.taps_h, k.cblocks, k.nsub);
 }

@@ -19,13 +19,14 @@ def _write_split(root, split, n, size, seed):
     tiles = synth.make_tiles_u8(n, size, seed=seed).numpy()
     masks = synth.make_masks(n, size, 2, seed=seed + 1).numpy().astype(np.uint8)
     for i in range(n):
+        y = 105000 + int(rng.randint(0, 5))  # image and label of a tile share z/x/y
         for sub, arr, mode in (("images", tiles[i], "RGB"), ("labels", masks[i], "P")):
             d = os.path.join(root, split, sub, "18", str(69000 + i))
             os.makedirs(d, exist_ok=True)
             img = Image.fromarray(arr, mode=mode if mode == "P" else None)
             if mode == "P":
                 img.putpalette(colors.make_palette("denim", "orange"))
-            img.save(os.path.join(d, "%d.png" % (105000 + int(rng.randint(0, 5)))))
+            img.save(os.path.join(d, "%d.png" % y))
 
 
 def test_rs_train_end_to_end_and_resume(tmp_path, cuda_device, monkeypatch):
