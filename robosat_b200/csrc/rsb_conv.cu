@@ -184,6 +184,9 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
         // ------------------------------------------------------------------ MMA issuer
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
+            // operand descriptors of stage 0; stage s adds its byte offset >> 4 to the 14-bit start-address field
+            const uint64_t da0 = make_sw128_kmajor_desc(smem_u32(smem_a));
+            const uint64_t db0 = make_sw128_kmajor_desc(smem_u32(smem_b));
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -195,8 +198,8 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t da = make_sw128_kmajor_desc(smem_u32(smem_a + stage * kABytes));
-                    const uint64_t db = make_sw128_kmajor_desc(smem_u32(smem_b + stage * Cfg::kBBytes));
+                    const uint64_t da = da0 + static_cast<uint64_t>(stage * (kABytes >> 4));
+                    const uint64_t db = db0 + static_cast<uint64_t>(stage * (Cfg::kBBytes >> 4));
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
