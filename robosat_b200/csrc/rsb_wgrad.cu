@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         if (elect_one()) {
             // A and B both MN-major
             constexpr uint32_t idesc = make_idesc_f16(128, 64) | (1u << 15) | (1u << 16);
+            const uint64_t desc0 = make_sw128_mnmajor_desc(smem_u32(smem), kWgTileBytes);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -162,15 +163,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
                 for (int t = t_lo; t < t_hi; ++t) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t st = smem_u32(smem + stage * kWgStageBytes);
+                    // descriptors of this stage: dY at the stage base, X block j two tiles further; +2048 B (>> 4 = 128) per K step
+                    const uint64_t da0 = desc0 + static_cast<uint64_t>(stage * (kWgStageBytes >> 4));
+                    const uint32_t acc_first = (t > t_lo) ? 1u : 0u;
                     for (int j = 0; j < nkb; ++j) {
                         const uint32_t d_tmem = tmem_base + acc * kWgAccCols + j * 64;
+                        const uint64_t db0 = da0 + static_cast<uint64_t>((2 + j) * (kWgTileBytes >> 4));
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            const uint64_t da = make_sw128_mnmajor_desc(st + k * 2048, kWgTileBytes);
-                            const uint64_t db = make_sw128_mnmajor_desc(st + (2 + j) * kWgTileBytes + k * 2048, kWgTileBytes);
-                            umma_f16(d_tmem, da, db, idesc, (t > t_lo || k > 0) ? 1u : 0u);
-                        }
+                        for (int k = 0; k < 8; ++k) umma_f16(d_tmem, da0 + 128 * k, db0 + 128 * k, idesc, k > 0 ? 1u : acc_first);
                     }
                     umma_commit(&empty_bar[stage]);
                     if (++stage == kWgStages) {
