@@ -407,8 +407,9 @@ extern "C" int rsb_bn_stats(const void* z, double* sums, int64_t M, int32_t C, v
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
     if (e != cudaSuccess) return set_cuda_error(e, "bn_stats memset");
+    // every block folds >= 16 row groups before its 2*C fp64 atomics (wide, short tensors were atomic-bound otherwise)
     const int rows_per_iter = 256 / (C / 8);
-    channel_reduce_kernel<0><<<tr_blocks((M + rows_per_iter - 1) / rows_per_iter, 1, 148 * 8), 256, 0, st>>>(
+    channel_reduce_kernel<0><<<tr_blocks((M + rows_per_iter * 16 - 1) / (rows_per_iter * 16), 1, 148 * 8), 256, 0, st>>>(
         static_cast<const __half*>(z), nullptr, nullptr, nullptr, nullptr, sums, sums + C, M, C);
     RSB_LAUNCH_CHECK("bn_stats launch");
     return RSB_OK;
@@ -443,7 +444,7 @@ extern "C" int rsb_bn_backward(const void* dy, const void* y, const void* z, con
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
     if (e != cudaSuccess) return set_cuda_error(e, "bn_backward memset");
     const int rows_per_iter = 256 / (C / 8);
-    channel_reduce_kernel<1><<<tr_blocks((M + rows_per_iter - 1) / rows_per_iter, 1, 148 * 8), 256, 0, st>>>(
+    channel_reduce_kernel<1><<<tr_blocks((M + rows_per_iter * 16 - 1) / (rows_per_iter * 16), 1, 148 * 8), 256, 0, st>>>(
         static_cast<const __half*>(dy), static_cast<const __half*>(y), static_cast<const __half*>(z), mean, invstd, sums, sums + C, M, C);
     bn_bwd_apply_kernel<<<tr_blocks(M * (C / 8), 256), 256, 0, st>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
                                                                    static_cast<const __half*>(z), mean, invstd, gamma, sums, sums + C,

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     } else if (warp_idx == 1) {
         if (elect_one()) {
             // A and B both MN-major
-            constexpr uint32_t idesc = make_idesc_f16(128, 64) | (1u << 15) | (1u << 16);
+            constexpr uint32_t idesc_base = (make_idesc_f16(128, 0)) | (1u << 15) | (1u << 16);  // N filled in per work item
             const uint64_t desc0 = make_sw128_mnmajor_desc(smem_u32(smem), kWgTileBytes);
             int stage = 0;
             uint32_t phase = 0;
@@ -164,14 +164,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     // descriptors of this stage: dY at the stage base, X block j two tiles further; +2048 B (>> 4 = 128) per K step
+                    // ONE MMA per K step covers all K blocks of the group: the X tiles sit back to back in the stage, so they form an
+                    // MN-major B operand of N = 64 * nkb columns with LBO = one tile (A is read from shared memory once per step)
                     const uint64_t da0 = desc0 + static_cast<uint64_t>(stage * (kWgStageBytes >> 4));
+                    const uint64_t db0 = da0 + static_cast<uint64_t>(2 * (kWgTileBytes >> 4));
                     const uint32_t acc_first = (t > t_lo) ? 1u : 0u;
-                    for (int j = 0; j < nkb; ++j) {
-                        const uint32_t d_tmem = tmem_base + acc * kWgAccCols + j * 64;
-                        const uint64_t db0 = da0 + static_cast<uint64_t>((2 + j) * (kWgTileBytes >> 4));
+                    const uint32_t d_tmem = tmem_base + acc * kWgAccCols;
+                    const uint32_t idesc_n = idesc_base | (static_cast<uint32_t>(nkb * 64 >> 3) << 17);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) umma_f16(d_tmem, da0 + 128 * k, db0 + 128 * k, idesc, k > 0 ? 1u : acc_first);
-                    }
+                    for (int k = 0; k < 8; ++k) umma_f16(d_tmem, da0 + 128 * k, db0 + 128 * k, idesc_n, k > 0 ? 1u : acc_first);
                     umma_commit(&empty_bar[stage]);
                     if (++stage == kWgStages) {
                         stage = 0;
