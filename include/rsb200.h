@@ -97,6 +97,10 @@ typedef struct rsb_conv_desc {
     const float* head_w;
     const float* head_b;
     float* head_out;
+
+    /* 1: compute each pair of neighbouring tiles with a CTA pair (cluster of 2, tcgen05 cta_group::2; mode 0,
+     * block_n >= 128): each CTA stages half of the weight tile. Same results; 0 = one CTA per tile. */
+    int32_t cta_pair;
 } rsb_conv_desc;
 
 typedef struct rsb_conv_plan rsb_conv_plan;

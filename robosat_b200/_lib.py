@@ -66,6 +66,7 @@ class ConvDesc(ctypes.Structure):
         ("head_w", ctypes.c_void_p),
         ("head_b", ctypes.c_void_p),
         ("head_out", ctypes.c_void_p),
+        ("cta_pair", ctypes.c_int32),
     ]
 
 

@@ -41,6 +41,7 @@ struct alignas(64) ConvKParams {
     int32_t seg_cb[RSB_MAX_SEGS];
     int32_t kblocks;
     int32_t tiles_w, tiles_h, tiles_n, n_blocks, phases, total_tiles;
+    int32_t pair_tiles;  // CTA-pair schedule: ceil(spatial tiles / 2) * phases * n_blocks
     int32_t TW, TH, TN;
     int32_t Wt, Ht, Nt;
     int32_t Cout;
@@ -56,9 +57,13 @@ struct alignas(64) ConvKParams {
     float* head_out;
 };
 
-template <int BLOCK_N, int MODE, bool HAS_RES>
+// TWO: the tile is computed by a CTA pair (cluster of 2, tcgen05 cta_group::2): rank r owns 128 of the pair's 256 tile
+// rows and stages half of the weight tile (BLOCK_N/2 rows); one MMA of the leader reads both halves, so each SM moves
+// 16 KB + BLOCK_N*64 B of shared memory per K block instead of 16 KB + BLOCK_N*128 B.
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO = false>
 struct ConvCfg {
-    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kBRows = TWO ? BLOCK_N / 2 : BLOCK_N;
+    static constexpr int kBBytes = kBRows * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     // epilogue staging: the C tile leaves through shared memory in chunks of kChunk columns (TMA store), and the
     // residual tile arrives the same way (TMA load); 2 buffers each
@@ -105,9 +110,22 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvKParams& p, int id) {
     return t;
 }
 
-template <int BLOCK_N, int MODE, bool HAS_RES>
-__global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
-    using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES>;
+// Work item `it` of this CTA -> flat tile id. One CTA per tile: identity. CTA pair: item = (spatial pair, phase, n block),
+// rank r takes spatial tile 2*pair + r (a tile past the end loads zeros and stores nothing).
+template <bool TWO>
+__device__ __forceinline__ int item_tile(const ConvKParams& p, int it, int rank) {
+    if (!TWO) return it;
+    const int per = p.n_blocks * p.phases;
+    return ((it / per) * 2 + rank) * per + it % per;
+}
+
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO>
+__global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThreads), 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
+    using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>;
+    const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
+    const int item0 = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int item_step = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int num_items = TWO ? p.pair_tiles : p.total_tiles;
     extern __shared__ uint8_t smem_raw[];
     // 128B swizzle atoms repeat every 1024 bytes: tile bases must be 1024-byte aligned
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -129,12 +147,12 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
         for (int i = 0; i < RSB_MAX_SRCS; ++i) tma_prefetch_desc(&p.tmA[i]);
         tma_prefetch_desc(&p.tmB);
         for (int i = 0; i < Cfg::kStages; ++i) {
-            mbar_init(&full_bar[i], 1);
+            mbar_init(&full_bar[i], TWO ? 2 : 1);  // pair: the leader's expect_tx arrive + the peer producer's arrive
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full_bar[i], 1);
-            mbar_init(&tmem_empty_bar[i], Cfg::kEpiWarps);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty_bar[i], (TWO ? 2 : 1) * Cfg::kEpiWarps);  // one arrive per epilogue warp (of both CTAs)
         }
         for (int i = 0; i < 32; ++i) mbar_init(&res_full_bar[i], 1);
         if (MODE == 0) {
@@ -143,9 +161,13 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
         }
         mbar_fence_init();
     }
-    if (warp_idx == 1) tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    if (warp_idx == 1) {
+        if (TWO) tmem_alloc_pair<Cfg::kTmemCols>(tmem_ptr);
+        else tmem_alloc<Cfg::kTmemCols>(tmem_ptr);
+    }
     tc_fence_before();
-    __syncthreads();
+    if (TWO) cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them remotely
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 
@@ -159,9 +181,10 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-                const TileCoord t = decode_tile(p, tile);
-                const int b_row = t.phase * p.Cout + t.n_blk * BLOCK_N;
+            const uint32_t lead_full0 = TWO ? mapa_u32(smem_u32(&full_bar[0]), 0) : 0;
+            for (int it = item0; it < num_items; it += item_step) {
+                const TileCoord t = decode_tile(p, item_tile<TWO>(p, it, rank));
+                const int b_row = t.phase * p.Cout + t.n_blk * BLOCK_N + rank * Cfg::kBRows;
                 int kb = 0;
                 for (int s = 0; s < p.nseg; ++s) {
                     const CUtensorMap* tm = &p.tmA[p.seg_src[s]];
@@ -169,9 +192,18 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
                     const int ch = t.h0 + p.seg_dh[s] + t.pa;
                     for (int cb = 0; cb < p.seg_cb[s]; ++cb, ++kb) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
-                        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                        tma_load_4d(smem_a + stage * kABytes, tm, &full_bar[stage], cb * kBlockK, cw, ch, t.n0);
-                        tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, b_row);
+                        if constexpr (TWO) {
+                            // both CTAs' boxes complete on the leader's barrier
+                            const uint32_t lead_full = lead_full0 + stage * 8;
+                            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                            else mbar_arrive_remote(lead_full);
+                            tma_load_4d_pair(smem_a + stage * kABytes, tm, lead_full, cb * kBlockK, cw, ch, t.n0);
+                            tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &p.tmB, lead_full, kb * kBlockK, b_row);
+                        } else {
+                            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                            tma_load_4d(smem_a + stage * kABytes, tm, &full_bar[stage], cb * kBlockK, cw, ch, t.n0);
+                            tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, b_row);
+                        }
                         if (++stage == Cfg::kStages) {
                             stage = 0;
                             phase ^= 1;
@@ -182,8 +214,8 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
         }
     } else if (warp_idx == 1) {
         // ------------------------------------------------------------------ MMA issuer
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_f16(TWO ? 2 * kBlockM : kBlockM, BLOCK_N);
             // operand descriptors of stage 0; stage s adds its byte offset >> 4 to the 14-bit start-address field
             const uint64_t da0 = make_sw128_kmajor_desc(smem_u32(smem_a));
             const uint64_t db0 = make_sw128_kmajor_desc(smem_u32(smem_b));
@@ -191,7 +223,7 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+            for (int it = item0; it < num_items; it += item_step) {
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
@@ -203,15 +235,20 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
-                        umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (TWO) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+                    // smem slot is free once these MMAs retire (pair: in both CTAs)
+                    if (TWO) umma_commit_pair(&empty_bar[stage]);
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == Cfg::kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+                // accumulator complete -> epilogue
+                if (TWO) umma_commit_pair(&tmem_full_bar[acc]);
+                else umma_commit(&tmem_full_bar[acc]);
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
@@ -236,18 +273,23 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
         uint8_t* my_r = smem_r + ew * (Cfg::kResBufs > 0 ? Cfg::kResBufs : 1) * Cfg::kWarpChunkBytes;
         uint64_t* my_res_bar = res_full_bar + ew * 4;
         uint32_t wchunk = 0;          // running chunk counter of this warp (selects staging buffers)
-        int res_tile = blockIdx.x;    // residual prefetch cursor (lane 0)
+        int res_item = item0;         // residual prefetch cursor (lane 0)
+        const uint32_t lead_tmem_empty0 = TWO ? mapa_u32(smem_u32(&tmem_empty_bar[0]), 0) : 0;
+        auto release_acc = [&](int a) {
+            if (TWO) mbar_arrive_remote(lead_tmem_empty0 + a * 8);
+            else mbar_arrive(&tmem_empty_bar[a]);
+        };
         int res_chunk = chunk0;
         auto issue_residual = [&](int rb) {
-            if (res_tile < p.total_tiles) {
-                const TileCoord rt = decode_tile(p, res_tile);
+            if (res_item < num_items) {
+                const TileCoord rt = decode_tile(p, item_tile<TWO>(p, res_item, rank));
                 mbar_expect_tx(&my_res_bar[rb], Cfg::kWarpChunkBytes);
                 tma_load_4d(my_r + rb * Cfg::kWarpChunkBytes, &p.tmR, &my_res_bar[rb], rt.n_blk * BLOCK_N + res_chunk * Cfg::kChunk,
                             rt.w0 + qw, rt.h0 + qh, rt.n0 + qn);
                 res_chunk += Cfg::kChunkStride;
                 if (res_chunk >= Cfg::kNumChunks) {
                     res_chunk = chunk0;
-                    res_tile += gridDim.x;
+                    res_item += item_step;
                 }
             }
         };
@@ -255,8 +297,8 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
 #pragma unroll 1
             for (int i = 0; i < Cfg::kResBufs; ++i) issue_residual(i);
         }
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-            const TileCoord t = decode_tile(p, tile);
+        for (int it = item0; it < num_items; it += item_step) {
+            const TileCoord t = decode_tile(p, item_tile<TWO>(p, it, rank));
             const int w = t.w0 + tw, h = t.h0 + th, n = t.n0 + tn;
             const bool valid = (w < p.Wt) && (h < p.Ht) && (n < p.Nt);
             mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -285,7 +327,7 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
                             // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
                             tc_fence_before();
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                            if (lane == 0) release_acc(acc);
                         }
                         float v[32];
 #pragma unroll
@@ -365,7 +407,7 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
             if constexpr (MODE == 1) {
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+                if (lane == 0) release_acc(acc);
             }
             if (++acc == 2) {
                 acc = 0;
@@ -376,10 +418,12 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES>::kThreads), 1
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (TWO) cluster_sync_all();  // neither CTA may retire (or free tensor memory) while the pair's MMAs can still touch it
+    else __syncthreads();
     if (warp_idx == 1) {
         tc_fence_after();
-        tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+        if (TWO) tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
+        else tmem_dealloc<Cfg::kTmemCols>(tmem_base);
     }
 }
 
@@ -450,6 +494,7 @@ struct rsb_conv_plan {
     int grid;
     int smem;
     bool has_res;
+    bool pair;  // CTA-pair (cta_group::2) schedule
 };
 
 static int validate_desc(const rsb_conv_desc* d, int* K_out) {
@@ -492,14 +537,15 @@ static int validate_desc(const rsb_conv_desc* d, int* K_out) {
     } else {
         return set_error(RSB_E_INVALID, "conv: unknown mode");
     }
+    if (d->cta_pair && (d->mode != 0 || d->block_n < 128)) return set_error(RSB_E_INVALID, "conv: cta_pair needs mode 0 and block_n >= 128");
     *K_out = kblocks * kBlockK;
     return RSB_OK;
 }
 
-template <int BLOCK_N, int MODE, bool HAS_RES>
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO = false>
 static int launch_conv(const rsb_conv_plan* plan, cudaStream_t stream) {
-    using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES>;
-    auto kern = conv_tc_kernel<BLOCK_N, MODE, HAS_RES>;
+    using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>;
+    auto kern = conv_tc_kernel<BLOCK_N, MODE, HAS_RES, TWO>;
     static bool attr_set = false;  // per instantiation
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
@@ -511,14 +557,54 @@ static int launch_conv(const rsb_conv_plan* plan, cudaStream_t stream) {
     cfg.blockDim = dim3(Cfg::kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (TWO) {
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = 2;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        cfg.numAttrs = 2;
+    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, plan->kp);
     if (e != cudaSuccess) return set_cuda_error(e, "conv_tc_kernel launch");
     return RSB_OK;
+}
+
+// how many CTA pairs the device can hold at once (pairs need two SMs of one TPC; persistent grid = that many clusters)
+template <int BLOCK_N, bool HAS_RES>
+static int pair_clusters_of() {
+    using Cfg = ConvCfg<BLOCK_N, 0, HAS_RES, true>;
+    auto kern = conv_tc_kernel<BLOCK_N, 0, HAS_RES, true>;
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * num_sms());
+    cfg.blockDim = dim3(Cfg::kThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    const int cap = num_sms() / 2;
+    cached = n < cap ? n : cap;
+    return cached;
+}
+static int pair_clusters(int block_n, bool res) {
+    if (block_n == 128) return res ? pair_clusters_of<128, true>() : pair_clusters_of<128, false>();
+    return res ? pair_clusters_of<256, true>() : pair_clusters_of<256, false>();
 }
 
 template <int BLOCK_N>
@@ -556,7 +642,8 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
     {
         const uint64_t dims[2] = {(uint64_t)K, (uint64_t)d->phases * d->Cout};
         const uint64_t strides[1] = {(uint64_t)K * 2};
-        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)d->block_n};
+        // a CTA of a pair stages half of the weight tile
+        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(d->cta_pair ? d->block_n / 2 : d->block_n)};
         rc = encode_tiled_f16(&kp.tmB, 2, d->weights, dims, strides, box);
         if (rc) {
             delete plan;
@@ -625,6 +712,7 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
     kp.n_blocks = d->Cout / d->block_n;
     kp.phases = d->phases;
     kp.total_tiles = kp.tiles_w * kp.tiles_h * kp.tiles_n * kp.n_blocks * kp.phases;
+    kp.pair_tiles = ((kp.tiles_w * kp.tiles_h * kp.tiles_n + 1) / 2) * kp.n_blocks * kp.phases;
     kp.Cout = d->Cout;
     kp.out_sy = d->out_sy > 0 ? d->out_sy : 1;
     kp.out_sx = d->out_sx > 0 ? d->out_sx : 1;
@@ -645,6 +733,19 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
     const int sms = num_sms();
     plan->grid = kp.total_tiles < sms ? kp.total_tiles : sms;
     plan->has_res = d->mode == 0 && d->residual != nullptr;
+    plan->pair = d->cta_pair != 0;
+    if (plan->pair) {
+        const int clusters = pair_clusters(d->block_n, plan->has_res);
+        if (clusters < 1) {
+            delete plan;
+            return set_error(RSB_E_CUDA, "conv: no CTA pair can be resident");
+        }
+        plan->grid = 2 * (kp.pair_tiles < clusters ? kp.pair_tiles : clusters);
+        if (d->block_n == 128) plan->smem = plan->has_res ? ConvCfg<128, 0, true, true>::kSmemBytes : ConvCfg<128, 0, false, true>::kSmemBytes;
+        else plan->smem = plan->has_res ? ConvCfg<256, 0, true, true>::kSmemBytes : ConvCfg<256, 0, false, true>::kSmemBytes;
+        *out_plan = plan;
+        return RSB_OK;
+    }
     switch (d->block_n) {
         case 32: plan->smem = smem_for<32>(d->mode, plan->has_res); break;
         case 64: plan->smem = smem_for<64>(d->mode, plan->has_res); break;
@@ -670,6 +771,10 @@ extern "C" int rsb_conv_run(const rsb_conv_plan* plan, void* stream_) {
     if (!plan) return set_error(RSB_E_INVALID, "conv: null plan");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (plan->mode == 1) return launch_conv<32, 1, false>(plan, stream);
+    if (plan->pair) {
+        if (plan->block_n == 128) return plan->has_res ? launch_conv<128, 0, true, true>(plan, stream) : launch_conv<128, 0, false, true>(plan, stream);
+        return plan->has_res ? launch_conv<256, 0, true, true>(plan, stream) : launch_conv<256, 0, false, true>(plan, stream);
+    }
     if (plan->has_res) {
         switch (plan->block_n) {
             case 32: return launch_conv<32, 0, true>(plan, stream);

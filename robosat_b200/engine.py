@@ -12,6 +12,7 @@ Bottleneck stack it calls), ConvRelu robosat/unet.py:44, DecoderBlock robosat/un
 """
 
 import ctypes
+import os
 from collections import OrderedDict
 
 import torch
@@ -119,6 +120,11 @@ def choose_tile(Wt, Ht, Nt):
     return best[1]
 
 
+# wide tiles (block_n >= 128) are computed by CTA pairs (tcgen05 cta_group::2): each SM stages half of the weight tile.
+# RSB_CTA_PAIR=0 falls back to one CTA per tile (A/B measurements).
+CTA_PAIR = os.environ.get("RSB_CTA_PAIR", "0") == "1"
+
+
 def choose_block_n(cout, m_tiles, phases, sms=148):
     """Largest N tile that still leaves about two waves of tiles for the persistent grid."""
     cands = [bn for bn in (256, 128, 64, 32) if cout % bn == 0]
@@ -223,7 +229,7 @@ def _src_parity(t, N, H, W, C, ph, pw):
 
 
 def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out_pitches, out_scale=(1, 1),
-                   residual=None, relu=True, block_n=None, head=None, out_offset_elems=0):
+                   residual=None, relu=True, block_n=None, head=None, out_offset_elems=0, cta_pair=None):
     """Fill an `rsb_conv_desc`. tile_space = (Wt, Ht, Nt); out_pitches = (pitch_w, pitch_h, pitch_n) in elements."""
     d = ConvDesc()
     d.nsrc = len(srcs)
@@ -253,6 +259,9 @@ def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out
         d.out = out.data_ptr() + 2 * out_offset_elems
         d.out_pitch_w, d.out_pitch_h, d.out_pitch_n = out_pitches
         d.residual = residual.data_ptr() if residual is not None else None
+        if cta_pair is None:
+            cta_pair = CTA_PAIR and d.block_n >= 128 and m_tiles >= 2
+        d.cta_pair = 1 if cta_pair else 0
     else:
         head_w, head_b, head_out, classes = head
         d.mode = 1

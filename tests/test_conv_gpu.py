@@ -56,6 +56,41 @@ def test_conv_multi_wave_persistent_schedule(block_n, cuda_device):
     lib.rsb_conv_plan_destroy(plan)
 
 
+_PAIR_CASES = [
+    lambda d: conv_cases.conv_case("1x1", 1, 16, 32, 256, 128, d, seed=2, residual=True, block_n=128),
+    lambda d: conv_cases.conv_case("3x3", 1, 24, 40, 128, 256, d, seed=4, block_n=256),
+    lambda d: conv_cases.conv_case("3x3", 8, 64, 64, 64, 256, d, seed=21, block_n=128),   # multi-wave
+    lambda d: conv_cases.conv_case("3x3", 5, 8, 8, 128, 256, d, seed=22, block_n=256),    # odd number of spatial tiles
+    lambda d: conv_cases.conv_case("1x1", 3, 8, 8, 512, 2048, d, seed=7, residual=True, block_n=256),
+    lambda d: conv_cases.conv_case("3x3s2", 2, 32, 32, 128, 128, d, seed=5, block_n=128),
+    lambda d: conv_cases.decoder_case(3, 4, 4, [256, 256], 256, d, seed=10, block_n=128),
+]
+
+
+@pytest.mark.parametrize("i", range(len(_PAIR_CASES)))
+def test_conv_cta_pair_matches_single_cta(i, cuda_device):
+    """cta_group::2 schedule (two SMs per 256-row tile pair, half a weight tile each) == one CTA per tile, bit for bit."""
+    lib = _lib.load()
+    case = _PAIR_CASES[i](cuda_device)
+    stream = _lib.current_stream_ptr()
+    outs = []
+    for pair in (0, 1):
+        case.desc.cta_pair = pair
+        plan = ctypes.c_void_p()
+        _lib.check(lib.rsb_conv_plan_create(ctypes.byref(case.desc), ctypes.byref(plan)), "plan_create")
+        try:
+            for _ in range(2):
+                case.out.zero_()
+                _lib.check(lib.rsb_conv_run(plan, stream), "conv_run")
+                torch.cuda.synchronize()
+            outs.append(case.out.clone())
+        finally:
+            lib.rsb_conv_plan_destroy(plan)
+    ref = case.ref()
+    assert (case.result() - ref).abs().max().item() <= 6e-3 * max(1.0, ref.abs().max().item() / 8), case.name
+    assert torch.equal(outs[0], outs[1]), case.name
+
+
 def test_prepass_u8_matches_reference_transform(cuda_device):
     """uint8 NHWC -> normalised fp16 s2d == ToTensor + Normalize (predict.py:71-73) then fp16 rounding."""
     import emulate
