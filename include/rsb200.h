@@ -258,6 +258,10 @@ int rsb_debug_umma(const void* a, int32_t a_total_rows, int32_t a_cols, const vo
                    int32_t a_blocks, int32_t row_offset, int32_t base_offset, int32_t lbo, int32_t sbo, int32_t k_step_bytes,
                    void* stream);
 
+/* tcgen05.mma issue-rate probe (bring-up only): every CTA (pair != 0: every CTA pair) issues 4*iters MMAs of
+ * M=128 (256 for a pair) x block_n x 16 on zeroed operands; out[cta] = cycles per MMA as seen by the issuing thread. */
+int rsb_debug_mma_rate(float* out, int32_t grid, int32_t pair, int32_t block_n, int32_t iters, int32_t commit_each, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

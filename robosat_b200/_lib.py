@@ -142,6 +142,7 @@ SIGNATURES = {
     "rsb_wgrad_plan_destroy": (None, [_vp]),
     "rsb_wgrad_run": (ctypes.c_int, [_vp, _vp]),
     "rsb_debug_umma": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp] + [_i32] * 8 + [_vp]),
+    "rsb_debug_mma_rate": (ctypes.c_int, [_vp] + [_i32] * 5 + [_vp]),
 }
 
 _lib = None

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThread
         for (int i = 0; i < RSB_MAX_SRCS; ++i) tma_prefetch_desc(&p.tmA[i]);
         tma_prefetch_desc(&p.tmB);
         for (int i = 0; i < Cfg::kStages; ++i) {
-            mbar_init(&full_bar[i], TWO ? 2 : 1);  // pair: the leader's expect_tx arrive + the peer producer's arrive
+            mbar_init(&full_bar[i], 1);  // pair: only the leader's is used; it expects the bytes of both CTAs' boxes
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -195,8 +195,9 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThread
                         if constexpr (TWO) {
                             // both CTAs' boxes complete on the leader's barrier
                             const uint32_t lead_full = lead_full0 + stage * 8;
+                            // (the peer's bytes may land before this expect_tx: the barrier cannot complete until the
+                            // leader's arrive, and the peer cannot run a ring lap ahead of the MMA's commits)
                             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-                            else mbar_arrive_remote(lead_full);
                             tma_load_4d_pair(smem_a + stage * kABytes, tm, lead_full, cb * kBlockK, cw, ch, t.n0);
                             tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &p.tmB, lead_full, kb * kBlockK, b_row);
                         } else {

@@ -88,6 +88,68 @@ __global__ void __launch_bounds__(128, 1) debug_umma_kernel(const __grid_constan
     if (warp == 0) tmem_dealloc<64>(tmem);
 }
 
+// tcgen05.mma issue-rate probe: `iters` K=64 blocks (4 MMAs each) on zeroed shared-memory operands, one CTA or one
+// CTA pair per tile, optionally a commit per block as the conv kernel does. out[blockIdx.x] = cycles per MMA.
+template <bool TWO>
+__global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(float* out, int block_n, int iters, int commit_each) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sa = smem;            // 4 stages x 16 KB
+    uint8_t* sb = smem + 65536;    // 4 stages x 32 KB
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 65536 + 131072);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 8);
+    const int warp = threadIdx.x >> 5;
+    const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
+    for (int i = threadIdx.x; i < (65536 + 131072) / 16; i += blockDim.x) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 8; ++i) mbar_init(&bar[i], 1);
+        mbar_fence_init();
+    }
+    fence_proxy_async_smem();
+    if (warp == 0) {
+        if (TWO) tmem_alloc_pair<256>(tmem_ptr);
+        else tmem_alloc<256>(tmem_ptr);
+    }
+    tc_fence_before();
+    if (TWO) cluster_sync_all();
+    else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr;
+    if (threadIdx.x == 0 && rank == 0) {
+        const uint32_t idesc = make_idesc_f16(TWO ? 256 : 128, block_n);
+        const uint64_t da0 = make_sw128_kmajor_desc(smem_u32(sa));
+        const uint64_t db0 = make_sw128_kmajor_desc(smem_u32(sb));
+        const long long t0 = clock64();
+        for (int it = 0; it < iters; ++it) {
+            const int st = it & 3;
+            const uint64_t da = da0 + static_cast<uint64_t>(st * (16384 >> 4));
+            const uint64_t db = db0 + static_cast<uint64_t>(st * (32768 >> 4));
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (TWO) umma_f16_pair(tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+                else umma_f16(tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+            }
+            if (commit_each) {
+                if (TWO) umma_commit_pair(&bar[1 + (it & 3)]);
+                else umma_commit(&bar[1 + (it & 3)]);
+            }
+        }
+        if (TWO) umma_commit_pair(&bar[0]);
+        else umma_commit(&bar[0]);
+        mbar_wait(&bar[0], 0);
+        const long long t1 = clock64();
+        out[blockIdx.x] = static_cast<float>(t1 - t0) / (4.0f * iters);
+    }
+    tc_fence_before();
+    if (TWO) cluster_sync_all();
+    else __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        if (TWO) tmem_dealloc_pair<256>(tmem);
+        else tmem_dealloc<256>(tmem);
+    }
+}
+
 }  // namespace rsb
 
 using namespace rsb;
@@ -128,4 +190,32 @@ extern "C" int rsb_debug_umma(const void* a, int32_t a_total_rows, int32_t a_col
     debug_umma_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(p);
     e = cudaGetLastError();
     return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "debug_umma launch");
+}
+
+extern "C" int rsb_debug_mma_rate(float* out, int32_t grid, int32_t pair, int32_t block_n, int32_t iters, int32_t commit_each, void* stream) {
+    if (!out || grid < 1 || iters < 1 || (pair && (grid & 1))) return set_error(RSB_E_INVALID, "debug_mma_rate: bad arguments");
+    int rc = rsb_device_ok();
+    if (rc) return rc;
+    const int smem = 65536 + 131072 + 128 + 1024;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = static_cast<cudaStream_t>(stream);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pair ? 1 : 0;
+    cudaError_t e;
+    if (pair) {
+        e = cudaFuncSetAttribute(debug_mma_rate_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, debug_mma_rate_kernel<true>, out, block_n, iters, commit_each);
+    } else {
+        e = cudaFuncSetAttribute(debug_mma_rate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, debug_mma_rate_kernel<false>, out, block_n, iters, commit_each);
+    }
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "debug_mma_rate launch");
 }

@@ -174,7 +174,9 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t cta) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default (CTA-scope) release semantics: a cluster-scope release costs a MEMBAR.ALL.GPU per arrive, and what this
+    // arrive orders (tcgen05.ld results) is already fenced by tcgen05.wait::ld + tcgen05.fence::before_thread_sync
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // pair loads: the box lands in this CTA's shared memory, the byte count on the barrier at `bar_cluster_addr` (the leader's)
 __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* desc, uint32_t bar_cluster_addr, int32_t c0,

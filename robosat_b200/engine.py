@@ -120,9 +120,9 @@ def choose_tile(Wt, Ht, Nt):
     return best[1]
 
 
-# wide tiles (block_n >= 128) are computed by CTA pairs (tcgen05 cta_group::2): each SM stages half of the weight tile.
-# RSB_CTA_PAIR=0 falls back to one CTA per tile (A/B measurements).
-CTA_PAIR = os.environ.get("RSB_CTA_PAIR", "0") == "1"
+# wide tiles (block_n >= 128) with long K loops are computed by CTA pairs (tcgen05 cta_group::2): each SM stages half of
+# the weight tile. Results are bit-identical; RSB_CTA_PAIR=0 keeps one CTA per tile everywhere (A/B measurements).
+CTA_PAIR = os.environ.get("RSB_CTA_PAIR", "1") == "1"
 
 
 def choose_block_n(cout, m_tiles, phases, sms=148):
@@ -260,7 +260,10 @@ def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out
         d.out_pitch_w, d.out_pitch_h, d.out_pitch_n = out_pitches
         d.residual = residual.data_ptr() if residual is not None else None
         if cta_pair is None:
-            cta_pair = CTA_PAIR and d.block_n >= 128 and m_tiles >= 2
+            # measured (profiles/r1_cta_pair.md): pairs win once the K loop is long enough to be shared-memory bound
+            # (dec0/dec1/dec3 -7..-10 %), and lose a few % on short, epilogue-bound K loops
+            kblocks = K // 64
+            cta_pair = CTA_PAIR and m_tiles >= 2 and ((d.block_n == 256 and kblocks >= 6) or (d.block_n == 128 and kblocks >= 18))
         d.cta_pair = 1 if cta_pair else 0
     else:
         head_w, head_b, head_out, classes = head
