@@ -227,9 +227,14 @@ int rsb_bn_backward(const void* dy, const void* y, const void* z, const float* m
                     void* stream);
 /* out = (a (+ b)) * (y > 0): ReLU backward with optional gradient fan-in (skip connections); y NULL: plain sum */
 int rsb_relu_backward(const void* a, const void* b, const void* y, void* out, int64_t n, void* stream);
-/* autograd of max_pool2d (unet.py:125, :132) on NHWC fp16: first maximum of every window receives its gradient */
-int rsb_maxpool_backward(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t s,
-                         int32_t p, void* stream);
+/* autograd of max_pool2d (unet.py:125, :132) on NHWC fp16: first maximum of every window receives its gradient.
+ * argmax_scratch: N*OH*OW*C bytes of device scratch (one window position per pooled element) -> two streaming passes;
+ * NULL -> single-pass kernel that re-derives the argmax per input pixel (slower, no scratch). Same results. */
+int rsb_maxpool_backward(const void* x, const void* dy, void* dx, void* argmax_scratch, int32_t N, int32_t H, int32_t W, int32_t C,
+                         int32_t k, int32_t s, int32_t p, void* stream);
+/* autograd's AccumulateGrad for every parameter at once (loss.backward(), train.py:186): dst_i[0:n_i] += alpha * src_i[0:n_i]
+ * for `segments` rows (src pointer, dst pointer, n_i <= 2^31) of a device-resident int64 table; fp32, one block per row. */
+int rsb_multi_axpy(const int64_t* table, int32_t segments, float alpha, void* stream);
 /* final 1x1 conv 32 -> classes with bias (unet.py:141) as its own step in training: fp32 NCHW logits from NHWC fp16 dec5 */
 int rsb_final_forward(const void* y5, const float* w, const float* b, float* logits, int32_t N, int32_t HW, int32_t classes,
                       void* stream);

@@ -133,7 +133,8 @@ SIGNATURES = {
     "rsb_bn_apply": (ctypes.c_int, [_vp] * 5 + [_i64, _i32, _i32, _vp]),
     "rsb_bn_backward": (ctypes.c_int, [_vp] * 11 + [_f32, _i64, _i32, _vp]),
     "rsb_relu_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
-    "rsb_maxpool_backward": (ctypes.c_int, [_vp, _vp, _vp] + [_i32] * 7 + [_vp]),
+    "rsb_multi_axpy": (ctypes.c_int, [_vp, _i32, ctypes.c_float, _vp]),
+    "rsb_maxpool_backward": (ctypes.c_int, [_vp, _vp, _vp, _vp] + [_i32] * 7 + [_vp]),
     "rsb_final_forward": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rsb_final_backward": (ctypes.c_int, [_vp] * 7 + [_f32, _i32, _i32, _i32, _vp]),
     "rsb_pack_weights": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp]),

@@ -276,6 +276,82 @@ __global__ void maxpool_bwd_kernel(const __half* __restrict__ x, const __half* _
     }
 }
 
+// Two-pass variant (what the engine uses): pass 1 recomputes, once per pooling window, the position (dy*k + dx) of its
+// first maximum; pass 2 gathers, per input pixel, the gradients of the <= ceil(k/s)^2 windows whose argmax it is.
+__global__ void maxpool_argmax_kernel(const __half* __restrict__ x, uint8_t* __restrict__ idx, int N, int H, int W, int C, int k, int s, int p,
+                                      int OH, int OW) {
+    const int C8 = C / 8;
+    const int64_t total = static_cast<int64_t>(N) * OH * OW * C8;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int c8 = static_cast<int>(i % C8);
+        int64_t r = i / C8;
+        const int ow = static_cast<int>(r % OW);
+        r /= OW;
+        const int oh = static_cast<int>(r % OH);
+        const int n = static_cast<int>(r / OH);
+        float best[8];
+        uint32_t pos[8];
+        bool any = false;
+        for (int dyy = 0; dyy < k; ++dyy) {
+            const int hh = oh * s - p + dyy;
+            if (hh < 0 || hh >= H) continue;
+            for (int dxx = 0; dxx < k; ++dxx) {
+                const int ww = ow * s - p + dxx;
+                if (ww < 0 || ww >= W) continue;
+                float v[8];
+                load8(x + ((static_cast<int64_t>(n) * H + hh) * W + ww) * C + c8 * 8, v);
+                const uint32_t q = static_cast<uint32_t>(dyy * k + dxx);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    if (!any || v[e] > best[e]) {
+                        best[e] = v[e];
+                        pos[e] = q;
+                    }
+                }
+                any = true;
+            }
+        }
+        uint2 o;
+        o.x = pos[0] | (pos[1] << 8) | (pos[2] << 16) | (pos[3] << 24);
+        o.y = pos[4] | (pos[5] << 8) | (pos[6] << 16) | (pos[7] << 24);
+        *reinterpret_cast<uint2*>(idx + i * 8) = o;
+    }
+}
+
+__global__ void maxpool_bwd_gather_kernel(const uint8_t* __restrict__ idx, const __half* __restrict__ dy, __half* __restrict__ dx, int N, int H,
+                                          int W, int C, int k, int s, int p, int OH, int OW) {
+    const int C8 = C / 8;
+    const int64_t total = static_cast<int64_t>(N) * H * W * C8;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int c8 = static_cast<int>(i % C8);
+        int64_t r = i / C8;
+        const int w = static_cast<int>(r % W);
+        r /= W;
+        const int h = static_cast<int>(r % H);
+        const int n = static_cast<int>(r / H);
+        float acc[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+        const int oh_lo = max(0, (h + p - k + s) / s), oh_hi = min(OH - 1, (h + p) / s);
+        const int ow_lo = max(0, (w + p - k + s) / s), ow_hi = min(OW - 1, (w + p) / s);
+        for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+            for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+                const int64_t o = ((static_cast<int64_t>(n) * OH + oh) * OW + ow) * C + c8 * 8;
+                const uint32_t me = static_cast<uint32_t>((h - (oh * s - p)) * k + (w - (ow * s - p)));
+                const uint2 q = __ldg(reinterpret_cast<const uint2*>(idx + o));
+                float g[8];
+                load8(dy + o, g);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const uint32_t a = ((e < 4 ? q.x : q.y) >> (8 * (e & 3))) & 0xffu;
+                    acc[e] += a == me ? g[e] : 0.f;
+                }
+            }
+        }
+        store8(dx + i * 8, acc);
+    }
+}
+
 // final 1x1 conv (32 -> C classes, with bias) forward: logits fp32 NCHW from NHWC fp16 activations (unet.py:141)
 __global__ void final_fwd_kernel(const __half* __restrict__ y5, const float* __restrict__ w, const float* __restrict__ b,
                                  float* __restrict__ logits, int64_t P, int64_t HW, int classes) {
@@ -390,6 +466,16 @@ __global__ void unpack_scatter_kernel(const float* __restrict__ packed_grad, con
     }
 }
 
+// dst_i[j] += alpha * src_i[j] over a table of (src, dst, n) fp32 segments, one block per segment: the whole network's
+// parameter gradients are added into the caller's .grad tensors in one launch (instead of one autograd add per tensor).
+__global__ void multi_axpy_kernel(const int64_t* __restrict__ table, float alpha) {
+    const int64_t* t = table + static_cast<int64_t>(blockIdx.x) * 3;
+    const float* __restrict__ src = reinterpret_cast<const float*>(t[0]);
+    float* __restrict__ dst = reinterpret_cast<float*>(t[1]);
+    const int n = static_cast<int>(t[2]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] += alpha * src[i];
+}
+
 }  // namespace rsb
 
 using namespace rsb;
@@ -462,12 +548,23 @@ extern "C" int rsb_relu_backward(const void* a, const void* b, const void* y, vo
     return RSB_OK;
 }
 
-extern "C" int rsb_maxpool_backward(const void* x, const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k,
-                                    int32_t s, int32_t p, void* stream) {
-    if (!x || !dy || !dx || N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 8) || k < 1 || s < 1 || p < 0)
+extern "C" int rsb_maxpool_backward(const void* x, const void* dy, void* dx, void* argmax_scratch, int32_t N, int32_t H, int32_t W, int32_t C,
+                                    int32_t k, int32_t s, int32_t p, void* stream) {
+    if (!x || !dy || !dx || N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 8) || k < 1 || k > 15 || s < 1 || p < 0)
         return set_error(RSB_E_INVALID, "maxpool_backward: bad arguments");
     const int OH = (H + 2 * p - k) / s + 1, OW = (W + 2 * p - k) / s + 1;
-    maxpool_bwd_kernel<<<tr_blocks(static_cast<int64_t>(N) * H * W * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (argmax_scratch) {
+        uint8_t* idx = static_cast<uint8_t*>(argmax_scratch);
+        maxpool_argmax_kernel<<<tr_blocks(static_cast<int64_t>(N) * OH * OW * (C / 8), 256), 256, 0, st>>>(static_cast<const __half*>(x), idx, N, H, W,
+                                                                                                          C, k, s, p, OH, OW);
+        RSB_LAUNCH_CHECK("maxpool_argmax launch");
+        maxpool_bwd_gather_kernel<<<tr_blocks(static_cast<int64_t>(N) * H * W * (C / 8), 256), 256, 0, st>>>(
+            idx, static_cast<const __half*>(dy), static_cast<__half*>(dx), N, H, W, C, k, s, p, OH, OW);
+        RSB_LAUNCH_CHECK("maxpool_bwd_gather launch");
+        return RSB_OK;
+    }
+    maxpool_bwd_kernel<<<tr_blocks(static_cast<int64_t>(N) * H * W * (C / 8), 256), 256, 0, st>>>(
         static_cast<const __half*>(x), static_cast<const __half*>(dy), static_cast<__half*>(dx), N, H, W, C, k, s, p, OH, OW);
     RSB_LAUNCH_CHECK("maxpool_backward launch");
     return RSB_OK;
@@ -510,5 +607,13 @@ extern "C" int rsb_unpack_grads(const float* packed_grad, const int32_t* map4, f
     if (!packed_grad || !map4 || !grad || n <= 0) return set_error(RSB_E_INVALID, "unpack_grads: bad arguments");
     unpack_scatter_kernel<<<tr_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(packed_grad, map4, grad, n, mul);
     RSB_LAUNCH_CHECK("unpack_grads launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_multi_axpy(const int64_t* table, int32_t segments, float alpha, void* stream) {
+    if (!table || segments < 0) return set_error(RSB_E_INVALID, "multi_axpy: bad arguments");
+    if (segments == 0) return RSB_OK;
+    multi_axpy_kernel<<<static_cast<unsigned>(segments), 256, 0, static_cast<cudaStream_t>(stream)>>>(table, alpha);
+    RSB_LAUNCH_CHECK("multi_axpy launch");
     return RSB_OK;
 }

@@ -125,14 +125,23 @@ def choose_tile(Wt, Ht, Nt):
 CTA_PAIR = os.environ.get("RSB_CTA_PAIR", "1") == "1"
 
 
-def choose_block_n(cout, m_tiles, phases, sms=148):
-    """Largest N tile that still leaves about two waves of tiles for the persistent grid."""
+def choose_block_n(cout, m_tiles, phases, kblocks=8, sms=148):
+    """N tile with the lowest modelled time for the persistent grid (ties -> the widest).
+
+    Model (cycles, from scripts/gpu_mma_rate.py and the per-layer tables under profiles/): a tile's K loop issues 4 MMAs
+    per K block and an M128 x N x K16 MMA takes max(66, N/2) cycles (N <= 64 is bound by the 4 KB shared-memory read of
+    the A operand, so narrow tiles run the tensor core at <= 50 %); the epilogue of the previous tile overlaps it and
+    costs ~16 (8 epilogue warps, N >= 128) or ~28 (4 warps) cycles per output column; the grid runs
+    ceil(tiles / SMs) rounds of that."""
     cands = [bn for bn in (256, 128, 64, 32) if cout % bn == 0]
     assert cands, "Cout must be a multiple of 32"
-    for bn in cands:
-        if m_tiles * phases * (cout // bn) >= 2 * sms:
-            return bn
-    return cands[-1] if cands[-1] >= 64 or len(cands) == 1 else cands[-2]
+
+    def cost(bn):
+        tiles = m_tiles * phases * (cout // bn)
+        per_tile = max(kblocks * 4 * max(66, bn // 2), bn * (16 if bn >= 128 else 28)) + 300
+        return -(-tiles // sms) * per_tile
+
+    return min(cands, key=lambda bn: (cost(bn), -bn))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -249,7 +258,7 @@ def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out
     d.Wt, d.Ht, d.Nt = Wt, Ht, Nt
     d.TW, d.TH, d.TN = choose_tile(Wt, Ht, Nt)
     m_tiles = -(-Wt // d.TW) * -(-Ht // d.TH) * -(-Nt // d.TN)
-    d.block_n = block_n or choose_block_n(cout, m_tiles, phases)
+    d.block_n = block_n or choose_block_n(cout, m_tiles, phases, K // 64)
     if residual is not None and block_n is None and d.block_n == 256:
         d.block_n = 128  # residual epilogues keep 4 residual slices in flight per warp: leave room for 4 pipeline stages
     d.out_sy, d.out_sx = out_scale

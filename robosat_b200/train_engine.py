@@ -169,6 +169,8 @@ class UNetTrainEngine:
         self._dw_chunks = []    # [fp32 arena tensor, elements used] packed weight gradients
         self._grads_flat, self._grad_offset, self._unpack_all = None, {}, None
         self._keep = []
+        self._pool_scratch = {}  # max-pool backward: one argmax byte per pooled element
+        self._accum_tables = {}
         self.grads = OrderedDict()
         self.units = OrderedDict()
         self.feats = OrderedDict()
@@ -549,7 +551,11 @@ class UNetTrainEngine:
                 _lib.check(lib.rsb_maxpool_nhwc(src.data_ptr(), dst.data_ptr(), n, h, w, c, kk, s, p, st), "rsb_maxpool_nhwc")
             elif k == "maxpool_bwd":
                 _, xx, dy, dx, n, h, w, c, kk, s, p = op
-                _lib.check(lib.rsb_maxpool_backward(xx.data_ptr(), dy.data_ptr(), dx.data_ptr(), n, h, w, c, kk, s, p, st), "rsb_maxpool_backward")
+                scratch = self._pool_scratch.get(id(dx))
+                if scratch is None:
+                    scratch = self._pool_scratch[id(dx)] = torch.empty(dy.numel(), dtype=torch.uint8, device=dx.device)
+                _lib.check(lib.rsb_maxpool_backward(xx.data_ptr(), dy.data_ptr(), dx.data_ptr(), scratch.data_ptr(), n, h, w, c, kk, s, p, st),
+                           "rsb_maxpool_backward")
             elif k == "wgrad":
                 _, u, dy = op
                 if not hasattr(u, "wgrad_plan"):
@@ -607,6 +613,26 @@ class UNetTrainEngine:
         assert x.is_cuda and x.is_contiguous()
         self._run(self.fwd_ops, x=x)
         return self.logits
+
+    def accumulate_into(self, targets):
+        """targets: {parameter name: fp32 contiguous .grad tensor}. Adds this step's gradients into them with ONE kernel
+        (what autograd's per-tensor AccumulateGrad would do in ~170 launches). The segment table is cached per set of
+        destination pointers."""
+        names = [n for n in targets if n in self.grads]
+        key = tuple((n, targets[n].data_ptr()) for n in names)
+        cached = self._accum_tables.get(key)
+        if cached is None:
+            rows, seg = [], 16384
+            for n in names:
+                g, t = self.grads[n], targets[n]
+                assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == g.numel() and t.device == g.device, n
+                for off in range(0, g.numel(), seg):
+                    rows.append((g.data_ptr() + 4 * off, t.data_ptr() + 4 * off, min(seg, g.numel() - off)))
+            table = torch.tensor(rows, dtype=torch.int64).reshape(-1, 3).to(self.device)
+            self._accum_tables.clear()
+            cached = self._accum_tables[key] = (table, len(rows))
+        table, nrows = cached
+        _lib.check(_lib.load().rsb_multi_axpy(table.data_ptr(), nrows, 1.0, _lib.current_stream_ptr()), "rsb_multi_axpy")
 
     def backward(self, dlogits):
         """dlogits: fp32 [N, C, H, W] gradient of the loss w.r.t. the logits (unscaled). Fills self.grads."""

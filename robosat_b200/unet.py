@@ -26,12 +26,23 @@ class _TrainStep(torch.autograd.Function):
     def forward(ctx, x, module, names, *params):
         eng = module._train_engine_for(x)
         logits = eng.forward(x.contiguous())
-        ctx.eng, ctx.names = eng, names
+        ctx.eng, ctx.names, ctx.params, ctx.fused = eng, names, params, module.fused_grad_accumulation
         return logits.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
         grads = ctx.eng.backward(grad_out.contiguous().float())
+        if ctx.fused:
+            # every parameter that already holds a dense fp32 .grad (the usual case after optimizer.zero_grad()) is
+            # accumulated in place by one kernel; autograd gets None for it and therefore launches no per-tensor add
+            targets = {}
+            for n, p in zip(ctx.names, ctx.params):
+                g = p.grad
+                if n in grads and g is not None and g.dtype == torch.float32 and g.is_contiguous() and g.device == grads[n].device:
+                    targets[n] = g
+            if targets:
+                ctx.eng.accumulate_into(targets)
+            return (None, None, None) + tuple(None if n in targets else grads.get(n) for n in ctx.names)
         return (None, None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
@@ -80,6 +91,9 @@ class UNet(nn.Module):
         self.final = nn.Conv2d(num_filters, num_classes, kernel_size=1)
         self._engines = {}
         self._train_engines = {}
+        # loss.backward() adds into existing .grad tensors with one kernel instead of one autograd add per parameter
+        # (False: hand every gradient to autograd, e.g. when tensor hooks on parameters must fire)
+        self.fused_grad_accumulation = True
         self.loss_scale = 4096.0  # activation gradients are fp16: scaled by this inside the backward plan, unscaled in param.grad
 
     # any weight change invalidates the packed plans

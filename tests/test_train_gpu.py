@@ -78,17 +78,23 @@ def test_relu_maxpool_final_pack_kernels(cuda_device):
     torch.cuda.synchronize()
     assert torch.equal(out.cpu(), ((a.float() + b.float()) * (y.float() > 0)).half())
     # max-pool backward (both pools of the network)
-    for (N, H, W, C, k, s, p) in [(2, 16, 16, 64, 3, 2, 1), (2, 4, 4, 128, 2, 2, 0)]:
-        x = torch.randn((N, C, H, W), generator=g).half().float().requires_grad_(True)
+    for (N, H, W, C, k, s, p) in [(2, 16, 16, 64, 3, 2, 1), (2, 4, 4, 128, 2, 2, 0), (3, 10, 14, 8, 3, 2, 1)]:
+        # post-ReLU inputs: many exact ties (zeros) -> the first maximum of a window must take the gradient, as in ATen
+        x = torch.relu(torch.randn((N, C, H, W), generator=g)).half().float().requires_grad_(True)
         yy = F.max_pool2d(x, k, s, p)
         dy = torch.randn(yy.shape, generator=g).half()
         yy.backward(dy.float())
         xd = x.detach().permute(0, 2, 3, 1).contiguous().half().to(d)
         dyd = dy.permute(0, 2, 3, 1).contiguous().to(d)
-        dx = torch.zeros_like(xd)
-        _lib.check(lib.rsb_maxpool_backward(xd.data_ptr(), dyd.data_ptr(), dx.data_ptr(), N, H, W, C, k, s, p, st), "maxpool_bwd")
-        torch.cuda.synchronize()
-        assert (dx.float().cpu().permute(0, 3, 1, 2) - x.grad).abs().max().item() <= 2e-3
+        scratch = torch.zeros(dyd.numel(), dtype=torch.uint8, device=d)
+        got = []
+        for ws in (None, scratch.data_ptr()):  # single-pass kernel, and the two-pass (argmax scratch) one the engine uses
+            dx = torch.zeros_like(xd)
+            _lib.check(lib.rsb_maxpool_backward(xd.data_ptr(), dyd.data_ptr(), dx.data_ptr(), ws, N, H, W, C, k, s, p, st), "maxpool_bwd")
+            torch.cuda.synchronize()
+            assert (dx.float().cpu().permute(0, 3, 1, 2) - x.grad).abs().max().item() <= 2e-3
+            got.append(dx.clone())
+        assert torch.equal(got[0], got[1])
     # final 1x1 forward / backward
     N, H, W, C = 2, 16, 24, 6
     y5 = torch.randn((N, H, W, 32), generator=g).half()
@@ -254,3 +260,40 @@ def test_unet_module_train_step_with_lovasz_and_adam(cuda_device):
         ev = net(x)
     ref_eval = unet_oracle.unet_forward({k: v.detach().cpu() for k, v in net.state_dict().items()}, x.cpu())
     assert _rel(ev.float().cpu(), ref_eval) < 1e-2
+
+
+def test_fused_grad_accumulation_matches_autograd_accumulate(cuda_device):
+    """loss.backward() with the one-kernel accumulation (rsb_multi_axpy into existing .grad tensors) == handing every
+    gradient to autograd's AccumulateGrad; a second backward without zero_grad() adds, as torch does."""
+    from robosat_b200.losses import CrossEntropyLoss2d
+    from robosat_b200.unet import UNet
+
+    net = UNet(2, pretrained=False).to(cuda_device)
+    net.load_state_dict({k[7:]: v for k, v in synth.make_state_dict(2, seed=0).items()})
+    net.train()
+    crit = CrossEntropyLoss2d().to(cuda_device)
+    x = synth.normalize_tiles(synth.make_tiles_u8(2, 64, seed=4)).to(cuda_device)
+    masks = synth.make_masks(2, 64, 2, seed=5).to(cuda_device)
+    used = [(n, p) for n, p in net.named_parameters() if not n.startswith("resnet.fc.")]
+
+    def run(fused, times):
+        net.fused_grad_accumulation = fused
+        for _, p in net.named_parameters():
+            p.grad = torch.zeros_like(p)
+        for _ in range(times):
+            crit(net(x), masks).backward()
+        torch.cuda.synchronize()
+        return {n: p.grad.clone() for n, p in used}
+
+    ref, one, two = run(False, 1), run(True, 1), run(True, 2)
+    for n, _ in used:
+        scale = ref[n].abs().max().item() + 1e-12
+        assert (one[n] - ref[n]).abs().max().item() <= 1e-4 * scale, n      # split-K fp32 atomics: order-dependent last bits
+        assert (two[n] - 2 * ref[n]).abs().max().item() <= 2e-4 * scale, n
+    # parameters without a .grad tensor still get theirs through autograd
+    net.fused_grad_accumulation = True
+    for _, p in net.named_parameters():
+        p.grad = None
+    crit(net(x), masks).backward()
+    assert all(p.grad is not None for _, p in used)
+    assert (dict(net.named_parameters())["final.weight"].grad - ref["final.weight"]).abs().max().item() <= 1e-4 * ref["final.weight"].abs().max().item()
