@@ -136,7 +136,7 @@ def layer_profile(engine, x, reps=3):
         if hasattr(d, "taps_h"):  # line-buffer plan
             K, phases, kern = d.taps_h * d.taps_w * d.cin, d.nsub * d.nphase_a, "conv_row_kernel<%d,%d,%d>" % (32 if d.cin == 32 else 64, d.Cout, d.mode)
         else:
-            K, phases, kern = 64 * sum(d.segs[i].cblocks for i in range(d.nseg)), d.phases, "conv_tc_kernel<%d,%d>" % (d.block_n, d.mode)
+            K, phases, kern = 64 * sum(d.segs[i].cblocks for i in range(d.nseg)), d.phases, "conv_tc_kernel<%d,%d,%d,%d>" % (d.block_n, d.mode, 1 if d.residual else 0, d.cta_pair)
         flops = 2.0 * d.Nt * d.Ht * d.Wt * phases * d.Cout * K
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
         for a, b in evs:
@@ -307,6 +307,9 @@ def main():
                 "frac": dk["gflop"] / dk["ms"] / pk["tflops"], "traffic": traffic, "peak_source": pk["src"] + " bf16 sustained",
                 "launches_per_step": dk["launches"], "ms_per_step": dk["ms"], "all_conv_tflops": conv_tf, "all_conv_ms": conv_ms,
                 "flops": "executed (sub-pixel decoder: 100.7 GFLOP/tile, not the 167.16 dense-equivalent)"}
+        # every instantiation's share of the step and its executed tensor rate (the 1x1 layers with K <= 128 are HBM-bound)
+        roof["by_kernel"] = {k: {"ms_per_step": round(v["ms"], 4), "launches": v["launches"], "tflops": round(v["gflop"] / v["ms"], 1)}
+                             for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1]["ms"])}
         if args.layers_out:
             with open(args.layers_out, "w") as fp:
                 json.dump({"layers": rows, "by_kernel": by_kernel}, fp, indent=1)

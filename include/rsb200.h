@@ -211,12 +211,16 @@ int rsb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
  * gradients are NHWC fp16 [M = N*H*W][C]; gradients carry the caller's loss scale; parameter gradients are fp32, unscaled.
  */
 /* train-mode BatchNorm2d (torchvision resnet50 inside unet.py:122-130): batch sums -> statistics / running-stat update -> apply.
- * sums: 2*C doubles of scratch. finalize writes mean, invstd, scale = gamma*invstd, shift = beta - mean*scale and updates
+ * sums: 20*C doubles of scratch (8 replicated accumulator slots, arrival counter, backward coefficients). finalize writes mean, invstd, scale = gamma*invstd, shift = beta - mean*scale and updates
  * running_mean / running_var (unbiased, momentum) / num_batches_tracked when those pointers are non-NULL. */
 int rsb_bn_stats(const void* z, double* sums, int64_t M, int32_t C, void* stream);
 int rsb_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                     int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int32_t C, int64_t M, float eps,
                     float momentum, void* stream);
+/* rsb_bn_stats + rsb_bn_finalize in one launch (the last block of the reduction does the per-channel epilogue) */
+int rsb_bn_stats_finalize(const void* z, double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                          int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int64_t M, int32_t C, float eps,
+                          float momentum, void* stream);
 /* y = relu?(z*scale + shift (+ residual)) */
 int rsb_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y, int64_t M, int32_t C,
                  int32_t relu, void* stream);

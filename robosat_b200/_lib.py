@@ -129,6 +129,7 @@ SIGNATURES = {
     "rsb_metrics_count": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rsb_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp]),
     "rsb_bn_stats": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
+    "rsb_bn_stats_finalize": (ctypes.c_int, [_vp] * 11 + [_i64, _i32, _f32, _f32, _vp]),
     "rsb_bn_finalize": (ctypes.c_int, [_vp] * 10 + [_i32, _i64, _f32, _f32, _vp]),
     "rsb_bn_apply": (ctypes.c_int, [_vp] * 5 + [_i64, _i32, _i32, _vp]),
     "rsb_bn_backward": (ctypes.c_int, [_vp] * 11 + [_f32, _i64, _i32, _vp]),

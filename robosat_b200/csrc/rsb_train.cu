@@ -22,6 +22,12 @@ static inline unsigned tr_blocks(int64_t total, int block, int cap = 148 * 16) {
     return static_cast<unsigned>(b);
 }
 
+// grid of the channel reductions: every block folds >= 4 row groups (2 per iteration in flight), at most 8 blocks per SM
+static inline unsigned reduce_blocks(int64_t M, int C) {
+    const int rows_per_iter = 256 / (C / 8);
+    return tr_blocks((M + rows_per_iter * 4 - 1) / (rows_per_iter * 4), 1, 148 * 8);
+}
+
 __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
     const __half2* h = reinterpret_cast<const __half2*>(&q);
@@ -41,51 +47,91 @@ __device__ __forceinline__ void store8(__half* p, const float (&v)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-channel sums over M rows of an NHWC fp16 tensor [M][C]; up to two fused reductions:
+// per-channel sums over M rows of an NHWC fp16 tensor [M][C]; two fused reductions:
 //   KIND 0 (forward stats)   : s0 += z            s1 += z*z
-//   KIND 1 (BN backward)     : g = dy * (y > 0 or no mask); s0 += g ; s1 += g * (z - mean) * invstd
-// 256 threads: C/8 threads cover one row (8 channels = 16 bytes each), 256/(C/8) rows per iteration.
+//   KIND 1 (BN backward)     : g = dy * (y > 0 or no mask); s0 += g ; s1 += g * z   (raw: consumers turn it into
+//                              sum g*zhat = (s1 - mean*s0) * invstd, which keeps mean / invstd out of the streaming loop)
+// 256 threads: C/8 threads cover one row (8 channels = 16 bytes each), 256/(C/8) rows per iteration, two iterations in
+// flight per thread. Block totals go to one of kRedSlots replicated fp64 accumulators (slot = block % kRedSlots) so that
+// at most blocks/kRedSlots atomics queue up on an address; consumers add the slots.
+static constexpr int kRedSlots = 8;
+
+// Scratch layout (doubles): [kRedSlots][2][C] accumulators | 1 arrival counter | 1 pad | (as floats) 3*C coefficients.
+// The LAST block to finish (arrival counter) folds the slots and does the per-channel epilogue, so no extra launch is needed:
+//   KIND 0: BatchNorm finalize (mean / invstd / folded scale+shift, running statistics)      -- when tail.gamma != NULL
+//   KIND 1: dgamma / dbeta and the coefficients A, B, D of dz = A*g + B*z + D for bn_bwd_apply_kernel
+struct RedTail {
+    const float* gamma;
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+    int64_t* num_batches;
+    float* mean;    // KIND 0: out; KIND 1: in
+    float* invstd;  // KIND 0: out; KIND 1: in
+    float* scale;
+    float* shift;
+    float* dgamma;
+    float* dbeta;
+    float eps, momentum, inv_scale;
+};
+
+__device__ __forceinline__ double red_slots(const double* sums, int which, int c, int C) {
+    double t = 0.0;
+#pragma unroll
+    for (int sl = 0; sl < kRedSlots; ++sl) t += __ldcg(&sums[(static_cast<int64_t>(sl) * 2 + which) * C + c]);
+    return t;
+}
+
 template <int KIND>
-__global__ void channel_reduce_kernel(const __half* __restrict__ a, const __half* __restrict__ y, const __half* __restrict__ z,
-                                      const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ s0,
-                                      double* __restrict__ s1, int64_t M, int C) {
+__global__ void __launch_bounds__(256, 3) channel_reduce_kernel(const __half* __restrict__ a, const __half* __restrict__ y, const __half* __restrict__ z,
+                                                             double* __restrict__ sums, int64_t M, int C, const RedTail tail) {
     __shared__ float sh0[256 * 8];
     __shared__ float sh1[256 * 8];
     const int tpr = C / 8;
     const int rows_per_iter = 256 / tpr;
     const int col = (threadIdx.x % tpr) * 8;
     const int rsub = threadIdx.x / tpr;
-    float acc0[8], acc1[8], mu[8], is[8];
+    float acc0[8], acc1[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        acc0[i] = acc1[i] = 0.f;
-        mu[i] = (KIND == 1) ? mean[col + i] : 0.f;
-        is[i] = (KIND == 1) ? invstd[col + i] : 0.f;
-    }
-    for (int64_t r = static_cast<int64_t>(blockIdx.x) * rows_per_iter + rsub; r < M; r += static_cast<int64_t>(gridDim.x) * rows_per_iter) {
-        float v[8];
-        load8(a + r * C + col, v);
-        if (KIND == 0) {
+    for (int i = 0; i < 8; ++i) acc0[i] = acc1[i] = 0.f;
+    const int64_t step = static_cast<int64_t>(gridDim.x) * rows_per_iter;
+    auto fold = [&](const float (&v)[8], const float (&zz)[8], const float (&yy)[8], bool masked) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 8; ++i) {
+            if (KIND == 0) {
                 acc0[i] += v[i];
-                acc1[i] += v[i] * v[i];
-            }
-        } else {
-            float zz[8];
-            load8(z + r * C + col, zz);
-            if (y) {
-                float yy[8];
-                load8(y + r * C + col, yy);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = yy[i] > 0.f ? v[i] : 0.f;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                acc0[i] += v[i];
-                acc1[i] += v[i] * (zz[i] - mu[i]) * is[i];
+                acc1[i] = fmaf(v[i], v[i], acc1[i]);
+            } else {
+                const float g = (masked && !(yy[i] > 0.f)) ? 0.f : v[i];
+                acc0[i] += g;
+                acc1[i] = fmaf(g, zz[i], acc1[i]);
             }
         }
+    };
+    int64_t r = static_cast<int64_t>(blockIdx.x) * rows_per_iter + rsub;
+    for (; r + step < M; r += 2 * step) {
+        float v0[8], v1[8], z0[8], z1[8], y0[8], y1[8];
+        load8(a + r * C + col, v0);
+        load8(a + (r + step) * C + col, v1);
+        if (KIND == 1) {
+            load8(z + r * C + col, z0);
+            load8(z + (r + step) * C + col, z1);
+            if (y) {
+                load8(y + r * C + col, y0);
+                load8(y + (r + step) * C + col, y1);
+            }
+        }
+        fold(v0, z0, y0, y != nullptr);
+        fold(v1, z1, y1, y != nullptr);
+    }
+    if (r < M) {
+        float v0[8], z0[8], y0[8];
+        load8(a + r * C + col, v0);
+        if (KIND == 1) {
+            load8(z + r * C + col, z0);
+            if (y) load8(y + r * C + col, y0);
+        }
+        fold(v0, z0, y0, y != nullptr);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -94,6 +140,8 @@ __global__ void channel_reduce_kernel(const __half* __restrict__ a, const __half
     }
     __syncthreads();
     // threads 0..C-1 (at most 2048 channels -> loop) fold the row-groups
+    double* s0 = sums + static_cast<int64_t>(blockIdx.x % kRedSlots) * 2 * C;
+    double* s1 = s0 + C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int t0 = c / 8, e = c % 8;
         float a0 = 0.f, a1 = 0.f;
@@ -104,18 +152,61 @@ __global__ void channel_reduce_kernel(const __half* __restrict__ a, const __half
         atomicAdd(&s0[c], static_cast<double>(a0));
         atomicAdd(&s1[c], static_cast<double>(a1));
     }
+    if (tail.gamma == nullptr) return;
+    // ---- last block: per-channel epilogue
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned* counter = reinterpret_cast<unsigned*>(sums + static_cast<int64_t>(kRedSlots) * 2 * C);
+        is_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const double dM = static_cast<double>(M);
+    if (KIND == 0 && threadIdx.x == 0 && tail.num_batches) *tail.num_batches += 1;
+    float* coef = reinterpret_cast<float*>(sums + static_cast<int64_t>(kRedSlots) * 2 * C + 2);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double t0 = red_slots(sums, 0, c, C), t1 = red_slots(sums, 1, c, C);
+        if (KIND == 0) {
+            const double mean = t0 / dM;
+            double var = t1 / dM - mean * mean;
+            if (var < 0) var = 0;
+            const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(tail.eps)));
+            const float sc = tail.gamma[c] * invstd;
+            tail.mean[c] = static_cast<float>(mean);
+            tail.invstd[c] = invstd;
+            tail.scale[c] = sc;
+            tail.shift[c] = tail.beta[c] - static_cast<float>(mean) * sc;
+            if (tail.running_mean) {
+                const double unbiased = dM > 1 ? var * dM / (dM - 1.0) : var;
+                tail.running_mean[c] = (1.f - tail.momentum) * tail.running_mean[c] + tail.momentum * static_cast<float>(mean);
+                tail.running_var[c] = (1.f - tail.momentum) * tail.running_var[c] + tail.momentum * static_cast<float>(unbiased);
+            }
+        } else {
+            const float is = tail.invstd[c], ga = tail.gamma[c], mu = tail.mean[c];
+            const double sgzh = (t1 - static_cast<double>(mu) * t0) * static_cast<double>(is);  // sum of g * zhat
+            tail.dgamma[c] = static_cast<float>(sgzh) * tail.inv_scale;
+            tail.dbeta[c] = static_cast<float>(t0) * tail.inv_scale;
+            const float mg = static_cast<float>(t0 / dM), mgz = static_cast<float>(sgzh / dM);
+            coef[c] = ga * is;                                        // A
+            coef[C + c] = -ga * is * is * mgz;                        // B
+            coef[2 * C + c] = -ga * is * mg + ga * is * is * mu * mgz;  // D
+        }
+    }
 }
 
 // mean / invstd / folded scale+shift from the batch sums, running-stat update (momentum, unbiased variance)
-__global__ void bn_finalize_kernel(const double* __restrict__ s0, const double* __restrict__ s1, const float* __restrict__ gamma,
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
                                    int64_t* __restrict__ num_batches, float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                    float* __restrict__ scale_out, float* __restrict__ shift_out, int C, double M, float eps, float momentum) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c == 0 && num_batches) *num_batches += 1;
     if (c >= C) return;
-    const double mean = s0[c] / M;
-    double var = s1[c] / M - mean * mean;
+    const double mean = red_slots(sums, 0, c, C) / M;
+    double var = red_slots(sums, 1, c, C) / M - mean * mean;
     if (var < 0) var = 0;
     const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
     const float sc = gamma[c] * invstd;
@@ -158,42 +249,26 @@ __global__ void bn_apply_kernel(const __half* __restrict__ z, const float* __res
     }
 }
 
-// dz = gamma*invstd * (g - sum_g/M - zhat * sum_gz/M) = A*g + B*z + D per channel, g = dy * (y > 0);
-// optionally also writes g (identity-branch gradient). Per-channel coefficients live in registers (see bn_apply_kernel).
-__global__ void bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, const __half* __restrict__ z,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                    const double* __restrict__ s0, const double* __restrict__ s1, __half* __restrict__ dz,
-                                    __half* __restrict__ g_out, float* __restrict__ dgamma, float* __restrict__ dbeta, float inv_scale,
-                                    int64_t M, int C) {
+// dz = gamma*invstd * (g - sum_g/M - zhat * sum_gzhat/M) = A*g + B*z + D per channel, g = dy * (y > 0);
+// optionally also writes g (identity-branch gradient). Per-channel coefficients live in registers (see bn_apply_kernel);
+// two 16-byte units per thread are in flight per iteration.
+__global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, const __half* __restrict__ z,
+                                                              const float* __restrict__ coef, __half* __restrict__ dz, __half* __restrict__ g_out,
+                                                              int64_t M, int C) {
     const int C8 = C / 8;
     const int64_t total = M * C8;
-    const double invM = 1.0 / static_cast<double>(M);
-    if (blockIdx.x == 0) {
-        // parameter gradients (unscaled fp32); written once
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            dgamma[c] = static_cast<float>(s1[c]) * inv_scale;
-            dbeta[c] = static_cast<float>(s0[c]) * inv_scale;
-        }
-    }
     const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int col = static_cast<int>(i0 % C8) * 8;
     float A[8], B[8], D[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-        const int c = col + e;
-        const float is = invstd[c], ga = gamma[c], mu = mean[c];
-        const float mg = static_cast<float>(s0[c] * invM), mgz = static_cast<float>(s1[c] * invM);
-        A[e] = ga * is;
-        B[e] = -ga * is * is * mgz;
-        D[e] = -ga * is * mg + ga * is * is * mu * mgz;
+        A[e] = coef[col + e];
+        B[e] = coef[C + col + e];
+        D[e] = coef[2 * C + col + e];
     }
-    for (int64_t i = i0; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        float g[8], zz[8];
-        load8(dy + i * 8, g);
-        load8(z + i * 8, zz);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    auto finish = [&](int64_t i, float (&g)[8], const float (&zz)[8], const float (&yy)[8]) {
         if (y) {
-            float yy[8];
-            load8(y + i * 8, yy);
 #pragma unroll
             for (int e = 0; e < 8; ++e) g[e] = yy[e] > 0.f ? g[e] : 0.f;
         }
@@ -202,6 +277,27 @@ __global__ void bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half*
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] = fmaf(A[e], g[e], fmaf(B[e], zz[e], D[e]));
         store8(dz + i * 8, o);
+    };
+    int64_t i = i0;
+    for (; i + stride < total; i += 2 * stride) {
+        float g0[8], g1[8], z0[8], z1[8], y0[8], y1[8];
+        load8(dy + i * 8, g0);
+        load8(dy + (i + stride) * 8, g1);
+        load8(z + i * 8, z0);
+        load8(z + (i + stride) * 8, z1);
+        if (y) {
+            load8(y + i * 8, y0);
+            load8(y + (i + stride) * 8, y1);
+        }
+        finish(i, g0, z0, y0);
+        finish(i + stride, g1, z1, y1);
+    }
+    if (i < total) {
+        float g0[8], z0[8], y0[8];
+        load8(dy + i * 8, g0);
+        load8(z + i * 8, z0);
+        if (y) load8(y + i * 8, y0);
+        finish(i, g0, z0, y0);
     }
 }
 
@@ -491,13 +587,36 @@ static bool bad_c(int C) { return C <= 0 || (C % 8) || (C > 2048) || (256 % (C /
 extern "C" int rsb_bn_stats(const void* z, double* sums, int64_t M, int32_t C, void* stream) {
     if (!z || !sums || M <= 0 || bad_c(C) || C < 64) return set_error(RSB_E_INVALID, "bn_stats: bad arguments (C in 64..2048, power of two)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * kRedSlots + 2), st);
     if (e != cudaSuccess) return set_cuda_error(e, "bn_stats memset");
-    // every block folds >= 16 row groups before its 2*C fp64 atomics (wide, short tensors were atomic-bound otherwise)
-    const int rows_per_iter = 256 / (C / 8);
-    channel_reduce_kernel<0><<<tr_blocks((M + rows_per_iter * 16 - 1) / (rows_per_iter * 16), 1, 148 * 8), 256, 0, st>>>(
-        static_cast<const __half*>(z), nullptr, nullptr, nullptr, nullptr, sums, sums + C, M, C);
+    RedTail tail = {};
+    channel_reduce_kernel<0><<<reduce_blocks(M, C), 256, 0, st>>>(static_cast<const __half*>(z), nullptr, nullptr, sums, M, C, tail);
     RSB_LAUNCH_CHECK("bn_stats launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_bn_stats_finalize(const void* z, double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                     int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int64_t M, int32_t C, float eps,
+                                     float momentum, void* stream) {
+    if (!z || !sums || !gamma || !beta || !mean || !invstd || !scale || !shift || M <= 0 || bad_c(C) || C < 64)
+        return set_error(RSB_E_INVALID, "bn_stats_finalize: bad arguments (C in 64..2048, power of two)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * kRedSlots + 2), st);
+    if (e != cudaSuccess) return set_cuda_error(e, "bn_stats_finalize memset");
+    RedTail tail = {};
+    tail.gamma = gamma;
+    tail.beta = beta;
+    tail.running_mean = running_mean;
+    tail.running_var = running_var;
+    tail.num_batches = num_batches;
+    tail.mean = mean;
+    tail.invstd = invstd;
+    tail.scale = scale;
+    tail.shift = shift;
+    tail.eps = eps;
+    tail.momentum = momentum;
+    channel_reduce_kernel<0><<<reduce_blocks(M, C), 256, 0, st>>>(static_cast<const __half*>(z), nullptr, nullptr, sums, M, C, tail);
+    RSB_LAUNCH_CHECK("bn_stats_finalize launch");
     return RSB_OK;
 }
 
@@ -505,7 +624,7 @@ extern "C" int rsb_bn_finalize(const double* sums, const float* gamma, const flo
                                int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int32_t C, int64_t M,
                                float eps, float momentum, void* stream) {
     if (!sums || !gamma || !beta || !mean || !invstd || !scale || !shift || C <= 0 || M <= 0) return set_error(RSB_E_INVALID, "bn_finalize: bad arguments");
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, sums + C, gamma, beta, running_mean, running_var,
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, gamma, beta, running_mean, running_var,
                                                                                    num_batches, mean, invstd, scale, shift, C,
                                                                                    static_cast<double>(M), eps, momentum);
     RSB_LAUNCH_CHECK("bn_finalize launch");
@@ -527,15 +646,21 @@ extern "C" int rsb_bn_backward(const void* dy, const void* y, const void* z, con
     if (!dy || !z || !mean || !invstd || !gamma || !sums || !dz || !dgamma || !dbeta || M <= 0 || bad_c(C) || C < 64)
         return set_error(RSB_E_INVALID, "bn_backward: bad arguments");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * kRedSlots + 2), st);
     if (e != cudaSuccess) return set_cuda_error(e, "bn_backward memset");
-    const int rows_per_iter = 256 / (C / 8);
-    channel_reduce_kernel<1><<<tr_blocks((M + rows_per_iter * 16 - 1) / (rows_per_iter * 16), 1, 148 * 8), 256, 0, st>>>(
-        static_cast<const __half*>(dy), static_cast<const __half*>(y), static_cast<const __half*>(z), mean, invstd, sums, sums + C, M, C);
-    bn_bwd_apply_kernel<<<tr_blocks(M * (C / 8), 256), 256, 0, st>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
-                                                                   static_cast<const __half*>(z), mean, invstd, gamma, sums, sums + C,
-                                                                   static_cast<__half*>(dz), static_cast<__half*>(g_out), dgamma, dbeta,
-                                                                   inv_loss_scale, M, C);
+    RedTail tail = {};
+    tail.gamma = gamma;
+    tail.mean = const_cast<float*>(mean);
+    tail.invstd = const_cast<float*>(invstd);
+    tail.dgamma = dgamma;
+    tail.dbeta = dbeta;
+    tail.inv_scale = inv_loss_scale;
+    channel_reduce_kernel<1><<<reduce_blocks(M, C), 256, 0, st>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
+                                                                  static_cast<const __half*>(z), sums, M, C, tail);
+    const float* coef = reinterpret_cast<const float*>(sums + static_cast<int64_t>(kRedSlots) * 2 * C + 2);
+    bn_bwd_apply_kernel<<<tr_blocks((M * (C / 8) + 1) / 2, 256), 256, 0, st>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
+                                                                             static_cast<const __half*>(z), coef, static_cast<__half*>(dz),
+                                                                             static_cast<__half*>(g_out), M, C);
     RSB_LAUNCH_CHECK("bn_backward launch");
     return RSB_OK;
 }

@@ -270,7 +270,7 @@ class UNetTrainEngine:
     def _bn(self, prefix, z, M, C):
         b = Unit(prefix)
         b.prefix, b.z, b.M, b.C = prefix, z, M, C
-        b.sums = self._buf(2 * C, dtype=torch.float64)
+        b.sums = self._buf(20 * C, dtype=torch.float64)  # 8 accumulator slots x {sum0, sum1} x C, arrival counter, backward coefficients
         b.mean, b.invstd, b.scale, b.shift = (self._buf(C, dtype=torch.float32) for _ in range(4))
         return b
 
@@ -523,14 +523,15 @@ class UNetTrainEngine:
                 for gmap, chunk, used in self._unpack_all:
                     _lib.check(lib.rsb_unpack_grads(chunk.data_ptr(), gmap.data_ptr(), self._grads_flat.data_ptr(), used, 1.0 / self.loss_scale, st), "rsb_unpack_grads")
             elif k == "bn_stats":
-                b = op[1]
-                _lib.check(lib.rsb_bn_stats(b.z.data_ptr(), b.sums.data_ptr(), b.M, b.C, st), "rsb_bn_stats")
-            elif k == "bn_finalize":
+                # batch sums + (in the reduction's last block) statistics, folded scale/shift and the running-stat update
                 b = op[1]
                 pf = b.prefix
-                _lib.check(lib.rsb_bn_finalize(b.sums.data_ptr(), P[pf + ".weight"].data_ptr(), P[pf + ".bias"].data_ptr(), P[pf + ".running_mean"].data_ptr(),
-                                               P[pf + ".running_var"].data_ptr(), P[pf + ".num_batches_tracked"].data_ptr(), b.mean.data_ptr(),
-                                               b.invstd.data_ptr(), b.scale.data_ptr(), b.shift.data_ptr(), b.C, b.M, BN_EPS, BN_MOMENTUM, st), "rsb_bn_finalize")
+                _lib.check(lib.rsb_bn_stats_finalize(b.z.data_ptr(), b.sums.data_ptr(), P[pf + ".weight"].data_ptr(), P[pf + ".bias"].data_ptr(),
+                                                     P[pf + ".running_mean"].data_ptr(), P[pf + ".running_var"].data_ptr(),
+                                                     P[pf + ".num_batches_tracked"].data_ptr(), b.mean.data_ptr(), b.invstd.data_ptr(),
+                                                     b.scale.data_ptr(), b.shift.data_ptr(), b.M, b.C, BN_EPS, BN_MOMENTUM, st), "rsb_bn_stats_finalize")
+            elif k == "bn_finalize":
+                pass  # fused into the bn_stats launch (kept as an op for the CPU emulation of the plan)
             elif k == "bn_apply":
                 _, b, res, y, relu = op
                 _lib.check(lib.rsb_bn_apply(b.z.data_ptr(), b.scale.data_ptr(), b.shift.data_ptr(), res.data_ptr() if res is not None else None,

@@ -200,12 +200,12 @@ def run_train_ops(eng, ops, x=None, dlogits=None):
             b = op[1]
             z = b.z.reshape(b.M, b.C).double()
             b.sums[:b.C] = z.sum(0)
-            b.sums[b.C:] = (z * z).sum(0)
+            b.sums[b.C:2 * b.C] = (z * z).sum(0)
         elif k == "bn_finalize":
             b = op[1]
             pf = b.prefix
             mean = b.sums[:b.C] / b.M
-            var = (b.sums[b.C:] / b.M - mean * mean).clamp_min(0)
+            var = (b.sums[b.C:2 * b.C] / b.M - mean * mean).clamp_min(0)
             invstd = (1.0 / torch.sqrt(var + eng_eps())).float()
             b.mean.copy_(mean.float())
             b.invstd.copy_(invstd)

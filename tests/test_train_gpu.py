@@ -30,7 +30,7 @@ def _rel(a, b):
 def test_batchnorm_train_kernels(cuda_device):
     lib, st = _lib.load(), _lib.current_stream_ptr()
     g = torch.Generator().manual_seed(0)
-    for (M, C) in [(2 * 16 * 16, 64), (3 * 8 * 8, 2048), (5 * 7 * 9, 256)]:
+    for (M, C) in [(2 * 16 * 16, 64), (3 * 8 * 8, 2048), (5 * 7 * 9, 256), (4 * 96 * 96, 128)]:  # last: > 1000 blocks
         z = (torch.randn((M, C), generator=g) * 1.5 + 0.3).half()
         res = torch.randn((M, C), generator=g).half()
         gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
@@ -46,7 +46,7 @@ def test_batchnorm_train_kernels(cuda_device):
         zd, resd, dyd = z.to(d), res.to(d), dy.to(d)
         gd, bd, rmd, rvd = gamma.to(d), beta.to(d), rm.to(d), rv.to(d)
         nb = torch.zeros((), dtype=torch.int64, device=d)
-        sums = torch.zeros(2 * C, dtype=torch.float64, device=d)
+        sums = torch.zeros(20 * C, dtype=torch.float64, device=d)
         mean, invstd, scale, shift = (torch.zeros(C, device=d) for _ in range(4))
         y = torch.zeros((M, C), dtype=torch.float16, device=d)
         _lib.check(lib.rsb_bn_stats(zd.data_ptr(), sums.data_ptr(), M, C, st), "stats")
@@ -65,6 +65,17 @@ def test_batchnorm_train_kernels(cuda_device):
         assert _rel(dg.cpu() * 2, gt.grad) < 2e-3 and _rel(db.cpu() * 2, bt.grad) < 2e-3
         mask = (yr > 0).float()
         assert _rel(gout.float().cpu(), dy.float() * mask) < 1e-3
+        # one-launch variant used by the engine: statistics + finalize in the reduction's last block
+        rm2, rv2 = rm.to(d), rv.to(d)
+        nb2 = torch.zeros((), dtype=torch.int64, device=d)
+        outs2 = [torch.zeros(C, device=d) for _ in range(4)]
+        _lib.check(lib.rsb_bn_stats_finalize(zd.data_ptr(), sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), rm2.data_ptr(), rv2.data_ptr(), nb2.data_ptr(),
+                                             outs2[0].data_ptr(), outs2[1].data_ptr(), outs2[2].data_ptr(), outs2[3].data_ptr(), M, C, 1e-5, 0.1, st),
+                   "stats_finalize")
+        torch.cuda.synchronize()
+        for got, want in zip(outs2 + [rm2, rv2], [mean, invstd, scale, shift, rmd, rvd]):
+            assert torch.allclose(got, want, rtol=1e-6, atol=1e-6)
+        assert int(nb2.item()) == 1
 
 
 def test_relu_maxpool_final_pack_kernels(cuda_device):
