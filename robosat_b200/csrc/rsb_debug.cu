@@ -116,18 +116,27 @@ __global__ void __launch_bounds__(128, 1) debug_mma_rate_kernel(float* out, int 
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr;
     if (threadIdx.x == 0 && rank == 0) {
-        const uint32_t idesc = make_idesc_f16(TWO ? 256 : 128, block_n);
-        const uint64_t da0 = make_sw128_kmajor_desc(smem_u32(sa));
-        const uint64_t db0 = make_sw128_kmajor_desc(smem_u32(sb));
+        const bool mn_major = (commit_each & 2) != 0;  // both operands MN-major (the wgrad kernel's layout)
+        commit_each &= 1;
+        uint32_t idesc = make_idesc_f16(TWO ? 256 : 128, block_n);
+        uint64_t da0 = make_sw128_kmajor_desc(smem_u32(sa));
+        uint64_t db0 = make_sw128_kmajor_desc(smem_u32(sb));
+        if (mn_major) {
+            idesc |= (1u << 15) | (1u << 16);
+            // rows = K (pixels), 64 M/N elements per 128-byte row; LBO = 16 KB between 64-wide column blocks, SBO = 1024 B
+            da0 = (da0 & ~(0x3FFFull << 16)) | (static_cast<uint64_t>(16384 >> 4) << 16);
+            db0 = (db0 & ~(0x3FFFull << 16)) | (static_cast<uint64_t>(16384 >> 4) << 16);
+        }
         const long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
             const int st = it & 3;
-            const uint64_t da = da0 + static_cast<uint64_t>(st * (16384 >> 4));
-            const uint64_t db = db0 + static_cast<uint64_t>(st * (32768 >> 4));
+            const uint64_t da = mn_major ? da0 + static_cast<uint64_t>((st & 1) * 512) : da0 + static_cast<uint64_t>(st * (16384 >> 4));
+            const uint64_t db = mn_major ? db0 + static_cast<uint64_t>((st & 1) * 512) : db0 + static_cast<uint64_t>(st * (32768 >> 4));
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                if (TWO) umma_f16_pair(tmem, da + 2 * k, db + 2 * k, idesc, 1u);
-                else umma_f16(tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+                const uint64_t ka = mn_major ? 128 * k : 2 * k;  // K=16 step: 2048 B (16 pixel rows) vs 32 B inside the swizzle row
+                if (TWO) umma_f16_pair(tmem, da + ka, db + ka, idesc, 1u);
+                else umma_f16(tmem, da + ka, db + ka, idesc, 1u);
             }
             if (commit_each) {
                 if (TWO) umma_commit_pair(&bar[1 + (it & 3)]);

@@ -9,7 +9,7 @@
 // (layout verified on hardware with scripts/gpu_probe_umma.py).
 //
 // Work item = (128 output channels) x (phase) x (group of <= 4 consecutive 64-wide K blocks) x (slice of the pixel tiles).
-// Per pixel tile: one dY box (2 x 16 KB) + one X box per K block (16 KB each) by TMA, 8 MMAs (M128 x N64 x K16) per K block
+// Per 128-pixel tile: one dY box (2 x 16 KB) + one X box per K block (16 KB each) by TMA, 8 MMAs (M128 x N<=256 x K16)
 // into TMEM accumulators (64 fp32 columns per K block, 2 accumulator stages). Epilogue: tcgen05.ld -> fp32 atomicAdd into
 // the packed gradient (split-K over pixel slices).
 
@@ -24,8 +24,12 @@
 namespace rsb {
 
 static constexpr int kWgGroup = 4;                     // K blocks per work item
-static constexpr int kWgTileBytes = 128 * 64 * 2;      // one [128 px][64 ch] fp16 box
+static constexpr int kWgPx = 128;                      // pixels (contraction elements) per pipeline stage
+static constexpr int kWgTileBytes = kWgPx * 64 * 2;    // one [128 px][64 ch] fp16 box
 static constexpr int kWgStageBytes = (2 + kWgGroup) * kWgTileBytes;  // 96 KB
+// Measured alternatives (B200, batch 16, profiles/r1_train_ops_*.txt): 4 stages of 64 pixels (48 KB) were SLOWER per pixel
+// (dec3 1.38 vs 0.91 us per 128 pixels, dec0 115 vs 85 us): the per-stage barrier round trip and TMA issue cost more than the
+// extra loads in flight gain. Two 96 KB stages it is.
 static constexpr int kWgStages = 2;
 static constexpr int kWgSmem = kWgStages * kWgStageBytes + 256 + 1024;
 static constexpr int kWgThreads = 192;
@@ -172,7 +176,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
                     const uint32_t d_tmem = tmem_base + acc * kWgAccCols;
                     const uint32_t idesc_n = idesc_base | (static_cast<uint32_t>(nkb * 64 >> 3) << 17);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) umma_f16(d_tmem, da0 + 128 * k, db0 + 128 * k, idesc_n, k > 0 ? 1u : acc_first);
+                    for (int k = 0; k < kWgPx / 16; ++k) umma_f16(d_tmem, da0 + 128 * k, db0 + 128 * k, idesc_n, k > 0 ? 1u : acc_first);
                     umma_commit(&empty_bar[stage]);
                     if (++stage == kWgStages) {
                         stage = 0;
@@ -249,6 +253,13 @@ extern "C" int rsb_wgrad_plan_create(const rsb_conv_desc* d, const void* dy, flo
     *out_plan = nullptr;
     if (d->nsrc < 1 || d->nsrc > RSB_MAX_SRCS || d->nseg < 1 || d->nseg > RSB_MAX_SEGS) return set_error(RSB_E_INVALID, "wgrad: bad source/segment count");
     if (d->TW * d->TH * d->TN != 128) return set_error(RSB_E_INVALID, "wgrad: TW*TH*TN must be 128");
+    // a pipeline stage covers kWgPx pixels: the forward's 128-pixel tile box, or half of it
+    int bw = d->TW, bh = d->TH, bn = d->TN;
+    if (kWgPx == 64) {
+        if (bn % 2 == 0) bn /= 2;
+        else if (bh % 2 == 0) bh /= 2;
+        else bw /= 2;
+    }
     if (!(d->phases == 1 || d->phases == 4)) return set_error(RSB_E_INVALID, "wgrad: phases must be 1 or 4");
     int rc = rsb_device_ok();
     if (rc) return rc;
@@ -260,7 +271,7 @@ extern "C" int rsb_wgrad_plan_create(const rsb_conv_desc* d, const void* dy, flo
         const rsb_conv_src& s = d->srcs[i];
         const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)s.N};
         const uint64_t strides[3] = {(uint64_t)s.pitch_w * 2, (uint64_t)s.pitch_h * 2, (uint64_t)s.pitch_n * 2};
-        const uint32_t box[4] = {64, (uint32_t)d->TW, (uint32_t)d->TH, (uint32_t)d->TN};
+        const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
         rc = encode_tiled_f16(&kp.tmX[i], 4, s.ptr, dims, strides, box);
         if (rc) {
             delete plan;
@@ -272,7 +283,7 @@ extern "C" int rsb_wgrad_plan_create(const rsb_conv_desc* d, const void* dy, flo
         const int sy = d->out_sy > 0 ? d->out_sy : 1, sx = d->out_sx > 0 ? d->out_sx : 1;
         const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wt, (uint64_t)d->Ht, (uint64_t)d->Nt};
         const uint64_t strides[3] = {(uint64_t)sx * d->out_pitch_w * 2, (uint64_t)sy * d->out_pitch_h * 2, (uint64_t)d->out_pitch_n * 2};
-        const uint32_t box[4] = {64, (uint32_t)d->TW, (uint32_t)d->TH, (uint32_t)d->TN};
+        const uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
         for (int ph = 0; ph < 4; ++ph) {
             const int a = ph >> 1, b = ph & 1;
             const __half* base = static_cast<const __half*>(dy) + (ph < d->phases ? a * d->out_pitch_h + b * d->out_pitch_w : 0);
@@ -295,26 +306,36 @@ extern "C" int rsb_wgrad_plan_create(const rsb_conv_desc* d, const void* dy, flo
     kp.seg_kb0[d->nseg] = kb;
     kp.kblocks = kb;
     kp.kgroups = (kb + kWgGroup - 1) / kWgGroup;
-    kp.TW = d->TW;
-    kp.TH = d->TH;
-    kp.TN = d->TN;
-    kp.tiles_w = (d->Wt + d->TW - 1) / d->TW;
-    kp.tiles_h = (d->Ht + d->TH - 1) / d->TH;
-    kp.tiles_n = (d->Nt + d->TN - 1) / d->TN;
+    kp.TW = bw;
+    kp.TH = bh;
+    kp.TN = bn;
+    kp.tiles_w = (d->Wt + bw - 1) / bw;
+    kp.tiles_h = (d->Ht + bh - 1) / bh;
+    kp.tiles_n = (d->Nt + bn - 1) / bn;
     kp.ptiles = kp.tiles_w * kp.tiles_h * kp.tiles_n;
     kp.co_blocks = (d->Cout + 127) / 128;
     kp.phases = d->phases;
     kp.Cout = d->Cout;
     kp.K = static_cast<int64_t>(kb) * 64;
     kp.dw = dw_packed;
-    // split the pixel tiles so that there are a few work items per SM (each item ends with 128 x 256 fp32 atomics)
+    // split-K over slices of the pixel tiles: pick the slice count that minimises rounds x (tiles per item + epilogue),
+    // rounds = ceil(items / SMs) of the persistent grid (e.g. 160 items on 148 SMs would run two rounds for 12 extra items);
+    // every slice adds a full copy of the gradient tile (128 x 256 fp32 reductions ~ 8 stage times) to the traffic
     const int sms = num_sms();
     const int base_items = kp.co_blocks * kp.phases * kp.kgroups;
-    // (every slice adds a full copy of the gradient tile to the reduction traffic: one wave of items is enough)
-    int slices = (sms + base_items - 1) / base_items;
-    if (slices > kp.ptiles) slices = kp.ptiles;
-    if (slices < 1) slices = 1;
-    kp.tiles_per_slice = (kp.ptiles + slices - 1) / slices;
+    int64_t best_cost = -1;
+    int best_tps = kp.ptiles;
+    for (int sl = 1; sl <= kp.ptiles && sl <= 4 * sms; ++sl) {
+        const int tps = (kp.ptiles + sl - 1) / sl;
+        const int eff = (kp.ptiles + tps - 1) / tps;
+        const int64_t rounds = (static_cast<int64_t>(base_items) * eff + sms - 1) / sms;
+        const int64_t cost = rounds * (tps + 8);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best_tps = tps;
+        }
+    }
+    kp.tiles_per_slice = best_tps;
     kp.slices = (kp.ptiles + kp.tiles_per_slice - 1) / kp.tiles_per_slice;
     kp.total_items = base_items * kp.slices;
     plan->grid = kp.total_items < sms ? kp.total_items : sms;
