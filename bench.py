@@ -150,6 +150,38 @@ def layer_profile(engine, x, reps=3):
     return rows
 
 
+def serve_leg(dev, requests=100, warmup=10, size=512):
+    """`rs serve` request latency (serve.py:135-172): one 3x512x512 tile per call through
+    `SegmentEngine.run` -- pinned uint8 H2D, normalise, U-Net, argmax, uint8 D2H, host sync -- replayed as one CUDA graph,
+    and the same kernels launched one by one on the stream. Secondary figure beside the headline."""
+    import time
+
+    import torch
+
+    from robosat_b200 import synth
+    from robosat_b200.serve import SegmentEngine
+
+    sd = synth.make_state_dict(2, seed=0)
+    tiles = synth.make_tiles_u8(4, size, seed=5)
+    out = {"metric": "rs serve latency per 512x512 tile (batch 1, host to host)", "unit": "ms", "requests": requests}
+    for key, use_graph in (("graph_ms", True), ("stream_ms", False)):
+        eng = SegmentEngine(sd, 2, size, size, device=dev, use_graph=use_graph)
+        if use_graph and eng.graph is None:
+            out["graph_error"] = eng.graph_error
+            continue
+        for i in range(warmup):
+            eng.h_in.copy_(tiles[i % 4])
+            eng.run()
+        t0 = time.perf_counter()
+        for i in range(requests):
+            eng.h_in.copy_(tiles[i % 4])
+            eng.run()
+        out[key] = (time.perf_counter() - t0) * 1e3 / requests
+        del eng
+        torch.cuda.empty_cache()
+    return out
+
+
 def train_leg(dev, steps=8, warmup=3, batch=16):
     """BASELINE.json configs[2] (rs train: 2-class, Lovasz, 3x512x512, batch 16, 1 GPU): one step = zero_grad + train-mode forward
     + Lovasz loss + backward + Adam through the public module API. Reported beside the headline, never instead of it."""
@@ -334,6 +366,10 @@ def main():
                 line["train"] = train_leg(dev)
             except Exception as exc:  # the headline must survive a failure of the secondary measurement
                 line["train"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            try:
+                line["serve"] = serve_leg(dev)
+            except Exception as exc:
+                line["serve"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -170,6 +170,9 @@ int rsb_head_quantize(const float* logits, uint8_t* quant, float* probs_fg, int3
                       int32_t overlap, void* stream);
 /* softmax over C for any class count: logits fp32 [N][C][H][W] -> probs fp32 same shape (predict.py:87) */
 int rsb_softmax_nchw(const float* logits, float* probs, int32_t N, int32_t C, int32_t HW, void* stream);
+/* `Predictor.segment` head (robosat/tools/serve.py:150-165): output.argmax(axis=0).astype(uint8) of fp32 NCHW logits
+ * -> uint8 [N][H*W] class indices, first maximum wins like np.argmax; C <= 255. */
+int rsb_head_argmax(const float* logits, uint8_t* mask, int32_t N, int32_t C, int32_t HW, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Losses and metrics on fp32 NCHW logits + int64 targets [N][H][W].

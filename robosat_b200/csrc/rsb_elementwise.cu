@@ -123,6 +123,26 @@ __global__ void head_quantize_kernel(const float* __restrict__ logits, uint8_t* 
     quant[gid] = static_cast<uint8_t>(digitize256(pfg));  // 256 wraps to 0 exactly like .astype(np.uint8)
 }
 
+// per-pixel class index of fp32 NCHW logits (first maximum wins, like np.argmax): the `rs serve` mask, serve.py:150-165
+__global__ void head_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, int N, int C, int64_t HW) {
+    const int64_t total = static_cast<int64_t>(N) * HW;
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int64_t pix = gid % HW;
+    const int64_t n = gid / HW;
+    const float* l = logits + n * C * HW + pix;
+    float m = l[0];
+    int best = 0;
+    for (int c = 1; c < C; ++c) {
+        const float v = l[c * HW];
+        if (v > m) {
+            m = v;
+            best = c;
+        }
+    }
+    mask[gid] = static_cast<uint8_t>(best);
+}
+
 __global__ void softmax_nchw_kernel(const float* __restrict__ logits, float* __restrict__ probs, int N, int C, int64_t HW) {
     const int64_t total = static_cast<int64_t>(N) * HW;
     const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -184,6 +204,14 @@ extern "C" int rsb_head_quantize(const float* logits, uint8_t* quant, float* pro
     head_quantize_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, quant, probs_fg, N, H, W, overlap);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "head_quantize launch");
+}
+
+extern "C" int rsb_head_argmax(const float* logits, uint8_t* mask, int32_t N, int32_t C, int32_t HW, void* stream) {
+    if (!logits || !mask || N <= 0 || C <= 0 || C > 255 || HW <= 0) return set_error(RSB_E_INVALID, "head_argmax: bad arguments");
+    const int64_t total = static_cast<int64_t>(N) * HW;
+    head_argmax_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, mask, N, C, HW);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "head_argmax launch");
 }
 
 extern "C" int rsb_softmax_nchw(const float* logits, float* probs, int32_t N, int32_t C, int32_t HW, void* stream) {

@@ -1,9 +1,9 @@
-"""`python -m robosat_b200.tools {train,predict} ...` -- the two `rs` sub-commands on the hot path
+"""`python -m robosat_b200.tools {train,predict,serve} ...` -- the `rs` sub-commands on the hot path
 (dispatch as in robosat/tools/__main__.py:22-59; the other sub-commands stay with the reference package)."""
 
 import argparse
 
-from robosat_b200.tools import predict, train
+from robosat_b200.tools import predict, serve, train
 
 
 def add_parsers():
@@ -11,6 +11,7 @@ def add_parsers():
     subparser = parser.add_subparsers(title="robosat tools", metavar="")
     train.add_parser(subparser)
     predict.add_parser(subparser)
+    serve.add_parser(subparser)
     subparser.required = True
     return parser.parse_args()
 

@@ -124,3 +124,19 @@ def test_adam_state_dict_layout_needs_gpu():
     import robosat_b200.optim  # noqa: F401
     import robosat_b200.tools.predict  # noqa: F401
     import robosat_b200.tools.train  # noqa: F401
+
+
+def test_serve_tool_parser_and_cpu_refusal():
+    """`rs serve` keeps the reference's flags (serve.py:76-93); the B200 Predictor refuses a cuda=false config loudly."""
+    import argparse
+
+    from robosat_b200 import _lib
+    from robosat_b200.serve import Predictor
+    from robosat_b200.tools import serve
+
+    parser = argparse.ArgumentParser()
+    serve.add_parser(parser.add_subparsers())
+    args = parser.parse_args(["serve", "--model", "m.toml", "--dataset", "d.toml", "--checkpoint", "c.pth", "--url", "http://x/{z}/{x}/{y}"])
+    assert (args.tile_size, args.host, args.port) == (512, "127.0.0.1", 5000) and args.func is serve.main
+    with pytest.raises(_lib.RsbError):
+        Predictor({"state_dict": {}}, {"common": {"cuda": False}}, {"common": {"classes": ["a", "b"], "colors": ["denim", "orange"]}})
