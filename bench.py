@@ -162,23 +162,27 @@ def serve_leg(dev, requests=100, warmup=10, size=512):
     from robosat_b200.serve import SegmentEngine
 
     sd = synth.make_state_dict(2, seed=0)
-    tiles = synth.make_tiles_u8(4, size, seed=5)
+    tiles = synth.make_tiles_u8(4, size, seed=5).numpy()
+    threads = torch.get_num_threads()
+    torch.set_num_threads(1)  # the CPU-baseline leg leaves 100+ OpenMP workers spinning; a request is single-threaded host work
     out = {"metric": "rs serve latency per 512x512 tile (batch 1, host to host)", "unit": "ms", "requests": requests}
     for key, use_graph in (("graph_ms", True), ("stream_ms", False)):
         eng = SegmentEngine(sd, 2, size, size, device=dev, use_graph=use_graph)
         if use_graph and eng.graph is None:
             out["graph_error"] = eng.graph_error
             continue
+        h_in = eng.h_in.numpy()
         for i in range(warmup):
-            eng.h_in.copy_(tiles[i % 4])
+            h_in[0] = tiles[i % 4]
             eng.run()
         t0 = time.perf_counter()
         for i in range(requests):
-            eng.h_in.copy_(tiles[i % 4])
+            h_in[0] = tiles[i % 4]
             eng.run()
         out[key] = (time.perf_counter() - t0) * 1e3 / requests
-        del eng
+        del eng, h_in
         torch.cuda.empty_cache()
+    torch.set_num_threads(threads)
     return out
 
 

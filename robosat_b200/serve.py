@@ -75,12 +75,12 @@ class SegmentEngine:
 
     def segment_u8(self, tiles):
         """tiles: uint8 [H, W, 3] or [B, H, W, 3] (numpy or torch, host) -> numpy uint8 [H, W] / [B, H, W] class indices."""
-        t = torch.as_tensor(np.ascontiguousarray(tiles)) if not torch.is_tensor(tiles) else tiles
-        single = t.dim() == 3
+        t = tiles.numpy() if torch.is_tensor(tiles) else np.asarray(tiles)
+        single = t.ndim == 3
         if single:
-            t = t.unsqueeze(0)
-        assert tuple(t.shape) == (self.batch, self.H, self.W, 3) and t.dtype == torch.uint8, "expected uint8 [B, H, W, 3]"
-        self.h_in.copy_(t)
+            t = t[None]
+        assert t.shape == (self.batch, self.H, self.W, 3) and t.dtype == np.uint8, "expected uint8 [B, H, W, 3]"
+        self.h_in.numpy()[...] = t  # plain memcpy into the pinned staging buffer
         out = self.run().numpy().copy()
         return out[0] if single else out
 
