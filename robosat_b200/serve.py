@@ -6,8 +6,10 @@ Reference: PIL image -> ConvertImageMode("RGB") -> ImageToTensor -> Normalize ->
 
 Here the whole device side of that call -- H2D copy of the raw uint8 pixels from a pinned buffer, normalisation,
 the U-Net plan (60 launches), the per-pixel argmax and the D2H copy of one byte per pixel -- is captured ONCE into a
-CUDA graph and replayed per request: at batch 1 the 60 kernels are shorter than their launch overhead, so the eager
-stream is launch-bound and the graph is not. Weights, activations and both pinned staging buffers are static.
+CUDA graph and replayed per request: one driver call instead of 63 ctypes launches (0.17 ms of single-threaded host work per
+request, and immune to host jitter). Measured on B200 (scripts/gpu_serve_diag.py): the batch-1 forward is 0.60 ms of GPU time
+either way -- the kernels chain through programmatic dependent launch, so the stream version is not launch-bound either; the
+floor is ~10 us of prologue / pipeline fill per layer. Weights, activations and both pinned staging buffers are static.
 """
 
 import numpy as np
