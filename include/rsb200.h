@@ -170,6 +170,10 @@ int rsb_head_quantize(const float* logits, uint8_t* quant, float* probs_fg, int3
                       int32_t overlap, void* stream);
 /* softmax over C for any class count: logits fp32 [N][C][H][W] -> probs fp32 same shape (predict.py:87) */
 int rsb_softmax_nchw(const float* logits, float* probs, int32_t N, int32_t C, int32_t HW, void* stream);
+/* `buffer_tile_image` (robosat/tiles.py:162-227) on the device: builds B buffered tiles uint8 [B][S+2o][S+2o][3] from a cache of
+ * decoded RGB tiles uint8 [slots][S][S][3]. slots: int32 [B][9] (device), row-major over (dy, dx) in {-1,0,1}^2, entry 4 = the
+ * centre tile, -1 = no such neighbour (nodata 0, as the reference's Image.new(color=0)). */
+int rsb_stitch_halo(const uint8_t* cache, const int32_t* slots, uint8_t* out, int32_t B, int32_t S, int32_t overlap, void* stream);
 /* `Predictor.segment` head (robosat/tools/serve.py:150-165): output.argmax(axis=0).astype(uint8) of fp32 NCHW logits
  * -> uint8 [N][H*W] class indices, first maximum wins like np.argmax; C <= 255. */
 int rsb_head_argmax(const float* logits, uint8_t* mask, int32_t N, int32_t C, int32_t HW, void* stream);

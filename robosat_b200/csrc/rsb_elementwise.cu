@@ -123,6 +123,36 @@ __global__ void head_quantize_kernel(const float* __restrict__ logits, uint8_t* 
     quant[gid] = static_cast<uint8_t>(digitize256(pfg));  // 256 wraps to 0 exactly like .astype(np.uint8)
 }
 
+// Halo stitch (robosat/tiles.py:162-227 `buffer_tile_image`): canvas pixel (Y, X) of the (S+2o)^2 buffered tile comes from the
+// centre tile or one of its 8 neighbours, all resident in a device tile cache [slot][S][S][3] uint8; a missing neighbour
+// (slot < 0) leaves nodata = 0. One thread per 4 canvas bytes of a row (rows are 3*(S+2o) bytes; S, o multiples of 4).
+__global__ void stitch_halo_kernel(const uint8_t* __restrict__ cache, const int32_t* __restrict__ slots, uint8_t* __restrict__ out, int B, int S,
+                                   int o) {
+    const int F = S + 2 * o;
+    const int row_words = F * 3 / 4;
+    const int64_t total = static_cast<int64_t>(B) * F * row_words;
+    for (int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; gid < total; gid += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int wq = static_cast<int>(gid % row_words);
+        const int Y = static_cast<int>((gid / row_words) % F);
+        const int b = static_cast<int>(gid / (static_cast<int64_t>(row_words) * F));
+        const int dy = Y < o ? -1 : (Y < o + S ? 0 : 1);
+        const int sy = Y - o - dy * S;
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int byte = wq * 4 + k;  // byte inside the canvas row
+            const int X = byte / 3, c = byte - X * 3;
+            const int dx = X < o ? -1 : (X < o + S ? 0 : 1);
+            const int sx = X - o - dx * S;
+            const int slot = slots[b * 9 + (dy + 1) * 3 + (dx + 1)];
+            uint32_t v = 0;
+            if (slot >= 0) v = cache[((static_cast<int64_t>(slot) * S + sy) * S + sx) * 3 + c];
+            word |= v << (8 * k);
+        }
+        reinterpret_cast<uint32_t*>(out)[gid] = word;
+    }
+}
+
 // per-pixel class index of fp32 NCHW logits (first maximum wins, like np.argmax): the `rs serve` mask, serve.py:150-165
 __global__ void head_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, int N, int C, int64_t HW) {
     const int64_t total = static_cast<int64_t>(N) * HW;
@@ -204,6 +234,18 @@ extern "C" int rsb_head_quantize(const float* logits, uint8_t* quant, float* pro
     head_quantize_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, quant, probs_fg, N, H, W, overlap);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "head_quantize launch");
+}
+
+extern "C" int rsb_stitch_halo(const uint8_t* cache, const int32_t* slots, uint8_t* out, int32_t B, int32_t S, int32_t overlap, void* stream) {
+    if (!cache || !slots || !out || B <= 0 || S <= 0 || overlap < 0 || overlap > S || ((S + 2 * overlap) * 3) % 4)
+        return set_error(RSB_E_INVALID, "stitch_halo: bad arguments ((S + 2*overlap)*3 must be a multiple of 4, overlap <= S)");
+    const int F = S + 2 * overlap;
+    const int64_t total = static_cast<int64_t>(B) * F * (F * 3 / 4);
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    stitch_halo_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(cache, slots, out, B, S, overlap);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "stitch_halo launch");
 }
 
 extern "C" int rsb_head_argmax(const float* logits, uint8_t* mask, int32_t N, int32_t C, int32_t HW, void* stream) {

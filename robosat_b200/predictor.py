@@ -94,6 +94,33 @@ class TilePredictor:
         slot["busy"] = True
         self._pending.append(slot)
 
+    def device_input(self):
+        """The device input buffer the next `submit_device` will read: fill it on the current stream (e.g. with
+        `HaloStitcher.stitch`) instead of copying a host batch."""
+        slot = self._slots[self._next % self.depth]
+        if slot.get("busy"):
+            # the forward pass that last read this buffer must be done before new kernels overwrite it
+            torch.cuda.current_stream(self.device).wait_event(slot["consumed"])
+        return slot["d_in"]
+
+    def submit_device(self):
+        """`submit` for a batch that is already in `device_input()`: forward, head, D2H -- no host-to-device copy."""
+        slot = self._slots[self._next % self.depth]
+        self._next += 1
+        main = torch.cuda.current_stream(self.device)
+        if slot.get("busy"):
+            slot["done"].synchronize()
+        logits = self.engine.forward(slot["d_in"])
+        slot["consumed"].record(main)
+        self.quantize(logits, slot["d_q"])
+        slot["computed"].record(main)
+        with torch.cuda.stream(self._copy_out):
+            self._copy_out.wait_event(slot["computed"])
+            slot["h_q"].copy_(slot["d_q"], non_blocking=True)
+            slot["done"].record(self._copy_out)
+        slot["busy"] = True
+        self._pending.append(slot)
+
     def pinned_input(self):
         """The pinned staging buffer the next `submit` will use (fill it in place to skip one host copy)."""
         return self._slots[self._next % self.depth]["h_in"]

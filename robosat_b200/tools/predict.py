@@ -67,37 +67,77 @@ def _run(rank, world, args, port):
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
         sd = broadcast_state_dict(sd, unet_state_template(num_classes), device)  # the single collective of this tool
 
-    directory = BufferedSlippyMapDirectory(args.tiles, transform=ImageToUint8Tensor(), size=args.tile_size, overlap=args.overlap)
-    assert len(directory) > 0, "at least one tile in dataset"
-    lo, hi = shard_range(len(directory), rank, world)
-    loader = DataLoader(Subset(directory, range(lo, hi)), batch_size=args.batch_size, num_workers=args.workers)
-
     size = args.tile_size + 2 * args.overlap
-    predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device)
     palette = continuous_palette_for_color("pink", 256)
+    pool_threads = max(4, (os.cpu_count() or 8) // max(world, 1))
 
-    try:
-        from tqdm import tqdm
+    def progress(it, total):
+        try:
+            from tqdm import tqdm
 
-        batches = tqdm(loader, desc="Eval", unit="batch", ascii=True, disable=rank != 0)
-    except ImportError:  # pragma: no cover
-        batches = loader
+            return tqdm(it, total=total, desc="Eval", unit="batch", ascii=True, disable=rank != 0)
+        except ImportError:  # pragma: no cover
+            return it
 
-    with ThreadPoolExecutor(max_workers=max(4, (os.cpu_count() or 8) // max(world, 1))) as pool:
-        pending = []
-        for images, tiles in batches:
-            n = images.shape[0]
-            staging = predictor.pinned_input()
-            staging[:n].copy_(images)
-            if n < args.batch_size:
-                staging[n:].zero_()  # last, ragged batch: pad with black tiles and drop their outputs
-            predictor.submit(staging)
-            quantized = predictor.collect().numpy()
-            for tile, q in zip(tiles, quantized[:n]):
-                x, y, z = (int(v) for v in tile)
-                pending.append(pool.submit(_save_png, args.probs, palette, x, y, z, q.copy()))
-        for f in pending:
-            f.result()
+    if os.environ.get("RSB_HOST_STITCH", "0") == "1":
+        # reference-shaped input path: every buffered tile is assembled on the host (up to 9 decodes per tile) and copied over PCIe
+        directory = BufferedSlippyMapDirectory(args.tiles, transform=ImageToUint8Tensor(), size=args.tile_size, overlap=args.overlap)
+        assert len(directory) > 0, "at least one tile in dataset"
+        lo, hi = shard_range(len(directory), rank, world)
+        loader = DataLoader(Subset(directory, range(lo, hi)), batch_size=args.batch_size, num_workers=args.workers)
+        predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device)
+        with ThreadPoolExecutor(max_workers=pool_threads) as pool:
+            pending = []
+            for images, tiles in progress(loader, len(loader)):
+                n = images.shape[0]
+                staging = predictor.pinned_input()
+                staging[:n].copy_(images)
+                if n < args.batch_size:
+                    staging[n:].zero_()  # last, ragged batch: pad with black tiles and drop their outputs
+                predictor.submit(staging)
+                quantized = predictor.collect().numpy()
+                for tile, q in zip(tiles, quantized[:n]):
+                    x, y, z = (int(v) for v in tile)
+                    pending.append(pool.submit(_save_png, args.probs, palette, x, y, z, q.copy()))
+            for f in pending:
+                f.result()
+    else:
+        # default: decode every tile once, keep it in a device-resident cache and stitch the halo there (robosat_b200/stitch.py)
+        from robosat_b200.stitch import DeviceTileCache, HaloStitcher
+        from robosat_b200.tiles import tiles_from_slippy_map
+
+        index = dict(tiles_from_slippy_map(args.tiles))
+        assert len(index) > 0, "at least one tile in dataset"
+        order = sorted(index, key=lambda t: (int(t.z), int(t.x), int(t.y)))  # column-major: neighbours stay resident
+        lo, hi = shard_range(len(order), rank, world)
+        mine = order[lo:hi]
+        capacity = max(9 * args.batch_size, int(os.environ.get("RSB_TILE_CACHE", "2048")))
+        cache = DeviceTileCache(index, args.tile_size, capacity, device=device, workers=args.workers if args.workers > 0 else min(16, pool_threads))
+        stitcher = HaloStitcher(cache, args.overlap, args.batch_size)
+        predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device)
+        chunks = [mine[i:i + args.batch_size] for i in range(0, len(mine), args.batch_size)]
+        with ThreadPoolExecutor(max_workers=pool_threads) as pool:
+            pending = []
+
+            def drain(tiles):
+                quantized = predictor.collect().numpy()
+                for tile, q in zip(tiles, quantized[:len(tiles)]):
+                    pending.append(pool.submit(_save_png, args.probs, palette, int(tile.x), int(tile.y), int(tile.z), q.copy()))
+
+            previous = None
+            for tiles in progress(chunks, len(chunks)):
+                stitcher.stitch(tiles, predictor.device_input())  # decode + upload what is new, assemble the buffered batch on the device
+                predictor.submit_device()
+                if previous is not None:
+                    drain(previous)  # batch i-1 is collected while batch i runs
+                previous = tiles
+            if previous is not None:
+                drain(previous)
+            for f in pending:
+                f.result()
+        cache.close()
+        if rank == 0 and os.environ.get("RSB_VERBOSE"):
+            print("tile cache: %d decodes for %d tiles (%d cache hits)" % (cache.decodes, len(mine), cache.hits))
 
     if world > 1:
         import torch.distributed as dist

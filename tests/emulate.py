@@ -278,3 +278,24 @@ def run_train_ops(eng, ops, x=None, dlogits=None):
 
 def eng_eps():
     return 1e-5
+
+
+def stitch_halo_cpu(store, table, size, overlap):
+    """numpy restatement of csrc/rsb_elementwise.cu:stitch_halo_kernel (same index arithmetic), for the CPU suite."""
+    import numpy as np
+
+    B = table.shape[0]
+    F = size + 2 * overlap
+    out = np.zeros((B, F, F, 3), dtype=np.uint8)
+    for b in range(B):
+        for Y in range(F):
+            dy = -1 if Y < overlap else (0 if Y < overlap + size else 1)
+            sy = Y - overlap - dy * size
+            for dx, (x0, x1) in ((-1, (0, overlap)), (0, (overlap, overlap + size)), (1, (overlap + size, F))):
+                if x1 <= x0:
+                    continue
+                slot = int(table[b, (dy + 1) * 3 + (dx + 1)])
+                if slot < 0:
+                    continue
+                out[b, Y, x0:x1] = store[slot, sy, x0 - overlap - dx * size:x1 - overlap - dx * size]
+    return out

@@ -35,7 +35,18 @@ def test_rs_predict_end_to_end(tmp_path, cuda_device, monkeypatch):
     monkeypatch.setenv("RSB_GPUS", "1")
     args = argparse.Namespace(batch_size=2, checkpoint=str(ckpt), overlap=32, tile_size=256, workers=0, tiles=str(tiles_dir), probs=str(probs_dir),
                               model=str(tmp_path / "model.toml"), dataset=str(tmp_path / "dataset.toml"))
-    predict.main(args)
+    predict.main(args)  # default input path: tiles decoded once, halo stitched on the device (robosat_b200/stitch.py)
+
+    # the reference-shaped input path (buffered tiles assembled on the host) must give byte-identical masks
+    probs_host = tmp_path / "probs_host"
+    monkeypatch.setenv("RSB_HOST_STITCH", "1")
+    host_args = argparse.Namespace(**{**vars(args), "probs": str(probs_host)})
+    predict.main(host_args)
+    monkeypatch.delenv("RSB_HOST_STITCH")
+    for (x, y) in coords:
+        a = np.array(Image.open(probs_dir / "17" / str(x) / ("%d.png" % y)))
+        b = np.array(Image.open(probs_host / "17" / str(x) / ("%d.png" % y)))
+        assert np.array_equal(a, b), (x, y)
 
     directory = BufferedSlippyMapDirectory(str(tiles_dir), transform=ImageToUint8Tensor(), size=256, overlap=32)
     palette = colors.continuous_palette_for_color("pink", 256)
