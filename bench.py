@@ -186,6 +186,33 @@ def serve_leg(dev, requests=100, warmup=10, size=512):
     return out
 
 
+def stitch_leg(dev, batch=32, size=512, overlap=32, reps=50):
+    """Halo stitch on the device (tiles.py:162-227): one `rsb_stitch_halo` launch builds the buffered
+    batch uint8 [32][576][576][3] from the device tile cache. HBM-bound byte work: algorithmic bytes = canvas read + written."""
+    import torch
+
+    from robosat_b200 import _lib
+
+    lib = _lib.load()
+    F = size + 2 * overlap
+    store = torch.randint(0, 256, (9 * batch, size, size, 3), dtype=torch.uint8, device=dev)
+    table = torch.arange(9 * batch, dtype=torch.int32, device=dev).reshape(batch, 9).contiguous()
+    out = torch.empty((batch, F, F, 3), dtype=torch.uint8, device=dev)
+    st = _lib.current_stream_ptr()
+    for _ in range(3):
+        _lib.check(lib.rsb_stitch_halo(store.data_ptr(), table.data_ptr(), out.data_ptr(), batch, size, overlap, st), "rsb_stitch_halo")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        _lib.check(lib.rsb_stitch_halo(store.data_ptr(), table.data_ptr(), out.data_ptr(), batch, size, overlap, st), "rsb_stitch_halo")
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    gbps = 2 * out.numel() / ms / 1e6
+    return {"metric": "halo stitch of 32 buffered 576x576 tiles on the device", "ms_per_batch": ms, "achieved_gbps": gbps,
+            "peak_gbps": peaks()["hbm_gbs"], "frac": gbps / peaks()["hbm_gbs"], "tiles_per_s": batch / ms * 1e3}
+
+
 def train_leg(dev, steps=8, warmup=3, batch=16):
     """BASELINE.json configs[2] (rs train: 2-class, Lovasz, 3x512x512, batch 16, 1 GPU): one step = zero_grad + train-mode forward
     + Lovasz loss + backward + Adam through the public module API. Reported beside the headline, never instead of it."""
@@ -370,6 +397,10 @@ def main():
                 line["train"] = train_leg(dev)
             except Exception as exc:  # the headline must survive a failure of the secondary measurement
                 line["train"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+            try:
+                line["stitch"] = stitch_leg(dev)
+            except Exception as exc:
+                line["stitch"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
             try:
                 line["serve"] = serve_leg(dev)
             except Exception as exc:

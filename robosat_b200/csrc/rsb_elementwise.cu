@@ -153,6 +153,35 @@ __global__ void stitch_halo_kernel(const uint8_t* __restrict__ cache, const int3
     }
 }
 
+// Same, 4 pixels (12 bytes = three 32-bit words) per thread: with S and o multiples of 4 a group never straddles two source
+// tiles and both addresses are 4-byte aligned.
+__global__ void stitch_halo_x4_kernel(const uint8_t* __restrict__ cache, const int32_t* __restrict__ slots, uint8_t* __restrict__ out, int B, int S,
+                                      int o) {
+    const int F = S + 2 * o;
+    const int groups = F / 4;
+    const int64_t total = static_cast<int64_t>(B) * F * groups;
+    for (int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; gid < total; gid += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int X = static_cast<int>(gid % groups) * 4;
+        const int Y = static_cast<int>((gid / groups) % F);
+        const int b = static_cast<int>(gid / (static_cast<int64_t>(groups) * F));
+        const int dy = Y < o ? -1 : (Y < o + S ? 0 : 1);
+        const int dx = X < o ? -1 : (X < o + S ? 0 : 1);
+        const int sy = Y - o - dy * S, sx = X - o - dx * S;
+        const int slot = slots[b * 9 + (dy + 1) * 3 + (dx + 1)];
+        uint32_t w0 = 0, w1 = 0, w2 = 0;
+        if (slot >= 0) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(cache + ((static_cast<int64_t>(slot) * S + sy) * S + sx) * 3);
+            w0 = __ldg(src);
+            w1 = __ldg(src + 1);
+            w2 = __ldg(src + 2);
+        }
+        uint32_t* dst = reinterpret_cast<uint32_t*>(out + ((static_cast<int64_t>(b) * F + Y) * F + X) * 3);
+        dst[0] = w0;
+        dst[1] = w1;
+        dst[2] = w2;
+    }
+}
+
 // per-pixel class index of fp32 NCHW logits (first maximum wins, like np.argmax): the `rs serve` mask, serve.py:150-165
 __global__ void head_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, int N, int C, int64_t HW) {
     const int64_t total = static_cast<int64_t>(N) * HW;
@@ -243,7 +272,14 @@ extern "C" int rsb_stitch_halo(const uint8_t* cache, const int32_t* slots, uint8
     const int64_t total = static_cast<int64_t>(B) * F * (F * 3 / 4);
     int64_t blocks = (total + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
-    stitch_halo_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(cache, slots, out, B, S, overlap);
+    if (S % 4 == 0 && overlap % 4 == 0 && (reinterpret_cast<uintptr_t>(cache) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0) {
+        const int64_t groups = static_cast<int64_t>(B) * F * (F / 4);
+        int64_t gblocks = (groups + 255) / 256;
+        if (gblocks > 148 * 16) gblocks = 148 * 16;
+        stitch_halo_x4_kernel<<<static_cast<unsigned>(gblocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(cache, slots, out, B, S, overlap);
+    } else {
+        stitch_halo_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(cache, slots, out, B, S, overlap);
+    }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "stitch_halo launch");
 }

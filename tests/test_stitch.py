@@ -33,7 +33,7 @@ def _reference(index, tile, overlap):
     return np.asarray(buffer_tile_image(tile, index, overlap=overlap, tile_size=SIZE))
 
 
-@pytest.mark.parametrize("overlap", [0, 8, 32, 64])
+@pytest.mark.parametrize("overlap", [0, 6, 8, 32, 64])
 def test_table_and_index_arithmetic_match_buffer_tile_image(tmp_path, overlap):
     index = _make_store(str(tmp_path), COORDS)
     cache = DeviceTileCache(index, SIZE, capacity=32, device="cpu", workers=2)
@@ -67,7 +67,7 @@ def test_cache_evicts_least_recently_used_and_redecodes(tmp_path):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("overlap,batch", [(32, 4), (0, 3), (64, 2)])
+@pytest.mark.parametrize("overlap,batch", [(32, 4), (0, 3), (64, 2), (6, 4)])  # overlap 6: the byte-wise kernel
 def test_device_stitch_bit_exact(tmp_path, overlap, batch, cuda_device):
     index = _make_store(str(tmp_path), COORDS)
     cache = DeviceTileCache(index, SIZE, capacity=9 * batch, device=cuda_device, workers=4)  # minimal capacity: evictions happen
