@@ -1,4 +1,4 @@
-"""Builders for single-convolution parity cases shared by the GPU tests and scripts/gpu_diag.py.
+"""Builders for single-convolution parity cases shared by the GPU tests and tests/gpu_diag.py.
 
 Each case builds an `rsb_conv_desc` exactly the way `robosat_b200.engine.UNetEngine` does for that layer
 kind, plus a CPU fp32 reference of the same operation (torch functional ops on the fp16-rounded operands,

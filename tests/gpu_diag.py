@@ -1,8 +1,8 @@
 """GPU bring-up diagnostics: run every single-convolution case in its own subprocess (so a hung kernel
 costs one timeout, not the whole call) and append one JSON line per case to gpurun_out/diag.jsonl.
 
-    python scripts/gpu_diag.py            # driver: all cases, then the small whole-network check
-    python scripts/gpu_diag.py --case 3   # worker
+    python tests/gpu_diag.py            # driver: all cases, then the small whole-network check
+    python tests/gpu_diag.py --case 3   # worker
 """
 
 import argparse
@@ -14,7 +14,7 @@ import sys
 import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]  # a test-side tool: it may use the oracle
 OUT = os.path.join(ROOT, "gpurun_out")
 
 
