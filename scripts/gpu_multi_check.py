@@ -3,7 +3,6 @@
   * rs train  with RSB_GPUS=2 runs an epoch (one NCCL all-reduce of the flat gradient arena per step) and writes a checkpoint
 """
 import argparse
-import filecmp
 import os
 import sys
 import tempfile

@@ -1,5 +1,4 @@
 """Where does a batch-1 request spend its time? (run on the GPU box)"""
-import sys
 import time
 
 import torch

@@ -100,7 +100,6 @@ def decoder_case(N, lh, lw, cins, cout, device, seed=0, block_n=None):
 def stem_case(N, H, W, device, seed=0):
     """resnet conv1 7x7/2 pad 3 + folded bn + relu through the pre-pass and the overlapped-window view."""
     from robosat_b200 import _lib
-    import ctypes
 
     g = torch.Generator().manual_seed(seed)
     x = _rand((N, 3, H, W), g)

@@ -1,7 +1,6 @@
 """Host-side logic without a GPU: weight packing, parity / phase / window views and the whole engine graph,
 executed by the CPU emulator of the kernel's addressing (tests/emulate.py) and compared with the oracle."""
 
-import numpy as np
 import pytest
 import torch
 
