@@ -232,10 +232,12 @@ int rsb_bn_stats_finalize(const void* z, double* sums, const float* gamma, const
 int rsb_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y, int64_t M, int32_t C,
                  int32_t relu, void* stream);
 /* autograd of relu(bn(z) (+ identity)): g = dy * (y > 0) (y NULL: no mask); dz = gamma*invstd*(g - mean(g) - zhat*mean(g*zhat));
- * g_out (optional) receives g = the gradient of the identity branch; dgamma/dbeta fp32 multiplied by inv_loss_scale. */
+ * g_out (optional) receives g = the gradient of the identity branch; dgamma/dbeta fp32 multiplied by inv_loss_scale.
+ * mask_scale / mask_shift (with y NULL): the output was the plain y = half(relu(z*scale + shift)) of rsb_bn_apply, so its ReLU mask
+ * is re-derived from z (bit-identical: half(o) > 0 <=> o > 2^-25) and y is not read at all. */
 int rsb_bn_backward(const void* dy, const void* y, const void* z, const float* mean, const float* invstd, const float* gamma,
-                    double* sums, void* dz, void* g_out, float* dgamma, float* dbeta, float inv_loss_scale, int64_t M, int32_t C,
-                    void* stream);
+                    const float* mask_scale, const float* mask_shift, double* sums, void* dz, void* g_out, float* dgamma, float* dbeta,
+                    float inv_loss_scale, int64_t M, int32_t C, void* stream);
 /* out = (a (+ b)) * (y > 0): ReLU backward with optional gradient fan-in (skip connections); y NULL: plain sum */
 int rsb_relu_backward(const void* a, const void* b, const void* y, void* out, int64_t n, void* stream);
 /* autograd of max_pool2d (unet.py:125, :132) on NHWC fp16: first maximum of every window receives its gradient.

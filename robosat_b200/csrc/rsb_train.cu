@@ -82,19 +82,32 @@ __device__ __forceinline__ double red_slots(const double* sums, int which, int c
     return t;
 }
 
-template <int KIND>
+// ZMASK: the ReLU mask of a plain relu(bn(z)) output is re-derived from z instead of reading y: bn_apply_kernel rounds
+// o = fma(z, scale, shift) to fp16, and half(o) > 0 exactly when o > 2^-25 (round-to-nearest-even), so the mask is bit-identical.
+static constexpr float kHalfPositive = 0x1p-25f;
+
+template <int KIND, bool ZMASK = false>
 __global__ void __launch_bounds__(256, 3) channel_reduce_kernel(const __half* __restrict__ a, const __half* __restrict__ y, const __half* __restrict__ z,
-                                                             double* __restrict__ sums, int64_t M, int C, const RedTail tail) {
+                                                             double* __restrict__ sums, int64_t M, int C, const RedTail tail,
+                                                             const float* __restrict__ msc = nullptr, const float* __restrict__ msh = nullptr) {
     __shared__ float sh0[256 * 8];
     __shared__ float sh1[256 * 8];
     const int tpr = C / 8;
     const int rows_per_iter = 256 / tpr;
     const int col = (threadIdx.x % tpr) * 8;
     const int rsub = threadIdx.x / tpr;
-    float acc0[8], acc1[8];
+    float acc0[8], acc1[8], zsc[8], zsh[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc0[i] = acc1[i] = 0.f;
+    for (int i = 0; i < 8; ++i) {
+        acc0[i] = acc1[i] = 0.f;
+        zsc[i] = ZMASK ? msc[col + i] : 0.f;
+        zsh[i] = ZMASK ? msh[col + i] : 0.f;
+    }
     const int64_t step = static_cast<int64_t>(gridDim.x) * rows_per_iter;
+    auto zmask = [&](const float (&zz)[8], float (&yy)[8]) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) yy[i] = fmaf(zz[i], zsc[i], zsh[i]) > kHalfPositive ? 1.f : 0.f;
+    };
     auto fold = [&](const float (&v)[8], const float (&zz)[8], const float (&yy)[8], bool masked) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -116,22 +129,26 @@ __global__ void __launch_bounds__(256, 3) channel_reduce_kernel(const __half* __
         if (KIND == 1) {
             load8(z + r * C + col, z0);
             load8(z + (r + step) * C + col, z1);
-            if (y) {
+            if (ZMASK) {
+                zmask(z0, y0);
+                zmask(z1, y1);
+            } else if (y) {
                 load8(y + r * C + col, y0);
                 load8(y + (r + step) * C + col, y1);
             }
         }
-        fold(v0, z0, y0, y != nullptr);
-        fold(v1, z1, y1, y != nullptr);
+        fold(v0, z0, y0, ZMASK || y != nullptr);
+        fold(v1, z1, y1, ZMASK || y != nullptr);
     }
     if (r < M) {
         float v0[8], z0[8], y0[8];
         load8(a + r * C + col, v0);
         if (KIND == 1) {
             load8(z + r * C + col, z0);
-            if (y) load8(y + r * C + col, y0);
+            if (ZMASK) zmask(z0, y0);
+            else if (y) load8(y + r * C + col, y0);
         }
-        fold(v0, z0, y0, y != nullptr);
+        fold(v0, z0, y0, ZMASK || y != nullptr);
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -252,23 +269,29 @@ __global__ void bn_apply_kernel(const __half* __restrict__ z, const float* __res
 // dz = gamma*invstd * (g - sum_g/M - zhat * sum_gzhat/M) = A*g + B*z + D per channel, g = dy * (y > 0);
 // optionally also writes g (identity-branch gradient). Per-channel coefficients live in registers (see bn_apply_kernel);
 // two 16-byte units per thread are in flight per iteration.
+template <bool ZMASK>
 __global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, const __half* __restrict__ z,
                                                               const float* __restrict__ coef, __half* __restrict__ dz, __half* __restrict__ g_out,
-                                                              int64_t M, int C) {
+                                                              int64_t M, int C, const float* __restrict__ msc, const float* __restrict__ msh) {
     const int C8 = C / 8;
     const int64_t total = M * C8;
     const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
     const int col = static_cast<int>(i0 % C8) * 8;
-    float A[8], B[8], D[8];
+    float A[8], B[8], D[8], zsc[8], zsh[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
         A[e] = coef[col + e];
         B[e] = coef[C + col + e];
         D[e] = coef[2 * C + col + e];
+        zsc[e] = ZMASK ? msc[col + e] : 0.f;
+        zsh[e] = ZMASK ? msh[col + e] : 0.f;
     }
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     auto finish = [&](int64_t i, float (&g)[8], const float (&zz)[8], const float (&yy)[8]) {
-        if (y) {
+        if (ZMASK) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) g[e] = fmaf(zz[e], zsc[e], zsh[e]) > kHalfPositive ? g[e] : 0.f;
+        } else if (y) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) g[e] = yy[e] > 0.f ? g[e] : 0.f;
         }
@@ -285,7 +308,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const __half* __re
         load8(dy + (i + stride) * 8, g1);
         load8(z + i * 8, z0);
         load8(z + (i + stride) * 8, z1);
-        if (y) {
+        if (!ZMASK && y) {
             load8(y + i * 8, y0);
             load8(y + (i + stride) * 8, y1);
         }
@@ -296,7 +319,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const __half* __re
         float g0[8], z0[8], y0[8];
         load8(dy + i * 8, g0);
         load8(z + i * 8, z0);
-        if (y) load8(y + i * 8, y0);
+        if (!ZMASK && y) load8(y + i * 8, y0);
         finish(i, g0, z0, y0);
     }
 }
@@ -641,10 +664,12 @@ extern "C" int rsb_bn_apply(const void* z, const float* scale, const float* shif
 }
 
 extern "C" int rsb_bn_backward(const void* dy, const void* y, const void* z, const float* mean, const float* invstd, const float* gamma,
-                               double* sums, void* dz, void* g_out, float* dgamma, float* dbeta, float inv_loss_scale, int64_t M,
-                               int32_t C, void* stream) {
+                               const float* mask_scale, const float* mask_shift, double* sums, void* dz, void* g_out, float* dgamma, float* dbeta,
+                               float inv_loss_scale, int64_t M, int32_t C, void* stream) {
     if (!dy || !z || !mean || !invstd || !gamma || !sums || !dz || !dgamma || !dbeta || M <= 0 || bad_c(C) || C < 64)
         return set_error(RSB_E_INVALID, "bn_backward: bad arguments");
+    if ((mask_scale != nullptr) != (mask_shift != nullptr) || (mask_scale && y))
+        return set_error(RSB_E_INVALID, "bn_backward: pass either y, or mask_scale + mask_shift, or neither");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * kRedSlots + 2), st);
     if (e != cudaSuccess) return set_cuda_error(e, "bn_backward memset");
@@ -655,12 +680,20 @@ extern "C" int rsb_bn_backward(const void* dy, const void* y, const void* z, con
     tail.dgamma = dgamma;
     tail.dbeta = dbeta;
     tail.inv_scale = inv_loss_scale;
-    channel_reduce_kernel<1><<<reduce_blocks(M, C), 256, 0, st>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
-                                                                  static_cast<const __half*>(z), sums, M, C, tail);
+    const __half* dyh = static_cast<const __half*>(dy);
+    const __half* yh = static_cast<const __half*>(y);
+    const __half* zh = static_cast<const __half*>(z);
     const float* coef = reinterpret_cast<const float*>(sums + static_cast<int64_t>(kRedSlots) * 2 * C + 2);
-    bn_bwd_apply_kernel<<<tr_blocks((M * (C / 8) + 1) / 2, 256), 256, 0, st>>>(static_cast<const __half*>(dy), static_cast<const __half*>(y),
-                                                                             static_cast<const __half*>(z), coef, static_cast<__half*>(dz),
-                                                                             static_cast<__half*>(g_out), M, C);
+    const unsigned ablocks = tr_blocks((M * (C / 8) + 1) / 2, 256);
+    if (mask_scale) {
+        channel_reduce_kernel<1, true><<<reduce_blocks(M, C), 256, 0, st>>>(dyh, nullptr, zh, sums, M, C, tail, mask_scale, mask_shift);
+        bn_bwd_apply_kernel<true><<<ablocks, 256, 0, st>>>(dyh, nullptr, zh, coef, static_cast<__half*>(dz), static_cast<__half*>(g_out), M, C,
+                                                            mask_scale, mask_shift);
+    } else {
+        channel_reduce_kernel<1, false><<<reduce_blocks(M, C), 256, 0, st>>>(dyh, yh, zh, sums, M, C, tail);
+        bn_bwd_apply_kernel<false><<<ablocks, 256, 0, st>>>(dyh, yh, zh, coef, static_cast<__half*>(dz), static_cast<__half*>(g_out), M, C, nullptr,
+                                                             nullptr);
+    }
     RSB_LAUNCH_CHECK("bn_backward launch");
     return RSB_OK;
 }

@@ -278,6 +278,7 @@ class UNetTrainEngine:
         self.fwd_ops.append(("bn_stats", b))
         self.fwd_ops.append(("bn_finalize", b))
         self.fwd_ops.append(("bn_apply", b, residual, y, relu))
+        b.plain_relu_y = y if (residual is None and relu) else None
 
     # ---------------------------------------------------------------- graph
     def _build(self):
@@ -539,8 +540,12 @@ class UNetTrainEngine:
             elif k == "bn_bwd":
                 _, b, dy, y, dz, g = op
                 pf = b.prefix
-                _lib.check(lib.rsb_bn_backward(dy.data_ptr(), y.data_ptr() if y is not None else None, b.z.data_ptr(), b.mean.data_ptr(), b.invstd.data_ptr(),
-                                               P[pf + ".weight"].data_ptr(), b.sums.data_ptr(), dz.data_ptr(), g.data_ptr() if g is not None else None,
+                # y = half(relu(z*scale + shift)) with no identity branch: the mask is re-derived from z, y is not read
+                zmask = y is not None and getattr(b, "plain_relu_y", None) is y
+                _lib.check(lib.rsb_bn_backward(dy.data_ptr(), y.data_ptr() if (y is not None and not zmask) else None, b.z.data_ptr(),
+                                               b.mean.data_ptr(), b.invstd.data_ptr(), P[pf + ".weight"].data_ptr(),
+                                               b.scale.data_ptr() if zmask else None, b.shift.data_ptr() if zmask else None,
+                                               b.sums.data_ptr(), dz.data_ptr(), g.data_ptr() if g is not None else None,
                                                self._grad(pf + ".weight").data_ptr(), self._grad(pf + ".bias").data_ptr(), 1.0 / self.loss_scale,
                                                b.M, b.C, st), "rsb_bn_backward")
             elif k == "relu_bwd":

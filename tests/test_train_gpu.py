@@ -55,8 +55,8 @@ def test_batchnorm_train_kernels(cuda_device):
         _lib.check(lib.rsb_bn_apply(zd.data_ptr(), scale.data_ptr(), shift.data_ptr(), resd.data_ptr(), y.data_ptr(), M, C, 1, st), "apply")
         dz, gout = torch.zeros_like(y), torch.zeros_like(y)
         dg, db = torch.zeros(C, device=d), torch.zeros(C, device=d)
-        _lib.check(lib.rsb_bn_backward(dyd.data_ptr(), y.data_ptr(), zd.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gd.data_ptr(), sums.data_ptr(),
-                                       dz.data_ptr(), gout.data_ptr(), dg.data_ptr(), db.data_ptr(), 0.5, M, C, st), "bwd")
+        _lib.check(lib.rsb_bn_backward(dyd.data_ptr(), y.data_ptr(), zd.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gd.data_ptr(), None, None,
+                                       sums.data_ptr(), dz.data_ptr(), gout.data_ptr(), dg.data_ptr(), db.data_ptr(), 0.5, M, C, st), "bwd")
         torch.cuda.synchronize()
         yr = y_ref.detach().reshape(C, M).t()
         assert (y.float().cpu() - yr).abs().max().item() <= 4e-3 * max(1.0, yr.abs().max().item() / 4)
@@ -65,6 +65,21 @@ def test_batchnorm_train_kernels(cuda_device):
         assert _rel(dg.cpu() * 2, gt.grad) < 2e-3 and _rel(db.cpu() * 2, bt.grad) < 2e-3
         mask = (yr > 0).float()
         assert _rel(gout.float().cpu(), dy.float() * mask) < 1e-3
+        # plain relu(bn(z)) (no identity branch): the mask re-derived from z gives the same bits as the mask read from y
+        y2 = torch.zeros_like(y)
+        _lib.check(lib.rsb_bn_apply(zd.data_ptr(), scale.data_ptr(), shift.data_ptr(), None, y2.data_ptr(), M, C, 1, st), "apply")
+        outs = []
+        for use_z in (False, True):
+            dz2, go2 = torch.zeros_like(y), torch.zeros_like(y)
+            dg2, db2 = torch.zeros(C, device=d), torch.zeros(C, device=d)
+            _lib.check(lib.rsb_bn_backward(dyd.data_ptr(), None if use_z else y2.data_ptr(), zd.data_ptr(), mean.data_ptr(), invstd.data_ptr(), gd.data_ptr(),
+                                           scale.data_ptr() if use_z else None, shift.data_ptr() if use_z else None, sums.data_ptr(), dz2.data_ptr(),
+                                           go2.data_ptr(), dg2.data_ptr(), db2.data_ptr(), 1.0, M, C, st), "bwd")
+            torch.cuda.synchronize()
+            outs.append((dz2.clone(), go2.clone(), dg2.clone(), db2.clone()))
+        assert torch.equal(outs[0][1], outs[1][1])  # the masked gradient: identical masks
+        assert torch.allclose(outs[0][0].float(), outs[1][0].float(), atol=2e-3, rtol=2e-3)  # dz: fp64 atomics may reorder the sums' last bits
+        assert torch.allclose(outs[0][2], outs[1][2], rtol=1e-5, atol=1e-6) and torch.allclose(outs[0][3], outs[1][3], rtol=1e-5, atol=1e-6)
         # one-launch variant used by the engine: statistics + finalize in the reduction's last block
         rm2, rv2 = rm.to(d), rv.to(d)
         nb2 = torch.zeros((), dtype=torch.int64, device=d)
