@@ -120,6 +120,8 @@ SIGNATURES = {
     "rsb_maxpool_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rsb_head_quantize": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rsb_stitch_halo": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
+    "rsb_softvote": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64, _vp]),
+    "rsb_class_histogram": (ctypes.c_int, [_vp, _i64, _i32, _vp, _vp]),
     "rsb_head_argmax": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "rsb_softmax_nchw": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _vp]),
     "rsb_cross_entropy": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp]),

@@ -182,6 +182,45 @@ __global__ void stitch_halo_x4_kernel(const uint8_t* __restrict__ cache, const i
     }
 }
 
+// `rs masks` (robosat/tools/masks.py:42-84): un-quantise K probability maps (`anchors[q]`, anchors = np.linspace(0, 1, 256)),
+// weighted-average them (np.average over the model axis) and take the arg-max of [background, foreground]. All arithmetic in
+// float64 in numpy's order (products rounded, sequential sum over the K inputs, one division by the weight sum / count), so
+// the result is bit-identical, including ties (arg-max returns the first maximum = background).
+__global__ void softvote_kernel(const uint8_t* __restrict__ quant, const double* __restrict__ weights, uint8_t* __restrict__ mask, int K, int64_t n) {
+    const double step = 1.0 / 255.0;
+    double scl = 0.0;
+    for (int k = 0; k < K; ++k) scl += weights ? weights[k] : 1.0;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        double fs = 0.0, bs = 0.0;
+        for (int k = 0; k < K; ++k) {
+            const int q = quant[static_cast<int64_t>(k) * n + i];
+            const double f = q >= 255 ? 1.0 : static_cast<double>(q) * step;  // linspace pins its last anchor to 1.0
+            const double b = 1.0 - f;
+            if (weights) {
+                // separate IEEE multiply and add, as numpy does (no FMA contraction: it would change the last bit and flip ties)
+                fs = __dadd_rn(fs, __dmul_rn(f, weights[k]));
+                bs = __dadd_rn(bs, __dmul_rn(b, weights[k]));
+            } else {
+                fs += f;
+                bs += b;
+            }
+        }
+        mask[i] = (fs / scl > bs / scl) ? 1 : 0;
+    }
+}
+
+// `rs weights` (robosat/tools/weights.py:39-49): np.bincount of the training masks, per class, accumulated over calls
+__global__ void class_histogram_kernel(const uint8_t* __restrict__ labels, int64_t n, int C, unsigned long long* __restrict__ counts) {
+    __shared__ unsigned int sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+        atomicAdd(&sh[labels[i]], 1u);
+    __syncthreads();
+    if (threadIdx.x < C && sh[threadIdx.x]) atomicAdd(&counts[threadIdx.x], static_cast<unsigned long long>(sh[threadIdx.x]));
+    // labels >= C are counted in shared memory but dropped here; the host checks the total (np.bincount would grow instead)
+}
+
 // per-pixel class index of fp32 NCHW logits (first maximum wins, like np.argmax): the `rs serve` mask, serve.py:150-165
 __global__ void head_argmax_kernel(const float* __restrict__ logits, uint8_t* __restrict__ mask, int N, int C, int64_t HW) {
     const int64_t total = static_cast<int64_t>(N) * HW;
@@ -282,6 +321,21 @@ extern "C" int rsb_stitch_halo(const uint8_t* cache, const int32_t* slots, uint8
     }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "stitch_halo launch");
+}
+
+extern "C" int rsb_softvote(const uint8_t* quant, const double* weights, uint8_t* mask, int32_t K, int64_t n, void* stream) {
+    if (!quant || !mask || K < 1 || n <= 0) return set_error(RSB_E_INVALID, "softvote: bad arguments");
+    softvote_kernel<<<grid_for(n, 256) > 148 * 16 ? 148 * 16 : grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(quant, weights, mask, K, n);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "softvote launch");
+}
+
+extern "C" int rsb_class_histogram(const uint8_t* labels, int64_t n, int32_t C, uint64_t* counts, void* stream) {
+    if (!labels || !counts || n <= 0 || C < 1 || C > 256) return set_error(RSB_E_INVALID, "class_histogram: bad arguments");
+    class_histogram_kernel<<<grid_for(n, 256) > 148 * 8 ? 148 * 8 : grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        labels, n, C, reinterpret_cast<unsigned long long*>(counts));
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "class_histogram launch");
 }
 
 extern "C" int rsb_head_argmax(const float* logits, uint8_t* mask, int32_t N, int32_t C, int32_t HW, void* stream) {
