@@ -9,6 +9,7 @@ import pytest
 import torch
 from PIL import Image
 
+from robosat_b200 import colors
 from robosat_b200.tools import masks, weights
 
 
@@ -74,7 +75,9 @@ def test_masks_and_weights_tools_end_to_end(tmp_path, cuda_device, capsys):
             os.makedirs(root / "18" / str(x), exist_ok=True)
             q = rng.randint(0, 256, size=(64, 64)).astype(np.uint8)
             quant[(k, x, y)] = q
-            Image.fromarray(q, mode="P").save(root / "18" / str(x) / ("%d.png" % y))
+            img = Image.fromarray(q, mode="P")
+            img.putpalette(colors.continuous_palette_for_color("pink", 256))  # what rs predict writes (predict.py:105-108)
+            img.save(root / "18" / str(x) / ("%d.png" % y), optimize=True)
     out = tmp_path / "masks"
     masks.main(argparse.Namespace(masks=str(out), probs=dirs, weights=[0.3, 0.7]))
     for (x, y) in coords:
@@ -88,7 +91,9 @@ def test_masks_and_weights_tools_end_to_end(tmp_path, cuda_device, capsys):
         os.makedirs(labels / "18" / str(x), exist_ok=True)
         m = (rng.rand(64, 64) < 0.2).astype(np.uint8)
         allpix.append(m.ravel())
-        Image.fromarray(m, mode="P").save(labels / "18" / str(x) / ("%d.png" % y))
+        img = Image.fromarray(m, mode="P")
+        img.putpalette(colors.make_palette("denim", "orange"))
+        img.save(labels / "18" / str(x) / ("%d.png" % y), optimize=True)
     (tmp_path / "dataset.toml").write_text("[common]\ndataset = '%s'\nclasses = ['background', 'parking']\ncolors = ['denim', 'orange']\n" % (tmp_path / "ds"))
     weights.main(argparse.Namespace(dataset=str(tmp_path / "dataset.toml")))
     printed = capsys.readouterr().out.strip().splitlines()[-1]
