@@ -402,7 +402,7 @@ def main():
                 "e2e": {"value": tiles / (e2e_ms / 1e3), "unit": "tiles/s", "h2d_bytes_per_step": pred.h2d_bytes, "d2h_bytes_per_step": pred.d2h_bytes,
                         "wall_ms": wall_ms, "api": "TilePredictor.submit/collect (pinned uint8 in, uint8 bins out)"},
                 "gpu_launches": world * args.steps * pred.num_launches(), "clocks": clocks, "roofline": roof}
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline:  # the CPU baseline is an N=1 figure (rank 0 only)
             cb, _ = cpu_reference_leg(steps=2, warmup=1, tiles_per_step=2)
             line["cpu_baseline"] = cb
         if world == 1 and not args.no_train:
