@@ -120,3 +120,26 @@ def test_train_engine_plan_matches_autograd_on_cpu():
     rels = [((eng.grads[k] - v.grad).pow(2).sum().sqrt() / v.grad.pow(2).sum().sqrt().clamp_min(1e-30)).item()
             for k, v in sdg.items() if v.requires_grad and not k.startswith("resnet.fc")]
     assert len(rels) == 168 and max(rels) < 6e-2 and sorted(rels)[len(rels) // 2] < 3e-2, (max(rels), sorted(rels)[len(rels) // 2])
+
+
+def test_cta_pair_policy_respects_kernel_constraints():
+    """Every descriptor the predict plan marks for CTA pairs satisfies what rsb_conv_plan_create demands (mode 0, block_n >= 128,
+    at least two spatial tiles) and the policy is on by default for the long-K wide layers (dec0/dec1/dec3, 3x3 of layer2-4)."""
+    from robosat_b200 import synth
+    from robosat_b200.engine import UNetEngine
+
+    eng = UNetEngine(synth.make_state_dict(2, seed=0), 2, 32, 512, 512, device="cpu", plan_only=True)
+    paired = {}
+    for op in eng.ops:
+        if op[0] != "conv" or not hasattr(op[1].desc, "nseg"):
+            continue
+        d = op[1].desc
+        kblocks = sum(d.segs[i].cblocks for i in range(d.nseg))
+        tiles = -(-d.Wt // d.TW) * -(-d.Ht // d.TH) * -(-d.Nt // d.TN)
+        if d.cta_pair:
+            assert d.mode == 0 and d.block_n >= 128 and tiles >= 2 and d.Cout % d.block_n == 0, op[1].name
+            assert (d.block_n == 256 and kblocks >= 6) or (d.block_n == 128 and kblocks >= 18), op[1].name
+            paired[op[1].name] = d.block_n
+    for name in ("dec0", "dec1", "dec3", "resnet.layer2.1.conv2", "resnet.layer3.2.conv2", "resnet.layer4.1.conv2"):
+        assert name in paired, name
+    assert "dec2" not in paired and "stem" not in paired  # Cout = 64: narrow tiles stay on one CTA
