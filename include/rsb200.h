@@ -12,6 +12,7 @@
  *   - return value: 0 on success, negative RSB_E_* on failure; rsb_last_error() gives the message
  *     (thread local). There is NO CPU fallback: without a usable sm_100 device every compute entry fails.
  *   - activations are NHWC fp16 ("channels last"), accumulators fp32; weights are pre-packed fp16
+ *   - two precisions: "fast" (one fp16 plane per tensor) and "strict" (hi + lo fp16 planes, see rsb_conv_desc.split)
  */
 #ifndef RSB200_H
 #define RSB200_H
@@ -31,6 +32,9 @@ extern "C" {
 #define RSB_MAX_SRCS 4
 
 int rsb_version(void);
+/* sizeof(rsb_conv_src), sizeof(rsb_conv_seg), sizeof(rsb_conv_desc), sizeof(rsb_rowconv_desc) as compiled into the library,
+ * so that a binding (ctypes, cgo, ...) can verify its struct declarations before the first call */
+void rsb_abi_layout(int32_t* out4);
 const char* rsb_last_error(void);
 /* 0 if a compute-capability-10.x device is current and the TMA driver entry point resolves */
 int rsb_device_ok(void);
@@ -60,6 +64,7 @@ typedef struct rsb_conv_src {
     int64_t pitch_n;
     int32_t C;            /* innermost extent (channels, or window elements for overlapped views) */
     int32_t W, H, N;      /* extents of the view (TMA zero-fills outside) */
+    int64_t plane;        /* split precision only: element stride from the hi plane (ptr) to the lo plane of the same view */
 } rsb_conv_src;
 
 typedef struct rsb_conv_seg {
@@ -101,6 +106,20 @@ typedef struct rsb_conv_desc {
     /* 1: compute each pair of neighbouring tiles with a CTA pair (cluster of 2, tcgen05 cta_group::2; mode 0,
      * block_n >= 128): each CTA stages half of the weight tile. Same results; 0 = one CTA per tile. */
     int32_t cta_pair;
+
+    /* Split ("strict") precision: every activation and weight is the unevaluated sum of two fp16 numbers, hi = half(v) and
+     * lo = half(v - hi) (22+ significant bits), stored as two planes; the kernel accumulates hi*hi + hi*lo + lo*hi in fp32
+     * (3 tensor-core MMAs per K step; the lo*lo term is below fp32 resolution). This is what meets the reference's fp32
+     * results (logits 1e-3 rel, argmax identical up to the fp32 noise floor); split == 0 is the fast single-fp16 mode.
+     *   srcs[i].plane        element stride between the planes of source i
+     *   weights              fp16 [2][phases*Cout][K] (hi plane, then lo plane)
+     *   out_plane/res_plane  element stride between the planes of out / residual
+     * acc_scale (0 = 1): the fp32 accumulator is multiplied by it before bias/residual; the host pre-scales the weights by
+     * its inverse (a power of two) so that the lo parts of small weights stay in fp16's normal range. */
+    int32_t split;
+    int64_t out_plane;
+    int64_t res_plane;
+    float acc_scale;
 } rsb_conv_desc;
 
 typedef struct rsb_conv_plan rsb_conv_plan;
@@ -158,10 +177,18 @@ int rsb_rowconv_run(const rsb_rowconv_plan* plan, void* stream);
 int rsb_prepass_s2d(const void* src, int32_t src_kind, void* dst, int32_t N, int32_t H, int32_t W,
                     const float* mean3_host, const float* std3_host, void* stream);
 
+/* strict precision: also writes the lo plane at dst + plane (elements): lo = half(x - float(half(x))) */
+int rsb_prepass_s2d_split(const void* src, int32_t src_kind, void* dst, int64_t plane, int32_t N, int32_t H, int32_t W,
+                          const float* mean3_host, const float* std3_host, void* stream);
+
 /* NHWC fp16 max pooling. Replaces resnet.maxpool (unet.py:125: k3 s2 p1) and F.max_pool2d(enc4, 2, 2) (unet.py:132).
  * Output pixel pitches are explicit so the result can land inside a padded buffer. */
 int rsb_maxpool_nhwc(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t s,
                      int32_t p, void* stream);
+
+/* strict precision: the maximum of the (hi, lo) pairs, i.e. of the exact fp32 sums hi + lo, written as a pair again */
+int rsb_maxpool_nhwc_split(const void* src, int64_t src_plane, void* dst, int64_t dst_plane, int32_t N, int32_t H, int32_t W,
+                           int32_t C, int32_t k, int32_t s, int32_t p, void* stream);
 
 /* Predict head. Replaces softmax(outputs, 1) ... np.digitize(foreground, linspace(0,1,256)).astype(uint8)
  * (predict.py:87, 93, 98-103) for the 2-class case, including the crop of the `overlap` border (datasets.py:133-136).

@@ -29,6 +29,7 @@ class ConvSrc(ctypes.Structure):
         ("W", ctypes.c_int32),
         ("H", ctypes.c_int32),
         ("N", ctypes.c_int32),
+        ("plane", ctypes.c_int64),
     ]
 
 
@@ -67,6 +68,10 @@ class ConvDesc(ctypes.Structure):
         ("head_b", ctypes.c_void_p),
         ("head_out", ctypes.c_void_p),
         ("cta_pair", ctypes.c_int32),
+        ("split", ctypes.c_int32),
+        ("out_plane", ctypes.c_int64),
+        ("res_plane", ctypes.c_int64),
+        ("acc_scale", ctypes.c_float),
     ]
 
 
@@ -106,6 +111,7 @@ class RowConvDesc(ctypes.Structure):
 _vp, _i32, _i64, _f32 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float
 SIGNATURES = {
     "rsb_version": (ctypes.c_int, []),
+    "rsb_abi_layout": (None, [ctypes.POINTER(_i32)]),
     "rsb_last_error": (ctypes.c_char_p, []),
     "rsb_device_ok": (ctypes.c_int, []),
     "rsb_conv_plan_create": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(_vp)]),
@@ -117,7 +123,9 @@ SIGNATURES = {
     "rsb_rowconv_plan_destroy": (None, [_vp]),
     "rsb_rowconv_run": (ctypes.c_int, [_vp, _vp]),
     "rsb_prepass_s2d": (ctypes.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, ctypes.POINTER(_f32), ctypes.POINTER(_f32), _vp]),
+    "rsb_prepass_s2d_split": (ctypes.c_int, [_vp, _i32, _vp, _i64, _i32, _i32, _i32, ctypes.POINTER(_f32), ctypes.POINTER(_f32), _vp]),
     "rsb_maxpool_nhwc": (ctypes.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "rsb_maxpool_nhwc_split": (ctypes.c_int, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "rsb_head_quantize": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "rsb_stitch_halo": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rsb_softvote": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i64, _vp]),
@@ -169,6 +177,11 @@ def load():
         fn = getattr(lib, name)  # AttributeError here means header and library disagree
         fn.restype = res
         fn.argtypes = args
+    sizes = (ctypes.c_int32 * 4)()
+    lib.rsb_abi_layout(sizes)
+    mine = [ctypes.sizeof(ConvSrc), ctypes.sizeof(ConvSeg), ctypes.sizeof(ConvDesc), ctypes.sizeof(RowConvDesc)]
+    if list(sizes) != mine:
+        raise RsbError("struct layout mismatch between include/rsb200.h as compiled ({}) and robosat_b200/_lib.py ({}): rebuild the library".format(list(sizes), mine))
     _lib = lib
     return lib
 

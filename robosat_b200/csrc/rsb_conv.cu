@@ -55,32 +55,39 @@ struct alignas(64) ConvKParams {
     const float* head_w;
     const float* head_b;
     float* head_out;
+    float acc_scale;
 };
 
 // TWO: the tile is computed by a CTA pair (cluster of 2, tcgen05 cta_group::2): rank r owns 128 of the pair's 256 tile
 // rows and stages half of the weight tile (BLOCK_N/2 rows); one MMA of the leader reads both halves, so each SM moves
 // 16 KB + BLOCK_N*64 B of shared memory per K block instead of 16 KB + BLOCK_N*128 B.
-template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO = false>
+// SPLIT: strict precision. Every operand is a (hi, lo) pair of fp16 planes; a pipeline stage holds both planes of the A box
+// and of the weight tile (one rank-5 / rank-3 TMA box each) and every K step issues three MMAs: hi*lo, lo*hi, hi*hi.
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO = false, bool SPLIT = false>
 struct ConvCfg {
+    static constexpr int kPlanes = SPLIT ? 2 : 1;
     static constexpr int kBRows = TWO ? BLOCK_N / 2 : BLOCK_N;
-    static constexpr int kBBytes = kBRows * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kBBytes = kBRows * kBlockK * 2;                 // one plane
+    static constexpr int kStageA = kPlanes * kABytes;
+    static constexpr int kStageB = kPlanes * kBBytes;
+    static constexpr int kStageBytes = kStageA + kStageB;
     // epilogue staging: the C tile leaves through shared memory in chunks of kChunk columns (TMA store), and the
-    // residual tile arrives the same way (TMA load); 2 buffers each
+    // residual tile arrives the same way (TMA load)
     static constexpr int kChunk = BLOCK_N >= 64 ? 64 : 32;
     static constexpr int kNumChunks = BLOCK_N / kChunk;
-    static constexpr int kChunkBytes = kBlockM * kChunk * 2;
     // every epilogue warp owns its 32 rows of the tile end to end (own staging slices, own TMA stores / residual
-    // loads, no cross-warp barrier): kStoreBufs store slices and kResBufs residual slices of kWarpChunkBytes each
+    // loads, no cross-warp barrier): kStoreBufs store slices and kResBufs residual slices of kSliceBytes each
     // A single warp per SM sub-partition is latency-bound (ncu: ~5 cycles per issued instruction), so wide tiles get
-    // two epilogue warps per TMEM lane quarter; the pair splits the tile's column chunks (even / odd).
-    static constexpr int kEpiWarps = (MODE == 0 && BLOCK_N >= 128) ? 8 : 4;
+    // two epilogue warps per TMEM lane quarter; the pair splits the tile's column chunks (even / odd). In split mode the K
+    // loop of a tile is three times as long, which hides a 4-warp epilogue, and shared memory is needed for the stages.
+    static constexpr int kEpiWarps = (MODE == 0 && BLOCK_N >= 128 && !SPLIT) ? 8 : 4;
     static constexpr int kChunkStride = kEpiWarps / 4;
     static constexpr int kThreads = 64 + 32 * kEpiWarps;
-    static constexpr int kWarpChunkBytes = 32 * kChunk * 2;
-    static constexpr int kStoreBufs = kEpiWarps == 8 ? 1 : 2;                 // per warp
-    static constexpr int kResBufs = HAS_RES ? (kEpiWarps == 8 ? 2 : 4) : 0;   // per warp
-    static constexpr int kEpiBytes = MODE == 0 ? (kStoreBufs + kResBufs) * kEpiWarps * kWarpChunkBytes : 0;
+    static constexpr int kWarpChunkBytes = 32 * kChunk * 2;               // one plane of one warp's slice
+    static constexpr int kSliceBytes = kPlanes * kWarpChunkBytes;
+    static constexpr int kStoreBufs = (kEpiWarps == 8 || SPLIT) ? 1 : 2;                       // per warp
+    static constexpr int kResBufs = HAS_RES ? ((kEpiWarps == 8 || SPLIT) ? 2 : 4) : 0;        // per warp
+    static constexpr int kEpiBytes = MODE == 0 ? (kStoreBufs + kResBufs) * kEpiWarps * kSliceBytes : 0;
     static constexpr int kBarBytes = 512;
     static constexpr int kMaxSmem = 232448;  // 227 KB opt-in limit per CTA
     static constexpr int kAvail = kMaxSmem - 1024 - kBarBytes - kEpiBytes;
@@ -119,9 +126,9 @@ __device__ __forceinline__ int item_tile(const ConvKParams& p, int it, int rank)
     return ((it / per) * 2 + rank) * per + it % per;
 }
 
-template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO>
-__global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThreads), 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
-    using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>;
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, bool SPLIT>
+__global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::kThreads), 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
+    using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>;
     const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
     const int item0 = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     const int item_step = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
@@ -130,9 +137,9 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThread
     // 128B swizzle atoms repeat every 1024 bytes: tile bases must be 1024-byte aligned
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + Cfg::kStages * kABytes;
-    uint8_t* smem_c = smem + Cfg::kStages * Cfg::kStageBytes;          // 2 store buffers (1024-aligned)
-    uint8_t* smem_r = smem_c + Cfg::kStoreBufs * Cfg::kEpiWarps * Cfg::kWarpChunkBytes;  // residual slices (HAS_RES)
+    uint8_t* smem_b = smem + Cfg::kStages * Cfg::kStageA;
+    uint8_t* smem_c = smem + Cfg::kStages * Cfg::kStageBytes;          // store slices (1024-aligned)
+    uint8_t* smem_r = smem_c + Cfg::kStoreBufs * Cfg::kEpiWarps * Cfg::kSliceBytes;  // residual slices (HAS_RES)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kEpiBytes);
     uint64_t* empty_bar = full_bar + Cfg::kStages;
     uint64_t* tmem_full_bar = empty_bar + Cfg::kStages;
@@ -198,12 +205,23 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThread
                             // (the peer's bytes may land before this expect_tx: the barrier cannot complete until the
                             // leader's arrive, and the peer cannot run a ring lap ahead of the MMA's commits)
                             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
-                            tma_load_4d_pair(smem_a + stage * kABytes, tm, lead_full, cb * kBlockK, cw, ch, t.n0);
-                            tma_load_2d_pair(smem_b + stage * Cfg::kBBytes, &p.tmB, lead_full, kb * kBlockK, b_row);
+                            if constexpr (SPLIT) {
+                                tma_load_5d_pair(smem_a + stage * Cfg::kStageA, tm, lead_full, cb * kBlockK, cw, ch, t.n0, 0);
+                                tma_load_3d_pair(smem_b + stage * Cfg::kStageB, &p.tmB, lead_full, kb * kBlockK, b_row, 0);
+                            } else {
+                                tma_load_4d_pair(smem_a + stage * Cfg::kStageA, tm, lead_full, cb * kBlockK, cw, ch, t.n0);
+                                tma_load_2d_pair(smem_b + stage * Cfg::kStageB, &p.tmB, lead_full, kb * kBlockK, b_row);
+                            }
                         } else {
                             mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-                            tma_load_4d(smem_a + stage * kABytes, tm, &full_bar[stage], cb * kBlockK, cw, ch, t.n0);
-                            tma_load_2d(smem_b + stage * Cfg::kBBytes, &p.tmB, &full_bar[stage], kb * kBlockK, b_row);
+                            if constexpr (SPLIT) {
+                                // one box carries both planes: [plane][TN][TH][TW][64 ch] / [plane][rows][64]
+                                tma_load_5d(smem_a + stage * Cfg::kStageA, tm, &full_bar[stage], cb * kBlockK, cw, ch, t.n0, 0);
+                                tma_load_3d(smem_b + stage * Cfg::kStageB, &p.tmB, &full_bar[stage], kb * kBlockK, b_row, 0);
+                            } else {
+                                tma_load_4d(smem_a + stage * Cfg::kStageA, tm, &full_bar[stage], cb * kBlockK, cw, ch, t.n0);
+                                tma_load_2d(smem_b + stage * Cfg::kStageB, &p.tmB, &full_bar[stage], kb * kBlockK, b_row);
+                            }
                         }
                         if (++stage == Cfg::kStages) {
                             stage = 0;
@@ -231,13 +249,28 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThread
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint64_t da = da0 + static_cast<uint64_t>(stage * (kABytes >> 4));
-                    const uint64_t db = db0 + static_cast<uint64_t>(stage * (Cfg::kBBytes >> 4));
+                    const uint64_t da = da0 + static_cast<uint64_t>(stage * (Cfg::kStageA >> 4));
+                    const uint64_t db = db0 + static_cast<uint64_t>(stage * (Cfg::kStageB >> 4));
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
-                        if (TWO) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                        else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        const uint32_t first = (kb | k) != 0 ? 1u : 0u;
+                        if constexpr (SPLIT) {
+                            // lo planes sit kABytes / kBBytes behind the hi planes; cross terms first (smallest magnitude)
+                            const uint64_t dal = da + (kABytes >> 4), dbl = db + (Cfg::kBBytes >> 4);
+                            if (TWO) {
+                                umma_f16_pair(d_tmem, da + 2 * k, dbl + 2 * k, idesc, first);
+                                umma_f16_pair(d_tmem, dal + 2 * k, db + 2 * k, idesc, 1u);
+                                umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+                            } else {
+                                umma_f16(d_tmem, da + 2 * k, dbl + 2 * k, idesc, first);
+                                umma_f16(d_tmem, dal + 2 * k, db + 2 * k, idesc, 1u);
+                                umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, 1u);
+                            }
+                        } else {
+                            if (TWO) umma_f16_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, first);
+                            else umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, first);
+                        }
                     }
                     // smem slot is free once these MMAs retire (pair: in both CTAs)
                     if (TWO) umma_commit_pair(&empty_bar[stage]);
@@ -270,8 +303,8 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThread
         const int qw = qrow0 % p.TW, qh = (qrow0 / p.TW) % p.TH, qn = qrow0 / (p.TW * p.TH);
         const int ew = warp_idx - 2;                 // epilogue warp index
         const int chunk0 = ew >> 2;                  // first column chunk of this warp; it takes every kChunkStride-th
-        uint8_t* my_c = smem_c + ew * Cfg::kStoreBufs * Cfg::kWarpChunkBytes;
-        uint8_t* my_r = smem_r + ew * (Cfg::kResBufs > 0 ? Cfg::kResBufs : 1) * Cfg::kWarpChunkBytes;
+        uint8_t* my_c = smem_c + ew * Cfg::kStoreBufs * Cfg::kSliceBytes;
+        uint8_t* my_r = smem_r + ew * (Cfg::kResBufs > 0 ? Cfg::kResBufs : 1) * Cfg::kSliceBytes;
         uint64_t* my_res_bar = res_full_bar + ew * 4;
         uint32_t wchunk = 0;          // running chunk counter of this warp (selects staging buffers)
         int res_item = item0;         // residual prefetch cursor (lane 0)
@@ -284,9 +317,13 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThread
         auto issue_residual = [&](int rb) {
             if (res_item < num_items) {
                 const TileCoord rt = decode_tile(p, item_tile<TWO>(p, res_item, rank));
-                mbar_expect_tx(&my_res_bar[rb], Cfg::kWarpChunkBytes);
-                tma_load_4d(my_r + rb * Cfg::kWarpChunkBytes, &p.tmR, &my_res_bar[rb], rt.n_blk * BLOCK_N + res_chunk * Cfg::kChunk,
-                            rt.w0 + qw, rt.h0 + qh, rt.n0 + qn);
+                mbar_expect_tx(&my_res_bar[rb], Cfg::kSliceBytes);
+                if constexpr (SPLIT)
+                    tma_load_5d(my_r + rb * Cfg::kSliceBytes, &p.tmR, &my_res_bar[rb], rt.n_blk * BLOCK_N + res_chunk * Cfg::kChunk,
+                                rt.w0 + qw, rt.h0 + qh, rt.n0 + qn, 0);
+                else
+                    tma_load_4d(my_r + rb * Cfg::kSliceBytes, &p.tmR, &my_res_bar[rb], rt.n_blk * BLOCK_N + res_chunk * Cfg::kChunk,
+                                rt.w0 + qw, rt.h0 + qh, rt.n0 + qn);
                 res_chunk += Cfg::kChunkStride;
                 if (res_chunk >= Cfg::kNumChunks) {
                     res_chunk = chunk0;
@@ -312,8 +349,8 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThread
                 for (int ck = chunk0; ck < Cfg::kNumChunks; ck += Cfg::kChunkStride, ++wchunk) {
                     constexpr int kRB = Cfg::kResBufs > 0 ? Cfg::kResBufs : 1;
                     const int rb = wchunk % kRB;
-                    uint8_t* cbuf = my_c + (wchunk % Cfg::kStoreBufs) * Cfg::kWarpChunkBytes;
-                    const uint8_t* rbuf = my_r + rb * Cfg::kWarpChunkBytes;
+                    uint8_t* cbuf = my_c + (wchunk % Cfg::kStoreBufs) * Cfg::kSliceBytes;
+                    const uint8_t* rbuf = my_r + rb * Cfg::kSliceBytes;
                     if (HAS_RES) mbar_wait(&my_res_bar[rb], (wchunk / kRB) & 1);
                     // the TMA store this warp issued kStoreBufs chunks ago (same slice) must have finished reading shared memory
                     if (lane == 0) tma_store_wait_read<Cfg::kStoreBufs - 1>();
@@ -331,17 +368,19 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThread
                             if (lane == 0) release_acc(acc);
                         }
                         float v[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+                        const float asc = p.acc_scale;  // power of two (1 in fast mode): exact
                         if (bptr) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4) {
                                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(bptr + c + j));
-                                v[j] += b4.x;
-                                v[j + 1] += b4.y;
-                                v[j + 2] += b4.z;
-                                v[j + 3] += b4.w;
+                                v[j] = fmaf(__uint_as_float(r[j]), asc, b4.x);
+                                v[j + 1] = fmaf(__uint_as_float(r[j + 1]), asc, b4.y);
+                                v[j + 2] = fmaf(__uint_as_float(r[j + 2]), asc, b4.z);
+                                v[j + 3] = fmaf(__uint_as_float(r[j + 3]), asc, b4.w);
                             }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * asc;
                         }
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
@@ -352,15 +391,28 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThread
                             if (HAS_RES) {
                                 const uint4 r4 = *reinterpret_cast<const uint4*>(rbuf + soff);
                                 const __half2* h2 = reinterpret_cast<const __half2*>(&r4);
+                                if constexpr (SPLIT) {
+                                    const uint4 l4 = *reinterpret_cast<const uint4*>(rbuf + Cfg::kWarpChunkBytes + soff);
+                                    const __half2* l2 = reinterpret_cast<const __half2*>(&l4);
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const float2 f = __half22float2(h2[e]);
-                                    v[j * 8 + 2 * e] += f.x;
-                                    v[j * 8 + 2 * e + 1] += f.y;
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 f = __half22float2(h2[e]);
+                                        const float2 g = __half22float2(l2[e]);
+                                        v[j * 8 + 2 * e] += f.x + g.x;  // hi + lo is exact in fp32
+                                        v[j * 8 + 2 * e + 1] += f.y + g.y;
+                                    }
+                                } else {
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        const float2 f = __half22float2(h2[e]);
+                                        v[j * 8 + 2 * e] += f.x;
+                                        v[j * 8 + 2 * e + 1] += f.y;
+                                    }
                                 }
                             }
-                            uint4 o4;
+                            uint4 o4, q4;
                             __half2* o2 = reinterpret_cast<__half2*>(&o4);
+                            __half2* q2 = reinterpret_cast<__half2*>(&q4);
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
                                 float a = v[j * 8 + 2 * e], b = v[j * 8 + 2 * e + 1];
@@ -369,14 +421,22 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThread
                                     b = fmaxf(b, 0.0f);
                                 }
                                 o2[e] = __floats2half2_rn(a, b);
+                                if constexpr (SPLIT) {
+                                    const float2 hf = __half22float2(o2[e]);
+                                    q2[e] = __floats2half2_rn(a - hf.x, b - hf.y);  // the residue is exact in fp32
+                                }
                             }
                             *reinterpret_cast<uint4*>(cbuf + soff) = o4;
+                            if constexpr (SPLIT) *reinterpret_cast<uint4*>(cbuf + Cfg::kWarpChunkBytes + soff) = q4;
                         }
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_4d(&p.tmC[t.phase], cbuf, t.n_blk * BLOCK_N + ck * Cfg::kChunk, t.w0 + qw, t.h0 + qh, t.n0 + qn);
+                        if constexpr (SPLIT)
+                            tma_store_5d(&p.tmC[t.phase], cbuf, t.n_blk * BLOCK_N + ck * Cfg::kChunk, t.w0 + qw, t.h0 + qh, t.n0 + qn, 0);
+                        else
+                            tma_store_4d(&p.tmC[t.phase], cbuf, t.n_blk * BLOCK_N + ck * Cfg::kChunk, t.w0 + qw, t.h0 + qh, t.n0 + qn);
                         tma_store_commit();
                         // residual slice `rb` has been consumed by the whole warp: refill it kResBufs chunks ahead
                         if (HAS_RES) issue_residual(rb);
@@ -391,7 +451,7 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>::kThread
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float a = __uint_as_float(r[j]);
+                    float a = __uint_as_float(r[j]) * p.acc_scale;
                     if (p.bias) a += __ldg(p.bias + j);
                     v[j] = p.relu ? fmaxf(a, 0.0f) : a;
                 }
@@ -446,6 +506,7 @@ __global__ void conv_simt_check_kernel(rsb_conv_desc d, int K) {
     const int n = static_cast<int>(px / d.Ht);
     const int pa = phase >> 1, pb = phase & 1;
     const __half* wts = static_cast<const __half*>(d.weights);
+    const int64_t w_plane = static_cast<int64_t>(d.phases) * d.Cout * K;
 
     float head_acc[8];
     for (int k = 0; k < 8; ++k) head_acc[k] = (d.mode == 1 && k < d.head_classes) ? d.head_b[k] : 0.f;
@@ -460,16 +521,30 @@ __global__ void conv_simt_check_kernel(rsb_conv_desc d, int K) {
             const bool inb = hh >= 0 && hh < src.H && ww >= 0 && ww < src.W && n < src.N;
             const __half* a = static_cast<const __half*>(src.ptr) + n * src.pitch_n + hh * src.pitch_h + ww * src.pitch_w;
             for (int c = 0; c < d.segs[s].cblocks * 64; ++c, ++kidx) {
-                if (inb && c < src.C) acc += __half2float(a[c]) * __half2float(wrow[kidx]);
+                if (inb && c < src.C) {
+                    float av = __half2float(a[c]), wv = __half2float(wrow[kidx]);
+                    if (d.split) {
+                        av += __half2float(a[c + src.plane]);
+                        wv += __half2float(wrow[kidx + w_plane]);
+                    }
+                    acc = fmaf(av, wv, acc);
+                }
             }
         }
+        acc *= d.acc_scale != 0.f ? d.acc_scale : 1.f;
         if (d.bias) acc += d.bias[co];
         const int64_t off = n * d.out_pitch_n + static_cast<int64_t>(h * d.out_sy + pa) * d.out_pitch_h +
                             static_cast<int64_t>(w * d.out_sx + pb) * d.out_pitch_w + co;
         if (d.mode == 0) {
-            if (d.residual) acc += __half2float(static_cast<const __half*>(d.residual)[off]);
+            if (d.residual) {
+                float rv = __half2float(static_cast<const __half*>(d.residual)[off]);
+                if (d.split) rv += __half2float(static_cast<const __half*>(d.residual)[off + d.res_plane]);
+                acc += rv;
+            }
             if (d.relu) acc = fmaxf(acc, 0.f);
-            static_cast<__half*>(d.out)[off] = __float2half_rn(acc);
+            const __half hi = __float2half_rn(acc);
+            static_cast<__half*>(d.out)[off] = hi;
+            if (d.split) static_cast<__half*>(d.out)[off + d.out_plane] = __float2half_rn(acc - __half2float(hi));
         } else {
             if (d.relu) acc = fmaxf(acc, 0.f);
             for (int k = 0; k < d.head_classes; ++k) head_acc[k] = fmaf(d.head_w[k * 32 + co], acc, head_acc[k]);
@@ -495,7 +570,8 @@ struct rsb_conv_plan {
     int grid;
     int smem;
     bool has_res;
-    bool pair;  // CTA-pair (cta_group::2) schedule
+    bool pair;   // CTA-pair (cta_group::2) schedule
+    bool split;  // strict precision (hi + lo planes)
 };
 
 static int validate_desc(const rsb_conv_desc* d, int* K_out) {
@@ -509,6 +585,7 @@ static int validate_desc(const rsb_conv_desc* d, int* K_out) {
     if (d->TW * d->TH * d->TN != kBlockM) return set_error(RSB_E_INVALID, "conv: TW*TH*TN must be 128");
     if (d->Wt <= 0 || d->Ht <= 0 || d->Nt <= 0) return set_error(RSB_E_INVALID, "conv: empty tile space");
     if (!d->weights) return set_error(RSB_E_INVALID, "conv: null weights");
+    if (d->split != 0 && d->split != 1) return set_error(RSB_E_INVALID, "conv: split must be 0 or 1");
     int kblocks = 0;
     for (int s = 0; s < d->nseg; ++s) {
         const rsb_conv_seg& g = d->segs[s];
@@ -523,6 +600,7 @@ static int validate_desc(const rsb_conv_desc* d, int* K_out) {
         if ((s.pitch_w * 2) % 16 || (s.pitch_h * 2) % 16 || (s.pitch_n * 2) % 16)
             return set_error(RSB_E_INVALID, "conv: source pitches must be multiples of 16 bytes");
         if (s.C < 1 || s.W < 1 || s.H < 1 || s.N < 1) return set_error(RSB_E_INVALID, "conv: empty source view");
+        if (d->split && (s.plane <= 0 || (s.plane * 2) % 16)) return set_error(RSB_E_INVALID, "conv: split needs a positive 16B-multiple plane stride per source");
     }
     if (d->mode == 0) {
         if (!d->out) return set_error(RSB_E_INVALID, "conv: null out");
@@ -531,6 +609,10 @@ static int validate_desc(const rsb_conv_desc* d, int* K_out) {
             return set_error(RSB_E_INVALID, "conv: out must be 16B aligned with 16B-multiple pitches");
         if (d->residual && (reinterpret_cast<uintptr_t>(d->residual) & 15))
             return set_error(RSB_E_INVALID, "conv: residual must be 16B aligned");
+        if (d->split && (d->out_plane <= 0 || (d->out_plane * 2) % 16)) return set_error(RSB_E_INVALID, "conv: split needs out_plane");
+        if (d->split && d->residual && (d->res_plane <= 0 || (d->res_plane * 2) % 16)) return set_error(RSB_E_INVALID, "conv: split needs res_plane");
+        if (d->split && d->residual && d->block_n == 256 && !d->cta_pair)
+            return set_error(RSB_E_INVALID, "conv: split + residual supports block_n <= 128 (or a CTA pair)");
     } else if (d->mode == 1) {
         if (d->block_n != 32 || d->Cout != 32 || d->phases != 1) return set_error(RSB_E_INVALID, "conv: head mode needs Cout == block_n == 32, phases == 1");
         if (d->head_classes < 1 || d->head_classes > 8 || !d->head_w || !d->head_b || !d->head_out)
@@ -543,75 +625,127 @@ static int validate_desc(const rsb_conv_desc* d, int* K_out) {
     return RSB_OK;
 }
 
-template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO = false>
-static int launch_conv(const rsb_conv_plan* plan, cudaStream_t stream) {
-    using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES, TWO>;
-    auto kern = conv_tc_kernel<BLOCK_N, MODE, HAS_RES, TWO>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
-        if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv)");
-        attr_set = true;
-    }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(plan->grid);
-    cfg.blockDim = dim3(Cfg::kThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    if (TWO) {
-        attr[1].id = cudaLaunchAttributeClusterDimension;
-        attr[1].val.clusterDim.x = 2;
-        attr[1].val.clusterDim.y = 1;
-        attr[1].val.clusterDim.z = 1;
-        cfg.numAttrs = 2;
-    }
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, plan->kp);
-    if (e != cudaSuccess) return set_cuda_error(e, "conv_tc_kernel launch");
-    return RSB_OK;
+static constexpr int kMaxDevices = 64;
+static int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
 }
 
-// how many CTA pairs the device can hold at once (pairs need two SMs of one TPC; persistent grid = that many clusters)
-template <int BLOCK_N, bool HAS_RES>
-static int pair_clusters_of() {
-    using Cfg = ConvCfg<BLOCK_N, 0, HAS_RES, true>;
-    auto kern = conv_tc_kernel<BLOCK_N, 0, HAS_RES, true>;
-    static int cached = -1;
-    if (cached >= 0) return cached;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess) return 0;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * num_sms());
-    cfg.blockDim = dim3(Cfg::kThreads);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
-        cudaGetLastError();
-        n = 0;
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, bool SPLIT>
+struct ConvInst {
+    using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>;
+    static constexpr int kSmem = Cfg::kSmemBytes;
+
+    // the opt-in shared-memory limit is a per-device function attribute: one process may drive several GPUs
+    static int prepare() {
+        static bool attr_set[kMaxDevices] = {};
+        const int dev = current_device();
+        if (!attr_set[dev]) {
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+            if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv)");
+            attr_set[dev] = true;
+        }
+        return RSB_OK;
     }
-    const int cap = num_sms() / 2;
-    cached = n < cap ? n : cap;
-    return cached;
-}
-static int pair_clusters(int block_n, bool res) {
-    if (block_n == 128) return res ? pair_clusters_of<128, true>() : pair_clusters_of<128, false>();
-    return res ? pair_clusters_of<256, true>() : pair_clusters_of<256, false>();
+
+    static int launch(const rsb_conv_plan* plan, cudaStream_t stream) {
+        int rc = prepare();
+        if (rc) return rc;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(plan->grid);
+        cfg.blockDim = dim3(Cfg::kThreads);
+        cfg.dynamicSmemBytes = kSmem;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (TWO) {
+            attr[1].id = cudaLaunchAttributeClusterDimension;
+            attr[1].val.clusterDim.x = 2;
+            attr[1].val.clusterDim.y = 1;
+            attr[1].val.clusterDim.z = 1;
+            cfg.numAttrs = 2;
+        }
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>, plan->kp);
+        if (e != cudaSuccess) return set_cuda_error(e, "conv_tc_kernel launch");
+        return RSB_OK;
+    }
+
+    // how many CTA pairs the device can hold at once (pairs need two SMs of one TPC; persistent grid = that many clusters)
+    static int pair_clusters() {
+        static int cached[kMaxDevices];
+        static bool have[kMaxDevices] = {};
+        const int dev = current_device();
+        if (have[dev]) return cached[dev];
+        if (prepare() != RSB_OK) return 0;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * num_sms());
+        cfg.blockDim = dim3(Cfg::kThreads);
+        cfg.dynamicSmemBytes = kSmem;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>, &cfg) != cudaSuccess) {
+            cudaGetLastError();
+            n = 0;
+        }
+        const int cap = num_sms() / 2;
+        cached[dev] = n < cap ? n : cap;
+        have[dev] = true;
+        return cached[dev];
+    }
+};
+
+// what to do with the instantiation a plan selects
+enum ConvAction { kLaunch, kSmemOf, kPairClusters };
+
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, bool SPLIT>
+static int conv_act(ConvAction a, const rsb_conv_plan* plan, cudaStream_t stream) {
+    using I = ConvInst<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>;
+    switch (a) {
+        case kLaunch: return I::launch(plan, stream);
+        case kSmemOf: return I::kSmem;
+        default: return I::pair_clusters();
+    }
 }
 
-template <int BLOCK_N>
-static int smem_for(int mode, bool res) {
-    if (mode == 1) return ConvCfg<BLOCK_N, 1, false>::kSmemBytes;
-    return res ? ConvCfg<BLOCK_N, 0, true>::kSmemBytes : ConvCfg<BLOCK_N, 0, false>::kSmemBytes;
+template <bool SPLIT>
+static int conv_dispatch(ConvAction a, const rsb_conv_plan* plan, cudaStream_t stream) {
+    if (plan->mode == 1) return conv_act<32, 1, false, false, SPLIT>(a, plan, stream);
+    if (plan->pair) {
+        if (plan->block_n == 128) return plan->has_res ? conv_act<128, 0, true, true, SPLIT>(a, plan, stream) : conv_act<128, 0, false, true, SPLIT>(a, plan, stream);
+        return plan->has_res ? conv_act<256, 0, true, true, SPLIT>(a, plan, stream) : conv_act<256, 0, false, true, SPLIT>(a, plan, stream);
+    }
+    if (plan->has_res) {
+        switch (plan->block_n) {
+            case 32: return conv_act<32, 0, true, false, SPLIT>(a, plan, stream);
+            case 64: return conv_act<64, 0, true, false, SPLIT>(a, plan, stream);
+            case 128: return conv_act<128, 0, true, false, SPLIT>(a, plan, stream);
+            case 256:
+                if constexpr (!SPLIT) return conv_act<256, 0, true, false, false>(a, plan, stream);
+                break;  // split + residual + 256 columns does not fit one SM (rejected by validate_desc)
+        }
+    } else {
+        switch (plan->block_n) {
+            case 32: return conv_act<32, 0, false, false, SPLIT>(a, plan, stream);
+            case 64: return conv_act<64, 0, false, false, SPLIT>(a, plan, stream);
+            case 128: return conv_act<128, 0, false, false, SPLIT>(a, plan, stream);
+            case 256: return conv_act<256, 0, false, false, SPLIT>(a, plan, stream);
+        }
+    }
+    return a == kLaunch ? set_error(RSB_E_INVALID, "conv: unsupported block_n / residual / split combination") : 0;
+}
+
+static int conv_select(ConvAction a, const rsb_conv_plan* plan, cudaStream_t stream) {
+    return plan->split ? conv_dispatch<true>(a, plan, stream) : conv_dispatch<false>(a, plan, stream);
 }
 
 extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_plan) {
@@ -627,13 +761,16 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
     if (!plan) return set_error(RSB_E_INVALID, "conv: out of host memory");
     memset(&plan->kp, 0, sizeof(plan->kp));
     ConvKParams& kp = plan->kp;
+    const bool split = d->split != 0;
+    // split precision: every view gains an outermost "plane" dimension of extent 2 and every box takes both planes
+    const int xr = split ? 1 : 0;
 
     for (int i = 0; i < d->nsrc; ++i) {
         const rsb_conv_src& s = d->srcs[i];
-        const uint64_t dims[4] = {(uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)s.N};
-        const uint64_t strides[3] = {(uint64_t)s.pitch_w * 2, (uint64_t)s.pitch_h * 2, (uint64_t)s.pitch_n * 2};
-        const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)d->TW, (uint32_t)d->TH, (uint32_t)d->TN};
-        rc = encode_tiled_f16(&kp.tmA[i], 4, s.ptr, dims, strides, box);
+        const uint64_t dims[5] = {(uint64_t)s.C, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)s.N, 2};
+        const uint64_t strides[4] = {(uint64_t)s.pitch_w * 2, (uint64_t)s.pitch_h * 2, (uint64_t)s.pitch_n * 2, (uint64_t)s.plane * 2};
+        const uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)d->TW, (uint32_t)d->TH, (uint32_t)d->TN, 2};
+        rc = encode_tiled_f16(&kp.tmA[i], 4 + xr, s.ptr, dims, strides, box);
         if (rc) {
             delete plan;
             return rc;
@@ -641,11 +778,12 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
     }
     for (int i = d->nsrc; i < RSB_MAX_SRCS; ++i) kp.tmA[i] = kp.tmA[0];
     {
-        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)d->phases * d->Cout};
-        const uint64_t strides[1] = {(uint64_t)K * 2};
+        const uint64_t rows = (uint64_t)d->phases * d->Cout;
+        const uint64_t dims[3] = {(uint64_t)K, rows, 2};
+        const uint64_t strides[2] = {(uint64_t)K * 2, rows * (uint64_t)K * 2};
         // a CTA of a pair stages half of the weight tile
-        const uint32_t box[2] = {(uint32_t)kBlockK, (uint32_t)(d->cta_pair ? d->block_n / 2 : d->block_n)};
-        rc = encode_tiled_f16(&kp.tmB, 2, d->weights, dims, strides, box);
+        const uint32_t box[3] = {(uint32_t)kBlockK, (uint32_t)(d->cta_pair ? d->block_n / 2 : d->block_n), 2};
+        rc = encode_tiled_f16(&kp.tmB, 2 + xr, d->weights, dims, strides, box);
         if (rc) {
             delete plan;
             return rc;
@@ -656,8 +794,9 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
         // out + n*pitch_n + (h*sy + a)*pitch_h + (w*sx + b)*pitch_w; stored / loaded in 64- (or 32-) channel chunks
         const int sy = d->out_sy > 0 ? d->out_sy : 1, sx = d->out_sx > 0 ? d->out_sx : 1;
         const int chunk = d->block_n >= 64 ? 64 : 32;
-        const uint64_t dims[4] = {(uint64_t)d->Cout, (uint64_t)d->Wt, (uint64_t)d->Ht, (uint64_t)d->Nt};
-        const uint64_t strides[3] = {(uint64_t)sx * d->out_pitch_w * 2, (uint64_t)sy * d->out_pitch_h * 2, (uint64_t)d->out_pitch_n * 2};
+        const uint64_t dims[5] = {(uint64_t)d->Cout, (uint64_t)d->Wt, (uint64_t)d->Ht, (uint64_t)d->Nt, 2};
+        uint64_t strides[4] = {(uint64_t)sx * d->out_pitch_w * 2, (uint64_t)sy * d->out_pitch_h * 2, (uint64_t)d->out_pitch_n * 2,
+                               (uint64_t)d->out_plane * 2};
         // one box per epilogue warp = 32 consecutive tile rows
         const int bw = d->TW < 32 ? d->TW : 32;
         const int bh = (32 / bw) < d->TH ? (32 / bw) : d->TH;
@@ -666,11 +805,11 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
             delete plan;
             return set_error(RSB_E_INVALID, "conv: TW must divide or be a multiple of 32");
         }
-        const uint32_t box[4] = {(uint32_t)chunk, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+        const uint32_t box[5] = {(uint32_t)chunk, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn, 2};
         for (int ph = 0; ph < 4; ++ph) {
             const int a = ph >> 1, b = ph & 1;
             const __half* base = static_cast<const __half*>(d->out) + (ph < d->phases ? a * d->out_pitch_h + b * d->out_pitch_w : 0);
-            rc = encode_tiled_f16(&kp.tmC[ph], 4, base, dims, strides, box, chunk * 2);
+            rc = encode_tiled_f16(&kp.tmC[ph], 4 + xr, base, dims, strides, box, chunk * 2);
             if (rc) {
                 delete plan;
                 return rc;
@@ -681,7 +820,8 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
                 delete plan;
                 return set_error(RSB_E_INVALID, "conv: residual needs phases == 1");
             }
-            rc = encode_tiled_f16(&kp.tmR, 4, d->residual, dims, strides, box, chunk * 2);
+            strides[3] = (uint64_t)d->res_plane * 2;
+            rc = encode_tiled_f16(&kp.tmR, 4 + xr, d->residual, dims, strides, box, chunk * 2);
             if (rc) {
                 delete plan;
                 return rc;
@@ -728,31 +868,24 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
     kp.head_w = d->head_w;
     kp.head_b = d->head_b;
     kp.head_out = d->head_out;
+    kp.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
 
     plan->block_n = d->block_n;
     plan->mode = d->mode;
+    plan->split = split;
     const int sms = num_sms();
     plan->grid = kp.total_tiles < sms ? kp.total_tiles : sms;
     plan->has_res = d->mode == 0 && d->residual != nullptr;
     plan->pair = d->cta_pair != 0;
     if (plan->pair) {
-        const int clusters = pair_clusters(d->block_n, plan->has_res);
+        const int clusters = conv_select(kPairClusters, plan, nullptr);
         if (clusters < 1) {
             delete plan;
             return set_error(RSB_E_CUDA, "conv: no CTA pair can be resident");
         }
         plan->grid = 2 * (kp.pair_tiles < clusters ? kp.pair_tiles : clusters);
-        if (d->block_n == 128) plan->smem = plan->has_res ? ConvCfg<128, 0, true, true>::kSmemBytes : ConvCfg<128, 0, false, true>::kSmemBytes;
-        else plan->smem = plan->has_res ? ConvCfg<256, 0, true, true>::kSmemBytes : ConvCfg<256, 0, false, true>::kSmemBytes;
-        *out_plan = plan;
-        return RSB_OK;
     }
-    switch (d->block_n) {
-        case 32: plan->smem = smem_for<32>(d->mode, plan->has_res); break;
-        case 64: plan->smem = smem_for<64>(d->mode, plan->has_res); break;
-        case 128: plan->smem = smem_for<128>(d->mode, plan->has_res); break;
-        default: plan->smem = smem_for<256>(d->mode, plan->has_res); break;
-    }
+    plan->smem = conv_select(kSmemOf, plan, nullptr);
     *out_plan = plan;
     return RSB_OK;
 }
@@ -770,28 +903,7 @@ extern "C" int rsb_conv_plan_info(const rsb_conv_plan* plan, int32_t* grid, int3
 
 extern "C" int rsb_conv_run(const rsb_conv_plan* plan, void* stream_) {
     if (!plan) return set_error(RSB_E_INVALID, "conv: null plan");
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    if (plan->mode == 1) return launch_conv<32, 1, false>(plan, stream);
-    if (plan->pair) {
-        if (plan->block_n == 128) return plan->has_res ? launch_conv<128, 0, true, true>(plan, stream) : launch_conv<128, 0, false, true>(plan, stream);
-        return plan->has_res ? launch_conv<256, 0, true, true>(plan, stream) : launch_conv<256, 0, false, true>(plan, stream);
-    }
-    if (plan->has_res) {
-        switch (plan->block_n) {
-            case 32: return launch_conv<32, 0, true>(plan, stream);
-            case 64: return launch_conv<64, 0, true>(plan, stream);
-            case 128: return launch_conv<128, 0, true>(plan, stream);
-            case 256: return launch_conv<256, 0, true>(plan, stream);
-        }
-    } else {
-        switch (plan->block_n) {
-            case 32: return launch_conv<32, 0, false>(plan, stream);
-            case 64: return launch_conv<64, 0, false>(plan, stream);
-            case 128: return launch_conv<128, 0, false>(plan, stream);
-            case 256: return launch_conv<256, 0, false>(plan, stream);
-        }
-    }
-    return set_error(RSB_E_INVALID, "conv: bad block_n");
+    return conv_select(kLaunch, plan, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int rsb_conv_run_simt_check(const rsb_conv_desc* d, void* stream_) {

@@ -16,8 +16,9 @@ struct Norm3 {
 };
 
 // dst fp16 [N][H2][W2 + 4][16]; one thread per (n, hh, padded column)
-template <int SRC_KIND>
-__global__ void prepass_s2d_kernel(const void* __restrict__ src, __half* __restrict__ dst, int N, int H, int W, Norm3 nm) {
+// SPLIT: also write the lo plane (dst + plane) holding half(x - float(half(x))): the strict-precision operand pair
+template <int SRC_KIND, bool SPLIT>
+__global__ void prepass_s2d_kernel(const void* __restrict__ src, __half* __restrict__ dst, int64_t plane, int N, int H, int W, Norm3 nm) {
     const int H2 = H / 2, W2 = W / 2, Wp = W2 + 4;
     const int64_t total = static_cast<int64_t>(N) * H2 * Wp;
     const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -26,8 +27,9 @@ __global__ void prepass_s2d_kernel(const void* __restrict__ src, __half* __restr
     const int hh = static_cast<int>((gid / Wp) % H2);
     const int n = static_cast<int>(gid / (static_cast<int64_t>(Wp) * H2));
     __align__(16) __half v[16];
+    __align__(16) __half l[16];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __float2half_rn(0.f);
+    for (int i = 0; i < 16; ++i) v[i] = l[i] = __float2half_rn(0.f);
     const int ww = wp - 2;
     if (ww >= 0 && ww < W2) {
 #pragma unroll
@@ -47,14 +49,24 @@ __global__ void prepass_s2d_kernel(const void* __restrict__ src, __half* __restr
                     x0 = (static_cast<float>(s[0]) / 255.0f - nm.mean[c]) / nm.std[c];
                     x1 = (static_cast<float>(s[3]) / 255.0f - nm.mean[c]) / nm.std[c];
                 }
-                v[(ph * 2 + 0) * 3 + c] = __float2half_rn(x0);
-                v[(ph * 2 + 1) * 3 + c] = __float2half_rn(x1);
+                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                v[(ph * 2 + 0) * 3 + c] = h0;
+                v[(ph * 2 + 1) * 3 + c] = h1;
+                if (SPLIT) {
+                    l[(ph * 2 + 0) * 3 + c] = __float2half_rn(x0 - __half2float(h0));
+                    l[(ph * 2 + 1) * 3 + c] = __float2half_rn(x1 - __half2float(h1));
+                }
             }
         }
     }
     uint4* o = reinterpret_cast<uint4*>(dst + gid * 16);
     o[0] = *reinterpret_cast<const uint4*>(&v[0]);
     o[1] = *reinterpret_cast<const uint4*>(&v[8]);
+    if (SPLIT) {
+        uint4* ol = reinterpret_cast<uint4*>(dst + plane + gid * 16);
+        ol[0] = *reinterpret_cast<const uint4*>(&l[0]);
+        ol[1] = *reinterpret_cast<const uint4*>(&l[8]);
+    }
 }
 
 // NHWC fp16 max pool, 8 channels (16 bytes) per thread
@@ -87,6 +99,54 @@ __global__ void maxpool_nhwc_kernel(const __half* __restrict__ src, __half* __re
         }
     }
     *reinterpret_cast<uint4*>(dst + ((static_cast<int64_t>(n) * OH + oh) * OW + ow) * C + c8 * 8) = *reinterpret_cast<uint4*>(m);
+}
+
+// Strict precision: values are (hi, lo) fp16 pairs; hi + lo is exact in fp32 and order-preserving, so the maximum is taken
+// on the fp32 sums and split again (the split of a value that came from a pair reproduces that pair).
+__global__ void maxpool_nhwc_split_kernel(const __half* __restrict__ src, int64_t src_plane, __half* __restrict__ dst, int64_t dst_plane,
+                                          int N, int H, int W, int C, int k, int s, int p, int OH, int OW) {
+    const int C8 = C / 8;
+    const int64_t total = static_cast<int64_t>(N) * OH * OW * C8;
+    const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int c8 = static_cast<int>(gid % C8);
+    int64_t r = gid / C8;
+    const int ow = static_cast<int>(r % OW);
+    r /= OW;
+    const int oh = static_cast<int>(r % OH);
+    const int n = static_cast<int>(r / OH);
+    float m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) m[i] = -3.0e38f;
+    for (int dy = 0; dy < k; ++dy) {
+        const int h = oh * s - p + dy;
+        if (h < 0 || h >= H) continue;
+        for (int dx = 0; dx < k; ++dx) {
+            const int w = ow * s - p + dx;
+            if (w < 0 || w >= W) continue;
+            const int64_t off = ((static_cast<int64_t>(n) * H + h) * W + w) * C + c8 * 8;
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + off));
+            const uint4 ql = __ldg(reinterpret_cast<const uint4*>(src + src_plane + off));
+            const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&ql);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 a = __half22float2(h2[i]), b = __half22float2(l2[i]);
+                m[2 * i] = fmaxf(m[2 * i], a.x + b.x);
+                m[2 * i + 1] = fmaxf(m[2 * i + 1], a.y + b.y);
+            }
+        }
+    }
+    __align__(16) __half hi[8];
+    __align__(16) __half lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        hi[i] = __float2half_rn(m[i]);
+        lo[i] = __float2half_rn(m[i] - __half2float(hi[i]));
+    }
+    const int64_t o = ((static_cast<int64_t>(n) * OH + oh) * OW + ow) * C + c8 * 8;
+    *reinterpret_cast<uint4*>(dst + o) = *reinterpret_cast<const uint4*>(hi);
+    *reinterpret_cast<uint4*>(dst + dst_plane + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
 // number of anchors of np.linspace(0, 1, 256) that are <= x, compared in float64 like np.digitize does
@@ -262,10 +322,11 @@ static inline unsigned grid_for(int64_t total, int block) { return static_cast<u
 
 using namespace rsb;
 
-extern "C" int rsb_prepass_s2d(const void* src, int32_t src_kind, void* dst, int32_t N, int32_t H, int32_t W,
-                               const float* mean3_host, const float* std3_host, void* stream) {
+static int prepass_common(const void* src, int32_t src_kind, void* dst, int64_t plane, int32_t N, int32_t H, int32_t W,
+                          const float* mean3_host, const float* std3_host, void* stream) {
     if (!src || !dst || N <= 0 || H <= 0 || W <= 0 || (H & 1) || (W & 1)) return set_error(RSB_E_INVALID, "prepass: bad arguments");
     if (src_kind != 0 && src_kind != 1) return set_error(RSB_E_INVALID, "prepass: src_kind must be 0 (f32 NCHW) or 1 (u8 NHWC)");
+    if (plane < 0 || (plane * 2) % 16) return set_error(RSB_E_INVALID, "prepass: plane stride must be a non-negative multiple of 8 elements");
     Norm3 nm;
     for (int c = 0; c < 3; ++c) {
         nm.mean[c] = mean3_host ? mean3_host[c] : 0.f;
@@ -274,12 +335,40 @@ extern "C" int rsb_prepass_s2d(const void* src, int32_t src_kind, void* dst, int
     }
     const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2 + 4);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (src_kind == 0)
-        prepass_s2d_kernel<0><<<grid_for(total, 256), 256, 0, st>>>(src, static_cast<__half*>(dst), N, H, W, nm);
-    else
-        prepass_s2d_kernel<1><<<grid_for(total, 256), 256, 0, st>>>(src, static_cast<__half*>(dst), N, H, W, nm);
+    __half* d = static_cast<__half*>(dst);
+    if (plane > 0) {
+        if (src_kind == 0) prepass_s2d_kernel<0, true><<<grid_for(total, 256), 256, 0, st>>>(src, d, plane, N, H, W, nm);
+        else prepass_s2d_kernel<1, true><<<grid_for(total, 256), 256, 0, st>>>(src, d, plane, N, H, W, nm);
+    } else {
+        if (src_kind == 0) prepass_s2d_kernel<0, false><<<grid_for(total, 256), 256, 0, st>>>(src, d, 0, N, H, W, nm);
+        else prepass_s2d_kernel<1, false><<<grid_for(total, 256), 256, 0, st>>>(src, d, 0, N, H, W, nm);
+    }
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "prepass_s2d launch");
+}
+
+extern "C" int rsb_prepass_s2d(const void* src, int32_t src_kind, void* dst, int32_t N, int32_t H, int32_t W,
+                               const float* mean3_host, const float* std3_host, void* stream) {
+    return prepass_common(src, src_kind, dst, 0, N, H, W, mean3_host, std3_host, stream);
+}
+
+extern "C" int rsb_prepass_s2d_split(const void* src, int32_t src_kind, void* dst, int64_t plane, int32_t N, int32_t H, int32_t W,
+                                     const float* mean3_host, const float* std3_host, void* stream) {
+    if (plane <= 0) return set_error(RSB_E_INVALID, "prepass_split: plane stride must be positive");
+    return prepass_common(src, src_kind, dst, plane, N, H, W, mean3_host, std3_host, stream);
+}
+
+extern "C" int rsb_maxpool_nhwc_split(const void* src, int64_t src_plane, void* dst, int64_t dst_plane, int32_t N, int32_t H, int32_t W,
+                                      int32_t C, int32_t k, int32_t s, int32_t p, void* stream) {
+    if (!src || !dst || N <= 0 || H <= 0 || W <= 0 || C <= 0 || (C % 8) || k < 1 || s < 1 || p < 0 || src_plane <= 0 || dst_plane <= 0 ||
+        (src_plane % 8) || (dst_plane % 8))
+        return set_error(RSB_E_INVALID, "maxpool_split: bad arguments (C and the plane strides must be multiples of 8)");
+    const int OH = (H + 2 * p - k) / s + 1, OW = (W + 2 * p - k) / s + 1;
+    const int64_t total = static_cast<int64_t>(N) * OH * OW * (C / 8);
+    maxpool_nhwc_split_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(src), src_plane, static_cast<__half*>(dst), dst_plane, N, H, W, C, k, s, p, OH, OW);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "maxpool_split launch");
 }
 
 extern "C" int rsb_maxpool_nhwc(const void* src, void* dst, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t s,

@@ -73,20 +73,30 @@ int encode_tiled_f16(CUtensorMap* map, int rank, const void* base, const uint64_
 }
 
 int num_sms() {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    // per device: one process may drive several GPUs (e.g. nn.DataParallel with two device_ids)
+    static int sms[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!sms[dev]) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        sms[dev] = n;
     }
-    return sms;
+    return sms[dev];
 }
 
 }  // namespace rsb
 
 using namespace rsb;
 
-extern "C" int rsb_version(void) { return 100; }
+extern "C" int rsb_version(void) { return 200; }
+
+extern "C" void rsb_abi_layout(int32_t* out4) {
+    out4[0] = static_cast<int32_t>(sizeof(rsb_conv_src));
+    out4[1] = static_cast<int32_t>(sizeof(rsb_conv_seg));
+    out4[2] = static_cast<int32_t>(sizeof(rsb_conv_desc));
+    out4[3] = static_cast<int32_t>(sizeof(rsb_rowconv_desc));
+}
 
 extern "C" const char* rsb_last_error(void) { return g_err; }
 

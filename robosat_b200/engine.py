@@ -36,13 +36,27 @@ def _strip(sd):
 
 
 def fold_bn(sd, conv_key, bn_prefix):
-    """Eval-mode BatchNorm folded into the preceding bias-free conv: w' = w*s, b' = beta - mean*s."""
-    w = sd[conv_key].float()
+    """Eval-mode BatchNorm folded into the preceding bias-free conv: w' = w*s, b' = beta - mean*s.
+    Folded in float64 so that the only rounding is the one to the operand format (fp16, or the fp16 hi/lo pair)."""
+    w = sd[conv_key].double()
     if bn_prefix is None:
         return w, None
-    s = sd[bn_prefix + ".weight"].float() / torch.sqrt(sd[bn_prefix + ".running_var"].float() + BN_EPS)
-    b = sd[bn_prefix + ".bias"].float() - sd[bn_prefix + ".running_mean"].float() * s
+    s = sd[bn_prefix + ".weight"].double() / torch.sqrt(sd[bn_prefix + ".running_var"].double() + BN_EPS)
+    b = sd[bn_prefix + ".bias"].double() - sd[bn_prefix + ".running_mean"].double() * s
     return w * s.view(-1, 1, 1, 1), b
+
+
+def split_fp16(w):
+    """float64 -> (scaled hi, scaled lo, acc_scale): w * 2^e = hi + lo with hi = half(w * 2^e), lo = half(w * 2^e - hi).
+
+    2^e moves the largest |w| into [2^13, 2^14) so the lo parts (2^-11 of their hi) of all but vanishing weights are normal
+    fp16 numbers; the kernel multiplies the fp32 accumulator by acc_scale = 2^-e (exact)."""
+    m = float(w.abs().max())
+    e = 0 if m == 0.0 else 13 - int(torch.floor(torch.log2(torch.tensor(m, dtype=torch.float64))))
+    ws = w.double() * (2.0 ** e)
+    hi = ws.to(torch.float16)
+    lo = (ws - hi.double()).to(torch.float16)
+    return hi, lo, 2.0 ** (-e)
 
 
 def pack_conv(w):
@@ -65,7 +79,7 @@ def pack_upsample_phases(w):
             taps = []
             for th in (0, 1):
                 for tw in (0, 1):
-                    acc = torch.zeros(co, ci, dtype=torch.float32)
+                    acc = torch.zeros(co, ci, dtype=w.dtype)
                     for kh in groups[a][th]:
                         for kw in groups[b][tw]:
                             acc += w[:, :, kh, kw]
@@ -80,7 +94,7 @@ def pack_stem(w):
     Input row 2*o + kh - 3 = 2*(o + t - 2) + ph with kh + 1 = 2*t + ph; the s2d channel is (ph*2+pw)*3 + c.
     """
     co = w.shape[0]
-    out = torch.zeros(co, 4, 4, 16, dtype=torch.float32)
+    out = torch.zeros(co, 4, 4, 16, dtype=w.dtype)
     for t in range(4):
         for ph in range(2):
             kh = 2 * t + ph - 1
@@ -98,7 +112,7 @@ def pack_stem(w):
 def pack_window3(w):
     """3x3 conv on 32 channels read as 3 row-taps of a 4-pixel window (4th pixel weight zero): K = 3*128."""
     co, ci, _, _ = w.shape
-    out = torch.zeros(co, 3, 4, ci, dtype=torch.float32)
+    out = torch.zeros(co, 3, 4, ci, dtype=w.dtype)
     out[:, :, :3, :] = w.permute(0, 2, 3, 1)
     return out.reshape(co, 3 * 4 * ci).contiguous()
 
@@ -125,7 +139,7 @@ def choose_tile(Wt, Ht, Nt):
 CTA_PAIR = os.environ.get("RSB_CTA_PAIR", "1") == "1"
 
 
-def choose_block_n(cout, m_tiles, phases, kblocks=8, sms=148):
+def choose_block_n(cout, m_tiles, phases, kblocks=8, sms=148, split=False):
     """N tile with the lowest modelled time for the persistent grid (ties -> the widest).
 
     Model (cycles, from scripts/gpu_mma_rate.py and the per-layer tables under profiles/): a tile's K loop issues 4 MMAs
@@ -138,7 +152,10 @@ def choose_block_n(cout, m_tiles, phases, kblocks=8, sms=148):
 
     def cost(bn):
         tiles = m_tiles * phases * (cout // bn)
-        per_tile = max(kblocks * 4 * max(66, bn // 2), bn * (16 if bn >= 128 else 28)) + 300
+        if split:  # three MMAs per K step, always the 4-warp epilogue
+            per_tile = max(kblocks * 12 * max(66, bn // 2), bn * 28) + 300
+        else:
+            per_tile = max(kblocks * 4 * max(66, bn // 2), bn * (16 if bn >= 128 else 28)) + 300
         return -(-tiles // sms) * per_tile
 
     return min(cands, key=lambda bn: (cost(bn), -bn))
@@ -229,18 +246,25 @@ def make_rowconv_desc(src, cin, weights, bias, cout, tile_space, out, out_pitche
     return d
 
 
-def _src_dense(t, N, H, W, C):
-    return ConvSrc(t.data_ptr(), C, W * C, H * W * C, C, W, H, N)
+def _src_dense(t, N, H, W, C, plane=0):
+    return ConvSrc(t.data_ptr(), C, W * C, H * W * C, C, W, H, N, plane)
 
 
-def _src_parity(t, N, H, W, C, ph, pw):
-    return ConvSrc(t.data_ptr() + 2 * (ph * W + pw) * C, 2 * C, 2 * W * C, H * W * C, C, W // 2, H // 2, N)
+def _src_parity(t, N, H, W, C, ph, pw, plane=0):
+    return ConvSrc(t.data_ptr() + 2 * (ph * W + pw) * C, 2 * C, 2 * W * C, H * W * C, C, W // 2, H // 2, N, plane)
 
 
 def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out_pitches, out_scale=(1, 1),
-                   residual=None, relu=True, block_n=None, head=None, out_offset_elems=0, cta_pair=None):
-    """Fill an `rsb_conv_desc`. tile_space = (Wt, Ht, Nt); out_pitches = (pitch_w, pitch_h, pitch_n) in elements."""
+                   residual=None, relu=True, block_n=None, head=None, out_offset_elems=0, cta_pair=None,
+                   split=False, acc_scale=1.0, out_plane=0, res_plane=0):
+    """Fill an `rsb_conv_desc`. tile_space = (Wt, Ht, Nt); out_pitches = (pitch_w, pitch_h, pitch_n) in elements.
+    split=True: strict precision -- weights fp16 [2][phases*Cout][K] (hi, lo planes), sources / out / residual carry
+    plane strides, the accumulator is multiplied by acc_scale (see include/rsb200.h)."""
     d = ConvDesc()
+    d.split = 1 if split else 0
+    d.acc_scale = acc_scale
+    d.out_plane = out_plane
+    d.res_plane = res_plane
     d.nsrc = len(srcs)
     for i, s in enumerate(srcs):
         d.srcs[i] = s
@@ -249,7 +273,8 @@ def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out
         d.segs[i] = ConvSeg(src, dh, dw, cb)
     K = 64 * sum(s[3] for s in segs)
     assert weights.dtype == torch.float16 and weights.is_contiguous()
-    assert tuple(weights.shape) == (phases * cout, K), (tuple(weights.shape), phases, cout, K)
+    wshape = (2, phases * cout, K) if split else (phases * cout, K)
+    assert tuple(weights.shape) == wshape, (tuple(weights.shape), wshape)
     d.weights = weights.data_ptr()
     d.bias = bias.data_ptr() if bias is not None else None
     d.Cout = cout
@@ -258,7 +283,7 @@ def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out
     d.Wt, d.Ht, d.Nt = Wt, Ht, Nt
     d.TW, d.TH, d.TN = choose_tile(Wt, Ht, Nt)
     m_tiles = -(-Wt // d.TW) * -(-Ht // d.TH) * -(-Nt // d.TN)
-    d.block_n = block_n or choose_block_n(cout, m_tiles, phases, K // 64)
+    d.block_n = block_n or choose_block_n(cout, m_tiles, phases, K // 64, split=split)
     if residual is not None and block_n is None and d.block_n == 256:
         d.block_n = 128  # residual epilogues keep 4 residual slices in flight per warp: leave room for 4 pipeline stages
     d.out_sy, d.out_sx = out_scale
@@ -272,7 +297,12 @@ def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out
             # measured (profiles/r1_cta_pair.md): pairs win once the K loop is long enough to be shared-memory bound
             # (dec0/dec1/dec3 -7..-10 %), and lose a few % on short, epilogue-bound K loops
             kblocks = K // 64
-            cta_pair = CTA_PAIR and m_tiles >= 2 and ((d.block_n == 256 and kblocks >= 6) or (d.block_n == 128 and kblocks >= 18))
+            if split:
+                # the weight tile is the larger half of a split stage (2 planes): sharing it between two SMs pays as soon as
+                # the K loop is long enough to amortise the cluster synchronisation
+                cta_pair = CTA_PAIR and m_tiles >= 2 and d.block_n >= 128 and kblocks >= 4
+            else:
+                cta_pair = CTA_PAIR and m_tiles >= 2 and ((d.block_n == 256 and kblocks >= 6) or (d.block_n == 128 and kblocks >= 18))
         d.cta_pair = 1 if cta_pair else 0
     else:
         head_w, head_b, head_out, classes = head
@@ -284,17 +314,36 @@ def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out
     return d
 
 
-class UNetEngine:
-    """Static-shape inference plan for `UNet(num_classes)` on one GPU."""
+PRECISIONS = ("strict", "fast")
 
-    def __init__(self, state_dict, num_classes, batch, height, width, device="cuda", plan_only=False, use_row=True):
+
+def default_precision():
+    """`strict` (hi/lo fp16 operand pairs, fp32-class results: the parity contract) unless RSB_PRECISION=fast."""
+    p = os.environ.get("RSB_PRECISION", "strict").lower()
+    if p not in PRECISIONS:
+        raise ValueError("RSB_PRECISION must be one of %s" % (PRECISIONS,))
+    return p
+
+
+class UNetEngine:
+    """Static-shape inference plan for `UNet(num_classes)` on one GPU.
+
+    precision="strict" (default): every activation / weight is an fp16 (hi, lo) pair and every K step runs three MMAs
+    (hi*lo + lo*hi + hi*hi, fp32 accumulate) -- logits agree with the fp32 reference to ~1e-5 relative, argmax up to
+    the fp32 noise floor. precision="fast": single fp16 operands (one MMA per K step, ~3x the throughput, logits ~2e-3)."""
+
+    def __init__(self, state_dict, num_classes, batch, height, width, device="cuda", plan_only=False, use_row=True, precision=None):
         """plan_only=True builds buffers and descriptors on `device` without touching the GPU library
         (used by the CPU tests, which execute the descriptors with tests/emulate.py)."""
         assert height % 32 == 0 and width % 32 == 0, "image resolution has to be divisible by 32 for resnet"
         # the reference's torch.cat([enc4, center]) (unet.py:134) only works when enc4's extent is even
         assert height % 64 == 0 and width % 64 == 0, "enc4 must have even extents (input divisible by 64), as in the reference"
         self.plan_only = plan_only
-        self.use_row = use_row  # line-buffer kernel for the >= 128-pixel-wide, small-Cout layers (layer1 3x3, dec4, dec5 + final)
+        self.precision = precision or default_precision()
+        assert self.precision in PRECISIONS, self.precision
+        self.strict = self.precision == "strict"
+        # line-buffer kernel for the >= 128-pixel-wide, small-Cout layers (layer1 3x3, dec4, dec5 + final); single-plane only
+        self.use_row = use_row and not self.strict
         if not plan_only:
             _lib.require_device()
         self.device = torch.device(device)
@@ -311,13 +360,38 @@ class UNetEngine:
         self._keep.append(t)
         return t
 
+    def _act(self, *shape):
+        """activation buffer: NHWC fp16, with a leading (hi, lo) plane axis in strict mode"""
+        return self._buf(*((2,) + shape if self.strict else shape))
+
+    def _plane(self, t):
+        return t.numel() // 2 if self.strict else 0
+
     def _dev(self, t, dtype):
         t = t.to(dtype).contiguous().to(self.device)
         self._keep.append(t)
         return t
 
-    def _add_conv(self, name, desc, keep=()):
-        op = ConvOp(name, desc, keep, create_plan=not self.plan_only)
+    def _wts(self, w):
+        """packed float64 weight matrix -> (device fp16 operand, acc_scale)"""
+        if not self.strict:
+            return self._dev(w, torch.float16), 1.0
+        hi, lo, scale = split_fp16(w)
+        return self._dev(torch.stack([hi, lo]), torch.float16), scale
+
+    def _dense(self, t, N, H, W, C):
+        return _src_dense(t, N, H, W, C, self._plane(t))
+
+    def _parity(self, t, N, H, W, C, ph, pw):
+        return _src_parity(t, N, H, W, C, ph, pw, self._plane(t))
+
+    def _conv(self, name, srcs, segs, w, b, cout, phases, tile_space, out, out_pitches, residual=None, **kw):
+        wd, scale = self._wts(w)
+        bd = self._dev(b, torch.float32) if b is not None else None
+        desc = make_conv_desc(srcs, segs, wd, bd, cout, phases, tile_space, out, out_pitches, residual=residual,
+                              split=self.strict, acc_scale=scale, out_plane=self._plane(out) if out is not None else 0,
+                              res_plane=self._plane(residual) if residual is not None else 0, **kw)
+        op = ConvOp(name, desc, (wd, bd), create_plan=not self.plan_only)
         self.ops.append(("conv", op))
         return op
 
@@ -333,22 +407,21 @@ class UNetEngine:
         dev = self._dev
 
         # input pre-pass: fp32 NCHW (or u8 NHWC) -> space-to-depth fp16 [N, H2, W2+4, 16]
-        self.s2d = self._buf(N, H2, W2 + 4, 16)
+        self.s2d = self._act(N, H2, W2 + 4, 16)
         self.ops.append(("prepass",))
 
         # stem: conv1 7x7/2 + bn1 + relu (unet.py:122-124) on tensor cores via the overlapped window view
         w, b = fold_bn(sd, "resnet.conv1.weight", "resnet.bn1")
-        wp, bp = dev(pack_stem(w), torch.float16), dev(b, torch.float32)
-        stem = self._buf(N, H2, W2, 64)
+        stem = self._act(N, H2, W2, 64)
         Wp = W2 + 4
-        src = ConvSrc(self.s2d.data_ptr(), 16, Wp * 16, H2 * Wp * 16, 64, W2, H2, N)
+        src = ConvSrc(self.s2d.data_ptr(), 16, Wp * 16, H2 * Wp * 16, 64, W2, H2, N, self._plane(self.s2d))
         segs = [(0, t - 2, 0, 1) for t in range(4)]
-        self._add_conv("stem", make_conv_desc([src], segs, wp, bp, 64, 1, (W2, H2, N), stem, (64, W2 * 64, H2 * W2 * 64)))
+        self._conv("stem", [src], segs, pack_stem(w), b, 64, 1, (W2, H2, N), stem, (64, W2 * 64, H2 * W2 * 64))
         self.feats["stem"] = (stem, (N, H2, W2, 64))
 
         # maxpool 3x3/2 pad 1 (unet.py:125)
         H4, W4 = H // 4, W // 4
-        enc0 = self._buf(N, H4, W4, 64)
+        enc0 = self._act(N, H4, W4, 64)
         self.ops.append(("maxpool", stem, enc0, N, H2, W2, 64, 3, 2, 1))
         self.feats["enc0"] = (enc0, (N, H4, W4, 64))
 
@@ -363,22 +436,21 @@ class UNetEngine:
                 oH, oW = curH // stride, curW // stride
                 # conv1 1x1 + bn1 + relu
                 w, b = fold_bn(sd, p + ".conv1.weight", p + ".bn1")
-                t1 = self._buf(N, curH, curW, planes)
-                self._add_conv(p + ".conv1", make_conv_desc(
-                    [_src_dense(cur, N, curH, curW, curC)], [(0, 0, 0, curC // 64)], dev(pack_conv(w), torch.float16),
-                    dev(b, torch.float32), planes, 1, (curW, curH, N), t1, (planes, curW * planes, curH * curW * planes)))
+                t1 = self._act(N, curH, curW, planes)
+                self._conv(p + ".conv1", [self._dense(cur, N, curH, curW, curC)], [(0, 0, 0, curC // 64)], pack_conv(w), b,
+                           planes, 1, (curW, curH, N), t1, (planes, curW * planes, curH * curW * planes))
                 # conv2 3x3 (stride) + bn2 + relu
                 w, b = fold_bn(sd, p + ".conv2.weight", p + ".bn2")
-                t2 = self._buf(N, oH, oW, planes)
+                t2 = self._act(N, oH, oW, planes)
                 if stride == 1 and planes == 64 and self.use_row and curW >= 128:
                     self._add_row(p + ".conv2", make_rowconv_desc(_src_dense(t1, N, curH, curW, planes), planes, dev(pack_conv(w), torch.float16),
                                                                   dev(b, torch.float32), planes, (oW, oH, N), t2, (planes, oW * planes, oH * oW * planes)))
                     srcs = None
                 elif stride == 1:
-                    srcs = [_src_dense(t1, N, curH, curW, planes)]
+                    srcs = [self._dense(t1, N, curH, curW, planes)]
                     segs = [(0, kh - 1, kw - 1, planes // 64) for kh in range(3) for kw in range(3)]
                 else:
-                    srcs = [_src_parity(t1, N, curH, curW, planes, ph, pw) for ph in range(2) for pw in range(2)]
+                    srcs = [self._parity(t1, N, curH, curW, planes, ph, pw) for ph in range(2) for pw in range(2)]
                     segs = []
                     for kh in range(3):
                         for kw in range(3):
@@ -386,28 +458,24 @@ class UNetEngine:
                             pw, dw = (kw - 1) % 2, (kw - 1) // 2
                             segs.append((ph * 2 + pw, dh, dw, planes // 64))
                 if srcs is not None:
-                    self._add_conv(p + ".conv2", make_conv_desc(
-                        srcs, segs, dev(pack_conv(w), torch.float16), dev(b, torch.float32), planes, 1, (oW, oH, N), t2,
-                        (planes, oW * planes, oH * oW * planes)))
+                    self._conv(p + ".conv2", srcs, segs, pack_conv(w), b, planes, 1, (oW, oH, N), t2, (planes, oW * planes, oH * oW * planes))
                 outC = planes * 4
                 w3, b3 = fold_bn(sd, p + ".conv3.weight", p + ".bn3")
-                out = self._buf(N, oH, oW, outC)
-                t2src = _src_dense(t2, N, oH, oW, planes)
+                out = self._act(N, oH, oW, outC)
+                t2src = self._dense(t2, N, oH, oW, planes)
                 if (p + ".downsample.0.weight") in sd:
                     # block 0: relu(bn3(conv3(t2)) + bn_d(downsample(x))) is ONE contraction over [t2 | x]:
                     # two 1x1 convs into the same output = two segments with concatenated weights and summed biases.
                     # The identity branch is never written to / re-read from HBM.
                     wd, bd = fold_bn(sd, p + ".downsample.0.weight", p + ".downsample.1")
-                    xsrc = _src_dense(cur, N, curH, curW, curC) if stride == 1 else _src_parity(cur, N, curH, curW, curC, 0, 0)
+                    xsrc = self._dense(cur, N, curH, curW, curC) if stride == 1 else self._parity(cur, N, curH, curW, curC, 0, 0)
                     wcat = torch.cat([pack_conv(w3), pack_conv(wd)], dim=1)
-                    self._add_conv(p + ".conv3+downsample", make_conv_desc(
-                        [t2src, xsrc], [(0, 0, 0, planes // 64), (1, 0, 0, curC // 64)], dev(wcat, torch.float16), dev(b3 + bd, torch.float32),
-                        outC, 1, (oW, oH, N), out, (outC, oW * outC, oH * oW * outC)))
+                    self._conv(p + ".conv3+downsample", [t2src, xsrc], [(0, 0, 0, planes // 64), (1, 0, 0, curC // 64)], wcat, b3 + bd,
+                               outC, 1, (oW, oH, N), out, (outC, oW * outC, oH * oW * outC))
                 else:
                     # conv3 1x1 + bn3 + identity + relu
-                    self._add_conv(p + ".conv3", make_conv_desc(
-                        [t2src], [(0, 0, 0, planes // 64)], dev(pack_conv(w3), torch.float16), dev(b3, torch.float32), outC, 1,
-                        (oW, oH, N), out, (outC, oW * outC, oH * oW * outC), residual=cur))
+                    self._conv(p + ".conv3", [t2src], [(0, 0, 0, planes // 64)], pack_conv(w3), b3, outC, 1,
+                               (oW, oH, N), out, (outC, oW * outC, oH * oW * outC), residual=cur)
                 self.feats[p] = (out, (N, oH, oW, outC))
                 cur, curC, curH, curW = out, outC, oH, oW
             encs.append((cur, curC, curH, curW))
@@ -416,43 +484,42 @@ class UNetEngine:
 
         # max_pool2d(enc4, 2, 2) (unet.py:132)
         hp, wpx = h4 // 2, w4 // 2
-        pool4 = self._buf(N, hp, wpx, c4)
+        pool4 = self._act(N, hp, wpx, c4)
         self.ops.append(("maxpool", enc4, pool4, N, h4, w4, c4, 2, 2, 0))
         self.feats["pool4"] = (pool4, (N, hp, wpx, c4))
 
         def decoder(name, sources, lh, lw, cout, out, out_pitches, out_offset=0):
             # DecoderBlock: nearest x2 + 3x3 conv + relu (unet.py:73, :44) as 4 phases of 2x2 taps on the low-res inputs
-            w = sd[name + ".block.block.weight"].float()
-            srcs = [_src_dense(t, N, lh, lw, c) for t, c in sources]
+            w = sd[name + ".block.block.weight"].double()
+            srcs = [self._dense(t, N, lh, lw, c) for t, c in sources]
             segs = [(si, th - 1, tw - 1, c // 64) for th in range(2) for tw in range(2) for si, (_, c) in enumerate(sources)]
-            self._add_conv(name, make_conv_desc(
-                srcs, segs, dev(pack_upsample_phases(w), torch.float16), None, cout, 4, (lw, lh, N), out, out_pitches,
-                out_scale=(2, 2), out_offset_elems=out_offset))
+            self._conv(name, srcs, segs, pack_upsample_phases(w), None, cout, 4, (lw, lh, N), out, out_pitches,
+                       out_scale=(2, 2), out_offset_elems=out_offset)
 
         def dense_pitches(h, w, c):
             return (c, w * c, h * w * c)
 
-        center = self._buf(N, h4, w4, 256)
+        center = self._act(N, h4, w4, 256)
         decoder("center", [(pool4, c4)], hp, wpx, 256, center, dense_pitches(h4, w4, 256))
         self.feats["center"] = (center, (N, h4, w4, 256))
-        dec0 = self._buf(N, h3, w3, 256)
+        dec0 = self._act(N, h3, w3, 256)
         decoder("dec0", [(enc4, c4), (center, 256)], h4, w4, 256, dec0, dense_pitches(h3, w3, 256))
         self.feats["dec0"] = (dec0, (N, h3, w3, 256))
-        dec1 = self._buf(N, h2, w2, 256)
+        dec1 = self._act(N, h2, w2, 256)
         decoder("dec1", [(enc3, c3), (dec0, 256)], h3, w3, 256, dec1, dense_pitches(h2, w2, 256))
         self.feats["dec1"] = (dec1, (N, h2, w2, 256))
-        dec2 = self._buf(N, h1, w1, 64)
+        dec2 = self._act(N, h1, w1, 64)
         decoder("dec2", [(enc2, c2), (dec1, 256)], h2, w2, 64, dec2, dense_pitches(h1, w1, 64))
         self.feats["dec2"] = (dec2, (N, h1, w1, 64))
-        dec3 = self._buf(N, H2, W2, 128)
+        dec3 = self._act(N, H2, W2, 128)
         decoder("dec3", [(enc1, c1), (dec2, 64)], h1, w1, 128, dec3, dense_pitches(H2, W2, 128))
         self.feats["dec3"] = (dec3, (N, H2, W2, 128))
 
         # dec4 writes into a W-padded buffer [N, H, W+4, 32] (pixel w at column w+1) so dec5 can read 4-pixel windows
         Wq = W + 4
-        self.dec4 = self._buf(N, H, Wq, 32)
+        self.dec4 = self._act(N, H, Wq, 32)
         if self.use_row and W2 >= 128:
-            w4 = sd["dec4.block.block.weight"].float()
+            w4 = sd["dec4.block.block.weight"].double()
             self._add_row("dec4", make_rowconv_desc(_src_dense(dec3, N, H2, W2, 128), 128, dev(pack_upsample_phases(w4), torch.float16), None, 32,
                                                     (W2, H2, N), self.dec4, (32, Wq * 32, H * Wq * 32), upsample=True, out_offset_elems=32))
         else:
@@ -460,7 +527,7 @@ class UNetEngine:
         self.feats["dec4"] = (self.dec4, (N, H, Wq, 32))
 
         # dec5 (3x3 32->32 + relu, unet.py:139) fused with final (1x1 32->C + bias, unet.py:141) -> fp32 NCHW logits
-        w5 = sd["dec5.block.weight"].float()
+        w5 = sd["dec5.block.weight"].double()
         self.logits = self._buf(N, self.C, H, W, dtype=torch.float32)
         head_w = dev(sd["final.weight"].float().reshape(self.C, 32), torch.float32)
         head_b = dev(sd["final.bias"].float(), torch.float32)
@@ -470,11 +537,10 @@ class UNetEngine:
             self._add_row("dec5+final", make_rowconv_desc(src, 32, dev(pack_conv(w5), torch.float16), None, 32, (W, H, N), None, None,
                                                           head=(head_w, head_b, self.logits, self.C)))
         else:
-            src = ConvSrc(self.dec4.data_ptr(), 32, Wq * 32, H * Wq * 32, 128, W, H, N)
+            src = ConvSrc(self.dec4.data_ptr(), 32, Wq * 32, H * Wq * 32, 128, W, H, N, self._plane(self.dec4))
             segs = [(0, kh - 1, 0, 2) for kh in range(3)]
-            self._add_conv("dec5+final", make_conv_desc(
-                [src], segs, dev(pack_window3(w5), torch.float16), None, 32, 1, (W, H, N), None, None,
-                head=(head_w, head_b, self.logits, self.C)))
+            self._conv("dec5+final", [src], segs, pack_window3(w5), None, 32, 1, (W, H, N), None, None,
+                       head=(head_w, head_b, self.logits, self.C))
 
         self._mean = (ctypes.c_float * 3)(*IMAGENET_MEAN)
         self._std = (ctypes.c_float * 3)(*IMAGENET_STD)
@@ -506,16 +572,27 @@ class UNetEngine:
             if op[0] == "conv":
                 op[1].run(stream)
             elif op[0] == "prepass":
-                _lib.check(lib.rsb_prepass_s2d(x.data_ptr(), kind, self.s2d.data_ptr(), N, H, W, self._mean, self._std, stream), "rsb_prepass_s2d")
+                if self.strict:
+                    _lib.check(lib.rsb_prepass_s2d_split(x.data_ptr(), kind, self.s2d.data_ptr(), self._plane(self.s2d), N, H, W,
+                                                         self._mean, self._std, stream), "rsb_prepass_s2d_split")
+                else:
+                    _lib.check(lib.rsb_prepass_s2d(x.data_ptr(), kind, self.s2d.data_ptr(), N, H, W, self._mean, self._std, stream), "rsb_prepass_s2d")
             else:
                 _, src, dst, n, h, w, c, k, s, p = op
-                _lib.check(lib.rsb_maxpool_nhwc(src.data_ptr(), dst.data_ptr(), n, h, w, c, k, s, p, stream), "rsb_maxpool_nhwc")
+                if self.strict:
+                    _lib.check(lib.rsb_maxpool_nhwc_split(src.data_ptr(), self._plane(src), dst.data_ptr(), self._plane(dst), n, h, w, c, k, s, p, stream),
+                               "rsb_maxpool_nhwc_split")
+                else:
+                    _lib.check(lib.rsb_maxpool_nhwc(src.data_ptr(), dst.data_ptr(), n, h, w, c, k, s, p, stream), "rsb_maxpool_nhwc")
         return self.logits
 
     def feature_nchw(self, name):
-        """Debug/parity view of an intermediate as fp32 NCHW on the CPU."""
+        """Debug/parity view of an intermediate as fp32 NCHW on the CPU (strict mode: hi + lo)."""
         t, (n, h, w, c) = self.feats[name]
-        t = t.detach().float().cpu().reshape(n, h, w, c)
+        t = t.detach().cpu()
+        if self.strict:
+            t = (t[0].double() + t[1].double()).float()
+        t = t.float().reshape(n, h, w, c)
         if name == "dec4":
             t = t[:, :, 1:w - 3, :]
         return t.permute(0, 3, 1, 2).contiguous()

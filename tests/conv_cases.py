@@ -21,7 +21,40 @@ def _nhwc_half(x_nchw, device):
 
 
 def _out_nchw(t, shape_nhwc):
-    return t.float().cpu().reshape(shape_nhwc).permute(0, 3, 1, 2).contiguous()
+    t = t.cpu()
+    if t.dim() == len(shape_nhwc) + 1:  # split precision: (hi, lo) planes
+        t = (t[0].double() + t[1].double())
+    return t.float().reshape(shape_nhwc).permute(0, 3, 1, 2).contiguous()
+
+
+def _pair_nhwc(x_nchw, device):
+    """fp32 NCHW -> [2, N, H, W, C] fp16 (hi, lo) planes"""
+    v = x_nchw.permute(0, 2, 3, 1).contiguous().float()
+    hi = v.half()
+    return torch.stack([hi, (v - hi.float()).half()]).to(device)
+
+
+def _pair_value(x_nchw):
+    """what the (hi, lo) pair of an fp32 tensor represents (float64)"""
+    hi = x_nchw.float().half()
+    lo = (x_nchw.float() - hi.float()).half()
+    return hi.double() + lo.double()
+
+
+def _wsplit(wp64, device):
+    hi, lo, scale = E.split_fp16(wp64.double())
+    return torch.stack([hi, lo]).to(device), scale, (hi.double() + lo.double()) * scale
+
+
+def _act_in(x, device, split):
+    """activation operand + the value it represents"""
+    if split:
+        return _pair_nhwc(x, device), _pair_value(x)
+    return _nhwc_half(x, device), x.half().float()
+
+
+def _plane(t, split):
+    return t.numel() // 2 if split else 0
 
 
 class Case:
@@ -33,26 +66,35 @@ class Case:
         return self.out_view(self.out)
 
 
-def conv_case(kind, N, H, W, cin, cout, device, seed=0, residual=False, relu=True, bias=True, block_n=None):
-    """kind: '1x1' | '3x3' | '3x3s2' | '1x1s2'"""
+def conv_case(kind, N, H, W, cin, cout, device, seed=0, residual=False, relu=True, bias=True, block_n=None, split=False, cta_pair=None):
+    """kind: '1x1' | '3x3' | '3x3s2' | '1x1s2'. split=True: strict precision (hi/lo planes, fp64 reference)"""
     g = torch.Generator().manual_seed(seed)
     k = 3 if kind.startswith("3x3") else 1
     stride = 2 if kind.endswith("s2") else 1
-    x = _rand((N, cin, H, W), g).half().float()
+    x = _rand((N, cin, H, W), g)
     w = _rand((cout, cin, k, k), g, (2.0 / (cin * k * k)) ** 0.5)
     b = _rand((cout,), g, 0.1) if bias else None
     oH, oW = H // stride, W // stride
-    xd = _nhwc_half(x, device)
-    wp = E.pack_conv(w).half().to(device)
+    xd, x = _act_in(x, device, split)
+    scale = 1.0
+    if split:
+        wp, scale, wv = _wsplit(E.pack_conv(w.double()), device)
+        w = wv.reshape(cout, k, k, cin).permute(0, 3, 1, 2).contiguous()
+    else:
+        wp = E.pack_conv(w).half().to(device)
+        w = w.half().float()
     bd = b.float().to(device) if bias else None
-    out = torch.zeros(N, oH, oW, cout, dtype=torch.float16, device=device)
-    res = _rand((N, cout, oH, oW), g).half().float() if residual else None
-    resd = _nhwc_half(res, device) if residual else None
+    out = torch.zeros(*((2,) if split else ()), N, oH, oW, cout, dtype=torch.float16, device=device)
+    res = _rand((N, cout, oH, oW), g) if residual else None
+    resd = None
+    if residual:
+        resd, res = _act_in(res, device, split)
+    pl = _plane(xd, split)
     if stride == 1:
-        srcs = [E._src_dense(xd, N, H, W, cin)]
+        srcs = [E._src_dense(xd, N, H, W, cin, pl)]
         segs = [(0, kh - k // 2, kw - k // 2, cin // 64) for kh in range(k) for kw in range(k)]
     else:
-        srcs = [E._src_parity(xd, N, H, W, cin, ph, pw) for ph in range(2) for pw in range(2)]
+        srcs = [E._src_parity(xd, N, H, W, cin, ph, pw, pl) for ph in range(2) for pw in range(2)]
         segs = []
         for kh in range(k):
             for kw in range(k):
@@ -62,42 +104,49 @@ def conv_case(kind, N, H, W, cin, cout, device, seed=0, residual=False, relu=Tru
         if k == 1:
             srcs = srcs[:1]
     desc = E.make_conv_desc(srcs, segs, wp, bd, cout, 1, (oW, oH, N), out, (cout, oW * cout, oH * oW * cout),
-                            residual=resd, relu=relu, block_n=block_n)
+                            residual=resd, relu=relu, block_n=block_n, split=split, acc_scale=scale, out_plane=_plane(out, split),
+                            res_plane=_plane(resd, split) if residual else 0, cta_pair=cta_pair)
 
     def ref():
-        y = F.conv2d(x, w.half().float(), b, stride=stride, padding=k // 2)
+        y = F.conv2d(x, w, b.to(x.dtype) if bias else None, stride=stride, padding=k // 2)
         if residual:
             y = y + res
-        return F.relu(y) if relu else y
+        return (F.relu(y) if relu else y).float()
 
-    return Case("%s_%dx%dx%d_%d-%d" % (kind, N, H, W, cin, cout), desc, (xd, wp, bd, resd), out,
+    return Case("%s%s_%dx%dx%d_%d-%d" % ("split_" if split else "", kind, N, H, W, cin, cout), desc, (xd, wp, bd, resd), out,
                 lambda t: _out_nchw(t, (N, oH, oW, cout)), ref)
 
 
-def decoder_case(N, lh, lw, cins, cout, device, seed=0, block_n=None):
+def decoder_case(N, lh, lw, cins, cout, device, seed=0, block_n=None, split=False, cta_pair=None):
     """DecoderBlock on cat(sources): nearest x2 -> 3x3 conv -> relu, as 4 phases on the low-res inputs."""
     g = torch.Generator().manual_seed(seed)
-    xs = [_rand((N, c, lh, lw), g).half().float() for c in cins]
+    xs = [_rand((N, c, lh, lw), g) for c in cins]
     ctot = sum(cins)
     w = _rand((cout, ctot, 3, 3), g, (2.0 / (ctot * 9)) ** 0.5)
-    xds = [_nhwc_half(x, device) for x in xs]
-    wp = E.pack_upsample_phases(w).half().to(device)
+    pairs = [_act_in(x, device, split) for x in xs]
+    xds, xs = [p[0] for p in pairs], [p[1] for p in pairs]
+    scale = 1.0
+    if split:
+        wp, scale, _ = _wsplit(E.pack_upsample_phases(w.double()), device)
+        w = w.double()
+    else:
+        wp = E.pack_upsample_phases(w).half().to(device)
     oH, oW = 2 * lh, 2 * lw
-    out = torch.zeros(N, oH, oW, cout, dtype=torch.float16, device=device)
-    srcs = [E._src_dense(t, N, lh, lw, c) for t, c in zip(xds, cins)]
+    out = torch.zeros(*((2,) if split else ()), N, oH, oW, cout, dtype=torch.float16, device=device)
+    srcs = [E._src_dense(t, N, lh, lw, c, _plane(t, split)) for t, c in zip(xds, cins)]
     segs = [(si, th - 1, tw - 1, c // 64) for th in range(2) for tw in range(2) for si, c in enumerate(cins)]
     desc = E.make_conv_desc(srcs, segs, wp, None, cout, 4, (lw, lh, N), out, (cout, oW * cout, oH * oW * cout),
-                            out_scale=(2, 2), block_n=block_n)
+                            out_scale=(2, 2), block_n=block_n, split=split, acc_scale=scale, out_plane=_plane(out, split), cta_pair=cta_pair)
 
     def ref():
         up = F.interpolate(torch.cat(xs, dim=1), scale_factor=2, mode="nearest")
-        return F.relu(F.conv2d(up, w, None, padding=1))
+        return F.relu(F.conv2d(up, w, None, padding=1)).float()
 
-    return Case("decoder_%dx%dx%d_%s-%d" % (N, lh, lw, "+".join(map(str, cins)), cout), desc, (xds, wp), out,
+    return Case("%sdecoder_%dx%dx%d_%s-%d" % ("split_" if split else "", N, lh, lw, "+".join(map(str, cins)), cout), desc, (xds, wp), out,
                 lambda t: _out_nchw(t, (N, oH, oW, cout)), ref)
 
 
-def stem_case(N, H, W, device, seed=0):
+def stem_case(N, H, W, device, seed=0, split=False):
     """resnet conv1 7x7/2 pad 3 + folded bn + relu through the pre-pass and the overlapped-window view."""
     from robosat_b200 import _lib
 
@@ -110,46 +159,63 @@ def stem_case(N, H, W, device, seed=0):
     if torch.device(device).type == "cpu":
         import emulate
 
-        s2d = emulate.prepass_s2d_cpu(x)
+        s2d = emulate.prepass_s2d_split_cpu(x) if split else emulate.prepass_s2d_cpu(x)
     else:
-        s2d = torch.zeros(N, H2, Wp, 16, dtype=torch.float16, device=device)
+        s2d = torch.zeros(*((2,) if split else ()), N, H2, Wp, 16, dtype=torch.float16, device=device)
         lib = _lib.load()
-        _lib.check(lib.rsb_prepass_s2d(xd.data_ptr(), 0, s2d.data_ptr(), N, H, W, None, None, _lib.current_stream_ptr()), "prepass")
-    wp = E.pack_stem(w).half().to(device)
+        if split:
+            _lib.check(lib.rsb_prepass_s2d_split(xd.data_ptr(), 0, s2d.data_ptr(), s2d.numel() // 2, N, H, W, None, None, _lib.current_stream_ptr()), "prepass")
+        else:
+            _lib.check(lib.rsb_prepass_s2d(xd.data_ptr(), 0, s2d.data_ptr(), N, H, W, None, None, _lib.current_stream_ptr()), "prepass")
+    scale = 1.0
+    if split:
+        wp, scale, _ = _wsplit(E.pack_stem(w.double()), device)
+    else:
+        wp = E.pack_stem(w).half().to(device)
     bd = b.to(device)
-    out = torch.zeros(N, H2, W2, 64, dtype=torch.float16, device=device)
-    src = ConvSrc(s2d.data_ptr(), 16, Wp * 16, H2 * Wp * 16, 64, W2, H2, N)
+    out = torch.zeros(*((2,) if split else ()), N, H2, W2, 64, dtype=torch.float16, device=device)
+    src = ConvSrc(s2d.data_ptr(), 16, Wp * 16, H2 * Wp * 16, 64, W2, H2, N, _plane(s2d, split))
     segs = [(0, t - 2, 0, 1) for t in range(4)]
-    desc = E.make_conv_desc([src], segs, wp, bd, 64, 1, (W2, H2, N), out, (64, W2 * 64, H2 * W2 * 64))
+    desc = E.make_conv_desc([src], segs, wp, bd, 64, 1, (W2, H2, N), out, (64, W2 * 64, H2 * W2 * 64), split=split, acc_scale=scale,
+                            out_plane=_plane(out, split))
 
     def ref():
+        if split:
+            return F.relu(F.conv2d(_pair_value(x), w.double(), b.double(), stride=2, padding=3)).float()
         return F.relu(F.conv2d(x.half().float(), w.half().float(), b, stride=2, padding=3))
 
-    return Case("stem_%dx%dx%d" % (N, H, W), desc, (xd, s2d, wp, bd), out, lambda t: _out_nchw(t, (N, H2, W2, 64)), ref)
+    return Case("%sstem_%dx%dx%d" % ("split_" if split else "", N, H, W), desc, (xd, s2d, wp, bd), out, lambda t: _out_nchw(t, (N, H2, W2, 64)), ref)
 
 
-def head_case(N, H, W, classes, device, seed=0):
+def head_case(N, H, W, classes, device, seed=0, split=False):
     """dec5 (3x3 32->32 + relu) fused with final (1x1 32->classes + bias) reading the W-padded dec4 buffer."""
     g = torch.Generator().manual_seed(seed)
-    x = _rand((N, 32, H, W), g).half().float()
+    x = _rand((N, 32, H, W), g)
     w5 = _rand((32, 32, 3, 3), g, (2.0 / 288) ** 0.5)
     wf = _rand((classes, 32, 1, 1), g, 0.3)
     bf = _rand((classes,), g, 0.1)
     Wq = W + 4
-    buf = torch.zeros(N, H, Wq, 32, dtype=torch.float16, device=device)
-    buf[:, :, 1:W + 1, :] = _nhwc_half(x, device)
-    wp = E.pack_window3(w5).half().to(device)
+    xd, x = _act_in(x, device, split)
+    buf = torch.zeros(*((2,) if split else ()), N, H, Wq, 32, dtype=torch.float16, device=device)
+    buf[..., 1:W + 1, :] = xd
+    scale = 1.0
+    if split:
+        wp, scale, _ = _wsplit(E.pack_window3(w5.double()), device)
+        w5 = w5.double()
+    else:
+        wp = E.pack_window3(w5).half().to(device)
+        w5 = w5.half().float()
     hw = wf.reshape(classes, 32).contiguous().to(device)
     hb = bf.to(device)
     logits = torch.zeros(N, classes, H, W, dtype=torch.float32, device=device)
-    src = ConvSrc(buf.data_ptr(), 32, Wq * 32, H * Wq * 32, 128, W, H, N)
+    src = ConvSrc(buf.data_ptr(), 32, Wq * 32, H * Wq * 32, 128, W, H, N, _plane(buf, split))
     segs = [(0, kh - 1, 0, 2) for kh in range(3)]
-    desc = E.make_conv_desc([src], segs, wp, None, 32, 1, (W, H, N), None, None, head=(hw, hb, logits, classes))
+    desc = E.make_conv_desc([src], segs, wp, None, 32, 1, (W, H, N), None, None, head=(hw, hb, logits, classes), split=split, acc_scale=scale)
 
     def ref():
-        return F.conv2d(F.relu(F.conv2d(x, w5.half().float(), None, padding=1)), wf, bf)
+        return F.conv2d(F.relu(F.conv2d(x, w5, None, padding=1)), wf.to(x.dtype), bf.to(x.dtype)).float()
 
-    return Case("head_%dx%dx%d_c%d" % (N, H, W, classes), desc, (buf, wp, hw, hb), logits, lambda t: t.float().cpu(), ref)
+    return Case("%shead_%dx%dx%d_c%d" % ("split_" if split else "", N, H, W, classes), desc, (buf, wp, hw, hb), logits, lambda t: t.float().cpu(), ref)
 
 
 def default_cases(device):
@@ -168,6 +234,30 @@ def default_cases(device):
         lambda: stem_case(2, 64, 64, device, seed=11),
         lambda: head_case(2, 32, 32, 2, device, seed=12),
         lambda: head_case(1, 32, 64, 6, device, seed=13),
+    ]
+
+
+def split_cases(device):
+    """The same layer kinds in strict precision (hi/lo operand planes, three MMAs per K step); references in float64."""
+    return [
+        lambda: conv_case("1x1", 2, 16, 16, 64, 64, device, seed=1, split=True),
+        lambda: conv_case("1x1", 1, 16, 32, 256, 128, device, seed=2, residual=True, block_n=128, split=True),
+        lambda: conv_case("1x1", 2, 16, 16, 64, 256, device, seed=14, residual=True, block_n=64, split=True),
+        lambda: conv_case("3x3", 2, 16, 16, 64, 64, device, seed=3, split=True),
+        lambda: conv_case("3x3", 1, 24, 40, 128, 256, device, seed=4, block_n=256, split=True, cta_pair=False),
+        lambda: conv_case("3x3", 1, 24, 40, 128, 256, device, seed=4, block_n=256, split=True, cta_pair=True),
+        lambda: conv_case("3x3", 8, 64, 64, 64, 256, device, seed=21, block_n=128, split=True, cta_pair=True),   # multi-wave
+        lambda: conv_case("3x3s2", 2, 32, 32, 128, 128, device, seed=5, split=True),
+        lambda: conv_case("1x1s2", 2, 32, 32, 256, 512, device, seed=6, relu=False, split=True),
+        lambda: conv_case("1x1", 3, 8, 8, 512, 2048, device, seed=7, residual=True, block_n=256, split=True, cta_pair=True),
+        lambda: conv_case("1x1", 3, 8, 8, 512, 2048, device, seed=7, residual=True, block_n=128, split=True, cta_pair=False),
+        lambda: decoder_case(2, 8, 8, [128, 64], 64, device, seed=8, split=True),
+        lambda: decoder_case(1, 16, 16, [128], 32, device, seed=9, split=True),
+        lambda: decoder_case(3, 4, 4, [256, 256], 256, device, seed=10, block_n=128, split=True),
+        lambda: decoder_case(2, 4, 4, [2048, 256], 256, device, seed=15, split=True),     # dec0's K = 9216 per phase: long accumulation
+        lambda: stem_case(2, 64, 64, device, seed=11, split=True),
+        lambda: head_case(2, 32, 32, 2, device, seed=12, split=True),
+        lambda: head_case(1, 32, 64, 6, device, seed=13, split=True),
     ]
 
 

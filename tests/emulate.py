@@ -32,34 +32,71 @@ def prepass_s2d_cpu(x):
     return out
 
 
+def prepass_s2d_split_cpu(x):
+    """rsb_prepass_s2d_split: [2, N, H/2, W/2+4, 16], plane 0 = half(x), plane 1 = half(x - float(half(x)))"""
+    import torch
+
+    hi = prepass_s2d_cpu(x)
+    N, C, H, W = x.shape
+    xs = torch.zeros(N, H // 2, W // 2 + 4, 16, dtype=torch.float32)
+    for ph in range(2):
+        for pw in range(2):
+            xs[:, :, 2:2 + W // 2, (ph * 2 + pw) * 3:(ph * 2 + pw) * 3 + 3] = x[:, :, ph::2, pw::2].permute(0, 2, 3, 1)
+    return torch.stack([hi, (xs - hi.float()).half()])
+
+
+def split_pair(v32):
+    """fp32 array -> (hi, lo) fp16 arrays the way the kernels' epilogues do it (residue exact in fp32)"""
+    hi = v32.astype(np.float16)
+    lo = (v32 - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+def _pair(ptr, plane, shape, strides):
+    """value of an operand view: fast mode = the fp16 plane; split mode = hi + lo (exact in fp32), as float64"""
+    v = _view(ptr, shape, strides).astype(np.float64)
+    if plane:
+        v = v + _view(ptr + 2 * plane, shape, strides).astype(np.float64)
+    return v
+
+
 def run_desc(d):
-    """Execute descriptor `d` (host pointers) and write its outputs like the device kernel would."""
+    """Execute descriptor `d` (host pointers) and write its outputs like the device kernel would.
+    Split descriptors: operands are hi + lo pairs; the contraction is done in float64 (the kernel's fp32 accumulation of
+    hi*hi + hi*lo + lo*hi differs from it by ~1e-7 relative), the epilogue in fp32 exactly like the kernel."""
+    split = bool(d.split)
     K = 64 * sum(d.segs[i].cblocks for i in range(d.nseg))
-    wts = _view(d.weights, (d.phases * d.Cout, K), (K, 1)).astype(np.float32)
+    rows = d.phases * d.Cout
+    wts = _pair(d.weights, rows * K if split else 0, (rows, K), (K, 1))
+    if not split:
+        wts = wts.astype(np.float32)
+    scale = np.float32(d.acc_scale if d.acc_scale != 0 else 1.0)
     bias = _view(d.bias, (d.Cout,), (1,), np.float32) if d.bias else None
     Nt, Ht, Wt = d.Nt, d.Ht, d.Wt
     hh0 = np.arange(Ht)[:, None]
     ww0 = np.arange(Wt)[None, :]
+    acc_t = np.float64 if split else np.float32
     for phase in range(d.phases):
         pa, pb = phase >> 1, phase & 1
-        acc = np.zeros((Nt, Ht, Wt, d.Cout), dtype=np.float32)
+        acc = np.zeros((Nt, Ht, Wt, d.Cout), dtype=acc_t)
         k0 = 0
         for si in range(d.nseg):
             seg = d.segs[si]
             src = d.srcs[seg.src]
             width = seg.cblocks * 64
-            sv = _view(src.ptr, (src.N, src.H, src.W, min(width, src.C)), (src.pitch_n, src.pitch_h, src.pitch_w, 1))
+            sv = _pair(src.ptr, src.plane if split else 0, (src.N, src.H, src.W, min(width, src.C)), (src.pitch_n, src.pitch_h, src.pitch_w, 1))
             hh = hh0 + seg.dh + pa
             ww = ww0 + seg.dw + pb
             inb = (hh >= 0) & (hh < src.H) & (ww >= 0) & (ww < src.W)
-            a = np.zeros((Nt, Ht, Wt, width), dtype=np.float32)
-            g = sv[:, np.clip(hh, 0, src.H - 1), np.clip(ww, 0, src.W - 1), :].astype(np.float32)  # [N, Ht, Wt, c]
+            a = np.zeros((Nt, Ht, Wt, width), dtype=acc_t)
+            g = sv[:, np.clip(hh, 0, src.H - 1), np.clip(ww, 0, src.W - 1), :].astype(acc_t)  # [N, Ht, Wt, c]
             g = g * inb[None, :, :, None]
             nn = min(Nt, src.N)
             a[:nn, :, :, :g.shape[-1]] = g[:nn]
             wseg = wts[phase * d.Cout:(phase + 1) * d.Cout, k0:k0 + width]
             acc += np.tensordot(a, wseg, axes=([3], [1]))
             k0 += width
+        acc = acc.astype(np.float32) * scale
         if bias is not None:
             acc += bias
         if d.mode == 0:
@@ -67,11 +104,16 @@ def run_desc(d):
             strides = (d.out_pitch_n, d.out_sy * d.out_pitch_h, d.out_sx * d.out_pitch_w, 1)
             if d.residual:
                 rbase = d.residual + 2 * (pa * d.out_pitch_h + pb * d.out_pitch_w)
-                acc += _view(rbase, (Nt, Ht, Wt, d.Cout), strides).astype(np.float32)
+                acc += _pair(rbase, d.res_plane if split else 0, (Nt, Ht, Wt, d.Cout), strides).astype(np.float32)
             if d.relu:
                 acc = np.maximum(acc, 0)
             ov = _view(base, (Nt, Ht, Wt, d.Cout), strides, writable=True)
-            ov[...] = acc.astype(np.float16)
+            if split:
+                hi, lo = split_pair(acc)
+                ov[...] = hi
+                _view(base + 2 * d.out_plane, (Nt, Ht, Wt, d.Cout), strides, writable=True)[...] = lo
+            else:
+                ov[...] = acc.astype(np.float16)
         else:
             if d.relu:
                 acc = np.maximum(acc, 0)
@@ -124,13 +166,20 @@ def run_engine(engine, x):
     import torch.nn.functional as F
 
     assert engine.plan_only and engine.device.type == "cpu"
+    strict = getattr(engine, "strict", False)
     for op in engine.ops:
         if op[0] == "prepass":
-            engine.s2d.copy_(prepass_s2d_cpu(x))
+            engine.s2d.copy_(prepass_s2d_split_cpu(x) if strict else prepass_s2d_cpu(x))
         elif op[0] == "maxpool":
             _, src, dst, n, h, w, c, k, s, p = op
-            y = F.max_pool2d(src.float().reshape(n, h, w, c).permute(0, 3, 1, 2), kernel_size=k, stride=s, padding=p)
-            dst.copy_(y.permute(0, 2, 3, 1).half())
+            if strict:
+                v = (src[0].float() + src[1].float()).reshape(n, h, w, c).permute(0, 3, 1, 2)
+                y = F.max_pool2d(v, kernel_size=k, stride=s, padding=p).permute(0, 2, 3, 1)
+                hi = y.half()
+                dst.copy_(torch.stack([hi, (y - hi.float()).half()]).reshape(dst.shape))
+            else:
+                y = F.max_pool2d(src.float().reshape(n, h, w, c).permute(0, 3, 1, 2), kernel_size=k, stride=s, padding=p)
+                dst.copy_(y.permute(0, 2, 3, 1).half())
         elif hasattr(op[1].desc, "taps_h"):
             run_rowdesc(op[1].desc)
         else:

@@ -29,16 +29,20 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     # sizes follow from the C declarations (8-byte aligned, no packing pragmas)
-    assert ctypes.sizeof(_lib.ConvSrc) == 48
+    assert ctypes.sizeof(_lib.ConvSrc) == 56
     assert ctypes.sizeof(_lib.ConvSeg) == 16
-    assert _lib.ConvDesc.srcs.offset == 8 and _lib.ConvDesc.segs.offset == 8 + 4 * 48 + 4
+    assert _lib.ConvDesc.srcs.offset == 8 and _lib.ConvDesc.segs.offset == 8 + 4 * 56 + 4
+    # the library reports the sizes it was compiled with; _lib.load() refuses to bind on a mismatch
+    sizes = (ctypes.c_int32 * 4)()
+    _lib.load().rsb_abi_layout(sizes)
+    assert list(sizes) == [ctypes.sizeof(_lib.ConvSrc), ctypes.sizeof(_lib.ConvSeg), ctypes.sizeof(_lib.ConvDesc), ctypes.sizeof(_lib.RowConvDesc)]
     assert _lib.RSB_MAX_SEGS == 16 and _lib.RSB_MAX_SRCS == 4  # keep in sync with include/rsb200.h
     assert ctypes.sizeof(_lib.ConvDesc) % 8 == 0
 
 
 def test_version_and_error_string_without_gpu():
     lib = _lib.load()
-    assert lib.rsb_version() >= 100
+    assert lib.rsb_version() >= 200
     assert isinstance(_lib.last_error(), str)
 
 

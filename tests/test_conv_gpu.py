@@ -42,6 +42,70 @@ def test_conv_case_matches_cpu_reference(i, cuda_device):
         lib.rsb_conv_plan_destroy(plan)
 
 
+@pytest.mark.parametrize("i", range(len(conv_cases.split_cases(None))))
+def test_split_conv_case_matches_fp64_reference(i, cuda_device):
+    """Strict precision (hi/lo fp16 operand planes, 3 MMAs per K step, fp32 accumulate in tensor memory) against a float64
+    reference of the same operation on the values the planes represent. Tolerance: 2e-5 of the output range -- two orders
+    below the fast mode's fp16 rounding and far inside the contract's 1e-3; the measured errors are printed."""
+    lib = _lib.load()
+    case = conv_cases.split_cases(cuda_device)[i]()
+    ref = case.ref()
+    stream = _lib.current_stream_ptr()
+    plan = ctypes.c_void_p()
+    _lib.check(lib.rsb_conv_plan_create(ctypes.byref(case.desc), ctypes.byref(plan)), "plan_create")
+    try:
+        outs = []
+        for _ in range(2):
+            case.out.zero_()
+            _lib.check(lib.rsb_conv_run(plan, stream), "conv_run")
+            torch.cuda.synchronize()
+            outs.append(case.out.clone())
+        assert torch.equal(outs[0], outs[1]), "split conv is not deterministic"
+        got = case.result()
+        scale = max(1.0, ref.abs().max().item())
+        err = (got - ref).abs().max().item()
+        print("%s: max|err| %.3e (%.2e of range)" % (case.name, err, err / scale))
+        assert err <= 2e-5 * scale, (case.name, err)
+        # the SIMT checker (plain fp32 FMAs on hi + lo) agrees
+        case.out.zero_()
+        _lib.check(lib.rsb_conv_run_simt_check(ctypes.byref(case.desc), stream), "simt")
+        torch.cuda.synchronize()
+        assert (case.result() - got).abs().max().item() <= 2e-5 * scale
+    finally:
+        lib.rsb_conv_plan_destroy(plan)
+
+
+def test_split_prepass_and_maxpool(cuda_device):
+    """strict-precision helpers: the pre-pass writes half(x) and half(x - half(x)); the max pool of pairs == max of the sums"""
+    import emulate
+    from robosat_b200 import synth
+
+    lib = _lib.load()
+    u8 = synth.make_tiles_u8(2, 64, seed=5)
+    ref = emulate.prepass_s2d_split_cpu(synth.normalize_tiles(u8))
+    dst = torch.zeros(2, 2, 32, 36, 16, dtype=torch.float16, device=cuda_device)
+    mean = (ctypes.c_float * 3)(*synth.IMAGENET_MEAN)
+    std = (ctypes.c_float * 3)(*synth.IMAGENET_STD)
+    u8d = u8.to(cuda_device)
+    _lib.check(lib.rsb_prepass_s2d_split(u8d.data_ptr(), 1, dst.data_ptr(), dst.numel() // 2, 2, 64, 64, mean, std, _lib.current_stream_ptr()), "prepass")
+    torch.cuda.synchronize()
+    assert torch.equal(dst.cpu(), ref)
+    g = torch.Generator().manual_seed(3)
+    for (N, H, W, C, k, s, p) in [(2, 32, 32, 64, 3, 2, 1), (3, 8, 8, 2048, 2, 2, 0)]:
+        x = torch.randn((N, C, H, W), generator=g)
+        hi = x.half()
+        lo = (x - hi.float()).half()
+        val = hi.float() + lo.float()
+        ref = torch.nn.functional.max_pool2d(val, k, s, p)
+        src = torch.stack([hi, lo]).permute(0, 1, 3, 4, 2).contiguous().to(cuda_device)
+        dst = torch.zeros(2, N, ref.shape[2], ref.shape[3], C, dtype=torch.float16, device=cuda_device)
+        _lib.check(lib.rsb_maxpool_nhwc_split(src.data_ptr(), src.numel() // 2, dst.data_ptr(), dst.numel() // 2, N, H, W, C, k, s, p,
+                                              _lib.current_stream_ptr()), "maxpool_split")
+        torch.cuda.synchronize()
+        d = dst.cpu()
+        assert torch.equal((d[0].float() + d[1].float()).permute(0, 3, 1, 2), ref)
+
+
 @pytest.mark.parametrize("block_n", [64, 128, 256])
 def test_conv_multi_wave_persistent_schedule(block_n, cuda_device):
     """More tiles than SMs: every CTA loops over several tiles and both TMEM accumulator stages are reused."""
