@@ -73,3 +73,14 @@ def allreduce_sum_(flat, world=None):
     if dist.is_available() and dist.is_initialized() and (world or dist.get_world_size()) > 1:
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
     return flat
+
+
+def check_async_error(device, what):
+    """NCCL collectives are asynchronous: a failure (peer died, link error) surfaces only when the stream is synchronised.
+    Called after each collective phase of the tools so that a broken rank turns into a non-zero exit at a named place
+    instead of a hang or a silently wrong result. TORCH_NCCL_ASYNC_ERROR_HANDLING=1 (set by the tools) additionally lets
+    the NCCL watchdog abort the process on a timed-out collective."""
+    try:
+        torch.cuda.synchronize(device)
+    except RuntimeError as exc:  # pragma: no cover  (needs a real fault)
+        raise SystemExit("Error: %s failed on rank %d: %s" % (what, dist.get_rank() if dist.is_initialized() else 0, exc))

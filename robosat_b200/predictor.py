@@ -15,11 +15,11 @@ from robosat_b200.engine import UNetEngine
 
 
 class TilePredictor:
-    def __init__(self, state_dict, num_classes, batch, size, overlap=0, device="cuda", depth=2):
+    def __init__(self, state_dict, num_classes, batch, size, overlap=0, device="cuda", depth=2, precision=None):
         """size: net input extent (tile_size + 2*overlap, predict.py:75); depth: in-flight batches for copy/compute overlap"""
         self.device = torch.device(device)
         self.batch, self.size, self.overlap, self.classes = batch, size, overlap, num_classes
-        self.engine = UNetEngine(state_dict, num_classes, batch, size, size, device=self.device)
+        self.engine = UNetEngine(state_dict, num_classes, batch, size, size, device=self.device, precision=precision)
         self.out_size = size - 2 * overlap
         self.depth = depth
         self._slots = []

@@ -24,11 +24,11 @@ from robosat_b200.engine import UNetEngine
 class SegmentEngine:
     """uint8 RGB tiles [B, H, W, 3] (host) -> uint8 class-index masks [B, H, W] (host), graph-replayed."""
 
-    def __init__(self, state_dict, num_classes, height, width, batch=1, device="cuda", use_graph=True):
+    def __init__(self, state_dict, num_classes, height, width, batch=1, device="cuda", use_graph=True, precision=None):
         assert num_classes <= 255
         self.device = torch.device(device)
         self.batch, self.H, self.W, self.classes = batch, height, width, num_classes
-        self.engine = UNetEngine(state_dict, num_classes, batch, height, width, device=self.device)
+        self.engine = UNetEngine(state_dict, num_classes, batch, height, width, device=self.device, precision=precision)
         self.h_in = torch.empty((batch, height, width, 3), dtype=torch.uint8, pin_memory=True)
         self.d_in = torch.empty((batch, height, width, 3), dtype=torch.uint8, device=self.device)
         self.d_mask = torch.empty((batch, height, width), dtype=torch.uint8, device=self.device)

@@ -54,6 +54,7 @@ class DeviceTileCache:
         self._pool = ThreadPoolExecutor(max_workers=workers)
         self.decodes = 0
         self.hits = 0
+        self.decode_wait_s = 0.0  # time the caller was blocked waiting for decodes (what is left on the critical path)
 
     def slot(self, tile):
         return self._slot.get(tile, -1)
@@ -68,6 +69,12 @@ class DeviceTileCache:
 
     def ensure(self, tiles):
         """Make every tile of `tiles` that exists in the store's index resident. Uploads are enqueued on the current stream."""
+        self.commit(self.prefetch(tiles))
+
+    def prefetch(self, tiles):
+        """First half of `ensure`: decide which tiles are missing, reserve their slots and START decoding them on the pool
+        threads; returns a ticket for `commit`. Between the two calls the caller is free to enqueue GPU work and wait for
+        earlier batches, so the decode of batch i+1 runs while the GPU computes batch i (decode off the critical path)."""
         self._clock += 1
         want = [t for t in dict.fromkeys(tiles) if t in self.index]
         keep = set(want)
@@ -79,21 +86,30 @@ class DeviceTileCache:
             else:
                 self._stamp[s] = self._clock
                 self.hits += 1
+        ticket = []
+        for t in missing:
+            s = self._take_slot(keep)
+            self._slot[t], self._owner[s], self._stamp[s] = s, t, self._clock
+            ticket.append((s, self._pool.submit(decode_rgb, self.index[t], self.size)))
+        self.decodes += len(missing)
+        return ticket
+
+    def commit(self, ticket):
+        """Second half of `ensure`: wait for the decodes of `ticket`, stage them in pinned memory and enqueue their uploads on
+        the current stream (i.e. after every kernel already enqueued that still reads the slots being replaced)."""
+        import time
+
         chunk = self._staging.shape[0]
-        for i in range(0, len(missing), chunk):
-            part = missing[i:i + chunk]
+        for i in range(0, len(ticket), chunk):
+            part = ticket[i:i + chunk]
             if self._staged is not None:
                 self._staged.synchronize()  # the previous upload has finished reading the staging buffer
             stage = self._staging.numpy()
-
-            def work(j, t):
-                stage[j] = decode_rgb(self.index[t], self.size)
-
-            list(self._pool.map(lambda jt: work(*jt), enumerate(part)))
-            self.decodes += len(part)
-            for j, t in enumerate(part):
-                s = self._take_slot(keep)
-                self._slot[t], self._owner[s], self._stamp[s] = s, t, self._clock
+            t0 = time.perf_counter()
+            for j, (_, fut) in enumerate(part):
+                stage[j] = fut.result()
+            self.decode_wait_s += time.perf_counter() - t0
+            for j, (s, _) in enumerate(part):
                 self.store[s].copy_(self._staging[j], non_blocking=True)
             if self._staged is not None:
                 self._staged.record(torch.cuda.current_stream(self.device))
@@ -117,12 +133,20 @@ class HaloStitcher:
         self._dtable = torch.empty((batch, 9), dtype=torch.int32, device=cache.device)
         self._used = [torch.cuda.Event() if cache.device.type == "cuda" else None for _ in range(2)]
         self._n = 0
+        self._ticket = None
+
+    def prefetch(self, tiles):
+        """Start decoding what `stitch(tiles, ...)` will need (call right after the previous `stitch`)."""
+        self._ticket = (tiles, self.cache.prefetch([k for t in tiles for k in neighbour_keys(t)]))
 
     def stitch(self, tiles, out):
         """tiles: <= batch Tile keys (missing rows of a ragged last batch become black); out: device uint8 [batch, F, F, 3]."""
         assert len(tiles) <= self.batch and tuple(out.shape) == (self.batch, self.full, self.full, 3) and out.dtype == torch.uint8
-        needed = [k for t in tiles for k in neighbour_keys(t)]
-        self.cache.ensure(needed)
+        if self._ticket is not None and self._ticket[0] is tiles:
+            self.cache.commit(self._ticket[1])  # decodes started by prefetch(tiles)
+        else:
+            self.cache.ensure([k for t in tiles for k in neighbour_keys(t)])
+        self._ticket = None
         i = self._n % 2
         self._n += 1
         if self._used[i] is not None:

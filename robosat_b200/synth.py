@@ -148,3 +148,31 @@ def make_masks(n, size, num_classes=2, seed=3):
     g.manual_seed(int(seed))
     coarse = torch.randint(0, num_classes, (n, 1, max(size // 16, 1), max(size // 16, 1)), generator=g)
     return torch.nn.functional.interpolate(coarse.float(), size=(size, size), mode="nearest").long().squeeze(1)
+
+
+def write_slippy_tiles(root, z, x_range, y_range, size=512, seed=7, workers=16, fmt="png"):
+    """A synthetic slippy-map directory `root/z/x/y.png` over a contiguous x/y grid (so that every interior tile has its 8
+    neighbours, SURVEY.md 8(d) cfg 4): lossless PNGs of `make_tiles_u8` imagery. Returns the number of tiles written."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    from PIL import Image
+
+    xs, ys = list(x_range), list(y_range)
+    pool_imgs = make_tiles_u8(64, size, seed=seed).numpy()  # 64 distinct images, reused round-robin with a flip/rotation per tile
+
+    def one(job):
+        i, x, y = job
+        a = pool_imgs[i % 64]
+        k = (i // 64) % 8
+        a = a[::-1] if k & 1 else a
+        a = a[:, ::-1] if k & 2 else a
+        a = a.transpose(1, 0, 2) if k & 4 else a
+        d = os.path.join(root, str(z), str(x))
+        os.makedirs(d, exist_ok=True)
+        Image.fromarray(a.copy()).save(os.path.join(d, "%d.%s" % (y, fmt)), compress_level=1)
+
+    jobs = [(i, x, y) for i, (x, y) in enumerate((x, y) for x in xs for y in ys)]
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        list(pool.map(one, jobs))
+    return len(jobs)

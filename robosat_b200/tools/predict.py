@@ -11,6 +11,7 @@ broadcast once over NCCL and no other collective is used.
 import argparse
 import os
 import sys
+import time
 from concurrent.futures import ThreadPoolExecutor
 
 import torch
@@ -37,18 +38,127 @@ def add_parser(subparser):
     parser.set_defaults(func=main)
 
 
-def _save_png(root, palette, x, y, z, quantized):
+def _save_png(root, palette, x, y, z, quantized, stats=None):
+    t0 = time.perf_counter()
     out = Image.fromarray(quantized, mode="P")
     out.putpalette(palette)
     os.makedirs(os.path.join(root, str(z), str(x)), exist_ok=True)
     out.save(os.path.join(root, str(z), str(x), str(y) + ".png"), optimize=True)
+    if stats is not None:
+        stats["png_cpu_s"] = stats.get("png_cpu_s", 0.0) + (time.perf_counter() - t0)  # summed over pool threads (GIL-protected add)
+
+
+def run_shard(rank, world, args, device, sd, num_classes, stats=None):
+    """This rank's share of the `rs predict` batch loop (predict.py:75-113): enumerate -> [decode -> halo stitch -> net -> bins]
+    -> PNG. No collective in here: `sd` is the (already broadcast) state_dict. `stats` (optional dict) receives the stage
+    times the cfg-4 benchmark reports: tiles, batches, wall_s, decode_wait_s (main thread blocked on decodes), gpu_wait_s
+    (blocked on the device result), png_cpu_s (encode seconds summed over pool threads), png_drain_s (waiting for the last
+    encodes after the last batch), pool_threads."""
+    from torch.utils.data import DataLoader, Subset
+
+    from robosat_b200.dist import shard_range
+    from robosat_b200.predictor import TilePredictor
+
+    t_start = time.perf_counter()
+    st = stats if stats is not None else {}
+    size = args.tile_size + 2 * args.overlap
+    palette = continuous_palette_for_color("pink", 256)
+    pool_threads = int(os.environ.get("RSB_PNG_THREADS", "0")) or max(4, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)) // max(world, 1))
+    st.update(pool_threads=pool_threads, gpu_wait_s=0.0, png_cpu_s=0.0)
+
+    def progress(it, total):
+        if os.environ.get("RSB_QUIET"):
+            return it
+        try:
+            from tqdm import tqdm
+
+            return tqdm(it, total=total, desc="Eval", unit="batch", ascii=True, disable=rank != 0)
+        except ImportError:  # pragma: no cover
+            return it
+
+    def collect(predictor):
+        t0 = time.perf_counter()
+        q = predictor.collect().numpy()
+        st["gpu_wait_s"] += time.perf_counter() - t0
+        return q
+
+    if os.environ.get("RSB_HOST_STITCH", "0") == "1":
+        # reference-shaped input path: every buffered tile is assembled on the host (up to 9 decodes per tile) and copied over PCIe
+        directory = BufferedSlippyMapDirectory(args.tiles, transform=ImageToUint8Tensor(), size=args.tile_size, overlap=args.overlap)
+        assert len(directory) > 0, "at least one tile in dataset"
+        lo, hi = shard_range(len(directory), rank, world)
+        loader = DataLoader(Subset(directory, range(lo, hi)), batch_size=args.batch_size, num_workers=args.workers)
+        predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device)
+        st.update(tiles=hi - lo, batches=len(loader), decode_wait_s=0.0)
+        with ThreadPoolExecutor(max_workers=pool_threads) as pool:
+            pending = []
+            for images, tiles in progress(loader, len(loader)):
+                n = images.shape[0]
+                staging = predictor.pinned_input()
+                staging[:n].copy_(images)
+                if n < args.batch_size:
+                    staging[n:].zero_()  # last, ragged batch: pad with black tiles and drop their outputs
+                predictor.submit(staging)
+                quantized = collect(predictor)
+                for tile, q in zip(tiles, quantized[:n]):
+                    x, y, z = (int(v) for v in tile)
+                    pending.append(pool.submit(_save_png, args.probs, palette, x, y, z, q.copy(), st))
+            t0 = time.perf_counter()
+            for f in pending:
+                f.result()
+            st["png_drain_s"] = time.perf_counter() - t0
+    else:
+        # default: decode every tile once, keep it in a device-resident cache and stitch the halo there (robosat_b200/stitch.py)
+        from robosat_b200.stitch import DeviceTileCache, HaloStitcher
+        from robosat_b200.tiles import tiles_from_slippy_map
+
+        index = dict(tiles_from_slippy_map(args.tiles))
+        assert len(index) > 0, "at least one tile in dataset"
+        order = sorted(index, key=lambda t: (int(t.z), int(t.x), int(t.y)))  # column-major: neighbours stay resident
+        lo, hi = shard_range(len(order), rank, world)
+        mine = order[lo:hi]
+        capacity = max(9 * args.batch_size, int(os.environ.get("RSB_TILE_CACHE", "2048")))
+        decode_threads = args.workers if args.workers > 0 else min(16, pool_threads)
+        cache = DeviceTileCache(index, args.tile_size, capacity, device=device, workers=decode_threads)
+        stitcher = HaloStitcher(cache, args.overlap, args.batch_size)
+        predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device)
+        chunks = [mine[i:i + args.batch_size] for i in range(0, len(mine), args.batch_size)]
+        st.update(tiles=len(mine), batches=len(chunks), decode_threads=decode_threads)
+        with ThreadPoolExecutor(max_workers=pool_threads) as pool:
+            pending = []
+
+            def drain(tiles):
+                quantized = collect(predictor)
+                for tile, q in zip(tiles, quantized[:len(tiles)]):
+                    pending.append(pool.submit(_save_png, args.probs, palette, int(tile.x), int(tile.y), int(tile.z), q.copy(), st))
+
+            previous = None
+            if chunks:
+                stitcher.prefetch(chunks[0])
+            for ci, tiles in enumerate(progress(chunks, len(chunks))):
+                stitcher.stitch(tiles, predictor.device_input())  # upload what was decoded ahead, assemble the buffered batch on the device
+                if ci + 1 < len(chunks):
+                    stitcher.prefetch(chunks[ci + 1])  # decode batch i+1 on the pool threads while the GPU runs batch i
+                predictor.submit_device()
+                if previous is not None:
+                    drain(previous)  # batch i-1 is collected while batch i runs
+                previous = tiles
+            if previous is not None:
+                drain(previous)
+            t0 = time.perf_counter()
+            for f in pending:
+                f.result()
+            st["png_drain_s"] = time.perf_counter() - t0
+        cache.close()
+        st.update(decode_wait_s=cache.decode_wait_s, decodes=cache.decodes, cache_hits=cache.hits)
+        if rank == 0 and os.environ.get("RSB_VERBOSE"):
+            print("tile cache: %d decodes for %d tiles (%d cache hits)" % (cache.decodes, len(mine), cache.hits))
+    st["wall_s"] = time.perf_counter() - t_start
+    return st
 
 
 def _run(rank, world, args, port):
-    from torch.utils.data import DataLoader, Subset
-
-    from robosat_b200.dist import broadcast_state_dict, shard_range, unet_state_template
-    from robosat_b200.predictor import TilePredictor
+    from robosat_b200.dist import broadcast_state_dict, check_async_error, unet_state_template
 
     dataset = load_config(args.dataset)
     num_classes = len(dataset["common"]["classes"])
@@ -64,85 +174,18 @@ def _run(rank, world, args, port):
 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", str(port))
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")  # a failed collective aborts the process instead of hanging it
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
         sd = broadcast_state_dict(sd, unet_state_template(num_classes), device)  # the single collective of this tool
+        check_async_error(device, "checkpoint broadcast")
 
-    size = args.tile_size + 2 * args.overlap
-    palette = continuous_palette_for_color("pink", 256)
-    pool_threads = max(4, (os.cpu_count() or 8) // max(world, 1))
-
-    def progress(it, total):
-        try:
-            from tqdm import tqdm
-
-            return tqdm(it, total=total, desc="Eval", unit="batch", ascii=True, disable=rank != 0)
-        except ImportError:  # pragma: no cover
-            return it
-
-    if os.environ.get("RSB_HOST_STITCH", "0") == "1":
-        # reference-shaped input path: every buffered tile is assembled on the host (up to 9 decodes per tile) and copied over PCIe
-        directory = BufferedSlippyMapDirectory(args.tiles, transform=ImageToUint8Tensor(), size=args.tile_size, overlap=args.overlap)
-        assert len(directory) > 0, "at least one tile in dataset"
-        lo, hi = shard_range(len(directory), rank, world)
-        loader = DataLoader(Subset(directory, range(lo, hi)), batch_size=args.batch_size, num_workers=args.workers)
-        predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device)
-        with ThreadPoolExecutor(max_workers=pool_threads) as pool:
-            pending = []
-            for images, tiles in progress(loader, len(loader)):
-                n = images.shape[0]
-                staging = predictor.pinned_input()
-                staging[:n].copy_(images)
-                if n < args.batch_size:
-                    staging[n:].zero_()  # last, ragged batch: pad with black tiles and drop their outputs
-                predictor.submit(staging)
-                quantized = predictor.collect().numpy()
-                for tile, q in zip(tiles, quantized[:n]):
-                    x, y, z = (int(v) for v in tile)
-                    pending.append(pool.submit(_save_png, args.probs, palette, x, y, z, q.copy()))
-            for f in pending:
-                f.result()
-    else:
-        # default: decode every tile once, keep it in a device-resident cache and stitch the halo there (robosat_b200/stitch.py)
-        from robosat_b200.stitch import DeviceTileCache, HaloStitcher
-        from robosat_b200.tiles import tiles_from_slippy_map
-
-        index = dict(tiles_from_slippy_map(args.tiles))
-        assert len(index) > 0, "at least one tile in dataset"
-        order = sorted(index, key=lambda t: (int(t.z), int(t.x), int(t.y)))  # column-major: neighbours stay resident
-        lo, hi = shard_range(len(order), rank, world)
-        mine = order[lo:hi]
-        capacity = max(9 * args.batch_size, int(os.environ.get("RSB_TILE_CACHE", "2048")))
-        cache = DeviceTileCache(index, args.tile_size, capacity, device=device, workers=args.workers if args.workers > 0 else min(16, pool_threads))
-        stitcher = HaloStitcher(cache, args.overlap, args.batch_size)
-        predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device)
-        chunks = [mine[i:i + args.batch_size] for i in range(0, len(mine), args.batch_size)]
-        with ThreadPoolExecutor(max_workers=pool_threads) as pool:
-            pending = []
-
-            def drain(tiles):
-                quantized = predictor.collect().numpy()
-                for tile, q in zip(tiles, quantized[:len(tiles)]):
-                    pending.append(pool.submit(_save_png, args.probs, palette, int(tile.x), int(tile.y), int(tile.z), q.copy()))
-
-            previous = None
-            for tiles in progress(chunks, len(chunks)):
-                stitcher.stitch(tiles, predictor.device_input())  # decode + upload what is new, assemble the buffered batch on the device
-                predictor.submit_device()
-                if previous is not None:
-                    drain(previous)  # batch i-1 is collected while batch i runs
-                previous = tiles
-            if previous is not None:
-                drain(previous)
-            for f in pending:
-                f.result()
-        cache.close()
-        if rank == 0 and os.environ.get("RSB_VERBOSE"):
-            print("tile cache: %d decodes for %d tiles (%d cache hits)" % (cache.decodes, len(mine), cache.hits))
+    run_shard(rank, world, args, device, sd, num_classes)
 
     if world > 1:
         import torch.distributed as dist
 
         dist.barrier()
+        check_async_error(device, "final barrier")
         dist.destroy_process_group()
 
 
@@ -165,4 +208,7 @@ def main(args):
         with socket.socket() as s:
             s.bind(("127.0.0.1", 0))
             port = s.getsockname()[1]
-        mp.spawn(_run, args=(world, args, port), nprocs=world, join=True)
+        try:
+            mp.spawn(_run, args=(world, args, port), nprocs=world, join=True)
+        except Exception as exc:  # a rank died (CUDA / NCCL error, bad tile): the whole tool exits non-zero, like the reference's sys.exit
+            sys.exit("Error: a predict rank failed: %s" % exc)

@@ -26,11 +26,23 @@ class _TrainStep(torch.autograd.Function):
     def forward(ctx, x, module, names, *params):
         eng = module._train_engine_for(x)
         logits = eng.forward(x.contiguous())
+        # the plan's saved activations / batch statistics are static buffers shared by every forward of this input shape:
+        # stamp the forward so that a backward through a graph whose buffers were overwritten fails instead of being wrong
+        eng.generation = getattr(eng, "generation", 0) + 1
+        ctx.generation, ctx.consumed = eng.generation, False
         ctx.eng, ctx.names, ctx.params, ctx.fused = eng, names, params, module.fused_grad_accumulation
         return logits.clone()
 
     @staticmethod
     def backward(ctx, grad_out):
+        if ctx.consumed:
+            raise RuntimeError("robosat_b200.UNet: backward() ran twice through the same forward (retain_graph): the training plan "
+                               "keeps one set of saved activations and consumes them in place; run forward again")
+        if ctx.eng.generation != ctx.generation:
+            raise RuntimeError("robosat_b200.UNet: a second train-mode forward with the same input shape ran before this graph's "
+                               "backward() and overwrote its saved activations (one static plan per shape); call backward() "
+                               "after each forward (gradient accumulation: forward, backward, forward, backward)")
+        ctx.consumed = True
         grads = ctx.eng.backward(grad_out.contiguous().float())
         if ctx.fused:
             # every parameter that already holds a dense fp32 .grad (the usual case after optimizer.zero_grad()) is
@@ -90,7 +102,9 @@ class UNet(nn.Module):
         self.dec5 = ConvRelu(num_filters, num_filters)
         self.final = nn.Conv2d(num_filters, num_classes, kernel_size=1)
         self._engines = {}
+        self._engines_version = None
         self._train_engines = {}
+        self.precision = None  # None: RSB_PRECISION or "strict" (see robosat_b200.engine.UNetEngine)
         # loss.backward() adds into existing .grad tensors with one kernel instead of one autograd add per parameter
         # (False: hand every gradient to autograd, e.g. when tensor hooks on parameters must fire)
         self.fused_grad_accumulation = True
@@ -104,6 +118,15 @@ class UNet(nn.Module):
 
     def invalidate_plans(self):
         self._engines.clear()
+
+    def _weights_version(self):
+        """Cheap fingerprint of the weights the inference plans were packed from: tensor identity + torch's in-place version
+        counters. It changes on load_state_dict (also through an nn.DataParallel / DDP wrapper, which never reaches this class's
+        override), optimizer steps and any other in-place edit, so a cached plan can never serve stale folded weights."""
+        v = 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            v = (v * 1000003 + t._version * 7919 + (t.data_ptr() & 0xFFFFFFFF)) & 0xFFFFFFFFFFFFFFFF
+        return v
 
     def train(self, mode=True):
         if mode:
@@ -124,13 +147,17 @@ class UNet(nn.Module):
         return eng
 
     def _engine_for(self, x):
-        key = (tuple(x.shape), x.dtype, x.device.index)
+        version = self._weights_version()
+        if version != self._engines_version:
+            self._engines.clear()
+            self._engines_version = version
+        key = (tuple(x.shape), x.dtype, x.device.index, self.precision)
         eng = self._engines.get(key)
         if eng is None:
             n = x.shape[0]
             h, w = (x.shape[2], x.shape[3]) if x.dtype == torch.float32 else (x.shape[1], x.shape[2])
             sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
-            eng = UNetEngine(sd, self.num_classes, n, h, w, device=x.device)
+            eng = UNetEngine(sd, self.num_classes, n, h, w, device=x.device, precision=self.precision)
             self._engines[key] = eng
         return eng
 

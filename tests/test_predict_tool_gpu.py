@@ -50,7 +50,7 @@ def test_rs_predict_end_to_end(tmp_path, cuda_device, monkeypatch):
 
     directory = BufferedSlippyMapDirectory(str(tiles_dir), transform=ImageToUint8Tensor(), size=256, overlap=32)
     palette = colors.continuous_palette_for_color("pink", 256)
-    worst, total_diff, total_px = 0, 0, 0
+    worst, total_diff, total_px, argmax_flips = 0, 0, 0, 0
     for i in range(len(directory)):
         image, xyz = directory[i]
         x, y, z = (int(v) for v in xyz)
@@ -62,8 +62,13 @@ def test_rs_predict_end_to_end(tmp_path, cuda_device, monkeypatch):
         ref = np.digitize(fg, np.linspace(0, 1, 256)).astype(np.uint8)
         diff = np.abs(np.array(out).astype(np.int32) - ref.astype(np.int32))
         worst = max(worst, int(diff.max()))
-        total_diff += int((diff > 1).sum())
+        total_diff += int((diff > 0).sum())
         total_px += diff.size
-    print("rs predict vs reference pipeline: worst bin difference %d, pixels off by more than one bin %d / %d" % (worst, total_diff, total_px))
-    # fp16 logits move the foreground probability by <= ~1e-2, i.e. a couple of the 255 bins on a few pixels
-    assert worst <= 4 and total_diff <= 0.01 * total_px
+        # the argmax the probability image encodes: foreground iff p > 0.5, i.e. bin >= 129 (anchor 128/255 > 0.5)
+        argmax_flips += int(((np.array(out) >= 129) != (ref >= 129)).sum())
+    print("rs predict vs reference pipeline: worst bin difference %d, pixels whose bin differs %d / %d, argmax flips %d" % (
+        worst, total_diff, total_px, argmax_flips))
+    # Default (strict) precision: the foreground probability agrees to ~1e-4, so a bin (width 1/255) can only differ where the
+    # reference probability sits that close to a bin edge -- by exactly one bin, on a small fraction of the pixels.
+    assert worst <= 1 and total_diff <= 0.02 * total_px
+    assert argmax_flips <= max(2, 8 * total_px // 131072)
