@@ -162,13 +162,62 @@ def cpu_reference_leg(steps, warmup, tiles_per_step, threads=None):
                       "(fastest of the candidates <= %d available)" % (steps, tiles_per_step, TILE, TILE, cores, avail)}, dt / steps
 
 
+def cpu_baseline_subprocess(steps=2, warmup=1, tiles_per_step=16):
+    """cpu_baseline of the GPU arm: `bench.py --impl reference` on a bounded sample (3 x 16 tiles, 10-30 s of CPU work) in a
+    child process that cannot see the GPUs."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup),
+                          "--tiles-per-step", str(tiles_per_step)], env=env, capture_output=True, text=True, timeout=900)
+    for ln in reversed(out.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError("reference arm printed no JSON: " + out.stderr[-300:])
+
+
+def reference_gpu_leg(dev, steps=3, warmup=2):
+    """Secondary (SURVEY.md 8(d) "optional secondary"): the UNMODIFIED reference with a visible GPU -- `nn.DataParallel(UNet)`
+    moves itself to cuda:0 and runs torch eager / cuDNN (TF32 convolutions by default): the existing Blackwell path. Timed host
+    to host like predict.py:83-87 (fp32 NCHW tiles in, fp32 probabilities out), batch 32. Not the CPU baseline, not our code."""
+    import torch
+
+    from baseline import ref_loader
+    from robosat_b200 import synth
+
+    sd = synth.make_state_dict(CLASSES, seed=0)
+    net = ref_loader.reference_net(sd, CLASSES)
+    x = synth.normalize_tiles(synth.make_tiles_u8(BATCH, TILE, seed=1))
+
+    def run():
+        with torch.no_grad():
+            return torch.nn.functional.softmax(net(x.to(dev)), dim=1).data.cpu().numpy()
+
+    for _ in range(warmup):
+        run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run()
+    dt = time.perf_counter() - t0
+    del net
+    torch.cuda.empty_cache()
+    return {"value": steps * BATCH / dt, "unit": "tiles/s", "kind": "unmodified reference on cuda:0 (torch %s eager, cuDNN, allow_tf32=%s)" % (
+        torch.__version__, torch.backends.cudnn.allow_tf32), "steps": steps, "batch": BATCH,
+            "note": "host to host incl. H2D of fp32 tiles and D2H of fp32 probabilities, as predict.py:83-87 does"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
+    # The reference's CPU path: on a host with a visible GPU `nn.DataParallel` moves the module to cuda:0 by itself (a one-GPU
+    # DataParallel calls module.to(device)), so the GPUs are hidden from THIS process before torch initialises CUDA -- exactly
+    # the situation of `cuda = false` on a GPU-less host (predict.py:47-63), where DataParallel is a pass-through.
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""
     # a step is a bounded sample of the workload's batch: up to its 32 tiles, shrunk so that the whole run stays within ~640
     # tiles (3-4 minutes at the 3-6 tiles/s the host cores reach; the per-tile CPU rate does not depend on the batch size
     # beyond a few tiles). The sample actually used is stated in cpu_baseline.sample.
-    per_step = max(1, min(BATCH, 640 // max(1, args.steps + args.warmup)))
+    per_step = args.tiles_per_step or max(1, min(BATCH, 640 // max(1, args.steps + args.warmup)))
     cb, s_per_step = cpu_reference_leg(args.steps, args.warmup, per_step)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tiles/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -251,18 +300,23 @@ def predict_leg(precision, sd, dev, rank, world, steps, warmup, dist, with_clock
         barrier()
         return e0.elapsed_time(e1)
 
-    for i in range(warmup):
-        step(i)
-    barrier()
+    # nvidia-smi needs ~1 s to start reporting and samples every 100 ms: the sampler covers warm-up, the timed K steps and
+    # the sustained run that follows, all of them the same back-to-back step
     sampler = ClockSampler(dev.index)
     if rank == 0 and with_clocks:
         sampler.start()
+        time.sleep(1.0)
+    for i in range(warmup):
+        step(i)
+    barrier()
     ms = timed(steps)
-    clocks = sampler.stop() if rank == 0 and with_clocks else None
     sustained_ms = sustained_steps = None
     if steps < 100:
         sustained_steps = max(100, int(1500.0 / max(ms / steps, 1e-3)))  # >= 1.5 s of back-to-back steps: the power-capped regime
         sustained_ms = timed(sustained_steps)
+    clocks = sampler.stop() if rank == 0 and with_clocks else None
+    if clocks is not None:
+        clocks["window"] = "warm-up + the %d timed steps%s" % (steps, " + the sustained run" if sustained_steps else "")
 
     # end to end through the host API: pinned host tiles in, uint8 bins out, copies inside the timed region
     host_batches = [synth.make_tiles_u8(BATCH, TILE, seed=200 + rank * 10 + i).pin_memory() for i in range(2)]
@@ -447,7 +501,7 @@ def cfg4_leg(dev, rank, world, dist, sd, tiles_per_gpu, batch=32, tile=512, over
     st = run_shard(rank, world, args, dev, sd, CLASSES, stats={})
     torch.cuda.synchronize()
     mine = time.perf_counter() - t0
-    keys = ["wall_s", "decode_wait_s", "gpu_wait_s", "png_drain_s", "png_cpu_s"]
+    keys = ["wall_s", "decode_wait_s", "gpu_wait_s", "png_drain_s", "png_cpu_s", "setup_s"]
     vec = torch.tensor([mine] + [float(st.get(k, 0.0)) for k in keys] + [float(st["tiles"])], device=dev, dtype=torch.float64)
     mx = vec.clone()
     sm = vec.clone()
@@ -482,7 +536,10 @@ def cfg4_leg(dev, rank, world, dist, sd, tiles_per_gpu, batch=32, tile=512, over
     bound = max(stage, key=stage.get)
     names = {"decode_wait_s": "decode (PIL PNG decode on %d pool threads per rank; main thread blocked waiting for it)" % st.get("decode_threads", 0),
              "gpu_wait_s": "net (main thread blocked on the device result)", "png_drain_s": "PNG encode (optimize=True, %d pool threads per rank)" % st["pool_threads"]}
+    setup = mx[6].item()
     return {"metric": "512x512 tiles/sec end to end (rs predict: PNG tiles in -> probability PNGs out)", "value": total_tiles / wall, "unit": "tiles/s",
+            "steady_state_tiles_per_s": total_tiles / max(wall - setup, 1e-9), "setup_s": setup,
+            "setup_note": "directory listing + plan construction (fold/split/pack 39 M weights on the host) + buffers: paid once per run, amortised over 100 k tiles",
             "n_gpus": world, "tiles": total_tiles, "tiles_per_gpu": total_tiles // world, "wall_s": wall, "batch": batch, "tile_size": tile, "overlap": overlap,
             "precision": "strict", "host_threads_per_rank": threads,
             "config": "rs predict: ResNet50-UNet, 2-class, 3x512x512 (+32 px halo), synthetic slippy-map PNG dir sharded across %d x B200 "
@@ -575,6 +632,7 @@ def main():
     ap.add_argument("--no-cfg4", action="store_true", help="skip the slippy-map directory leg (configs[3])")
     ap.add_argument("--no-extras", action="store_true", help="headline + fast mode only")
     ap.add_argument("--cfg4-tiles", type=int, default=1024, help="tiles per GPU in the synthetic slippy-map directory")
+    ap.add_argument("--tiles-per-step", type=int, default=0, help="(--impl reference) tiles per step instead of the automatic bounded sample")
     ap.add_argument("--layers-out", default=None, help="write the per-layer timing tables (JSON) here (_strict / _fast suffix)")
     args = ap.parse_args()
 
@@ -644,8 +702,8 @@ def main():
         line.update(extras)
         if world == 1 and not args.no_extras:
             if not args.no_cpu_baseline:  # the CPU baseline is an N=1 figure (rank 0 only), ~10-30 s of CPU work
-                cb = guarded(cpu_reference_leg, 2, 1, 16)
-                line["cpu_baseline"] = cb[0] if isinstance(cb, tuple) else cb
+                line["cpu_baseline"] = guarded(cpu_baseline_subprocess)
+            line["reference_cudnn"] = guarded(reference_gpu_leg, dev)
             line["stitch"] = guarded(stitch_leg, dev)
             line["serve"] = guarded(serve_leg, dev)
         print(json.dumps(line), flush=True)

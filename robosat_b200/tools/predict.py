@@ -118,12 +118,13 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
         lo, hi = shard_range(len(order), rank, world)
         mine = order[lo:hi]
         capacity = max(9 * args.batch_size, int(os.environ.get("RSB_TILE_CACHE", "2048")))
-        decode_threads = args.workers if args.workers > 0 else min(16, pool_threads)
+        decode_threads = args.workers if args.workers > 0 else min(32, pool_threads)
         cache = DeviceTileCache(index, args.tile_size, capacity, device=device, workers=decode_threads)
         stitcher = HaloStitcher(cache, args.overlap, args.batch_size)
         predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device)
         chunks = [mine[i:i + args.batch_size] for i in range(0, len(mine), args.batch_size)]
         st.update(tiles=len(mine), batches=len(chunks), decode_threads=decode_threads)
+        st["setup_s"] = time.perf_counter() - t_start  # enumerate + plan (weight folding / packing) + buffers, before the first batch
         with ThreadPoolExecutor(max_workers=pool_threads) as pool:
             pending = []
 
