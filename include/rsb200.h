@@ -27,6 +27,7 @@ extern "C" {
 #define RSB_E_INVALID -1   /* bad argument / unsupported shape */
 #define RSB_E_CUDA -2      /* CUDA runtime or driver error */
 #define RSB_E_NODEVICE -3  /* no sm_100 device / driver entry point missing */
+#define RSB_E_UNSUPPORTED -4 /* (host codecs only) valid input of a kind this entry point does not handle: use another decoder */
 
 #define RSB_MAX_SEGS 16
 #define RSB_MAX_SRCS 4
@@ -209,6 +210,21 @@ int rsb_class_histogram(const uint8_t* labels, int64_t n, int32_t C, uint64_t* c
 /* `Predictor.segment` head (robosat/tools/serve.py:150-165): output.argmax(axis=0).astype(uint8) of fp32 NCHW logits
  * -> uint8 [N][H*W] class indices, first maximum wins like np.argmax; C <= 255. */
 int rsb_head_argmax(const float* logits, uint8_t* mask, int32_t N, int32_t C, int32_t HW, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-side PNG codec for the files either side of the predict path (HOST pointers, plain C over zlib, no Python / GIL so the
+ * tools' pool threads run truly in parallel). Pixel-identical to PIL; not a compute fallback -- no device work happens here.
+ */
+/* `Image.open(path).convert("RGB")` (robosat/tiles.py:150-159,181) for 8-bit non-interlaced PNGs (gray, RGB, palette, +alpha):
+ * out_rgb_host uint8 [h][w][3]. RSB_E_UNSUPPORTED for other PNG flavours / non-PNG files (the caller then uses PIL). */
+int rsb_png_decode_rgb(const uint8_t* file_bytes_host, int64_t n, uint8_t* out_rgb_host, int32_t w_expected, int32_t h_expected);
+int rsb_png_read_rgb(const char* path, uint8_t* out_rgb_host, int32_t w_expected, int32_t h_expected);
+/* `Image.fromarray(q, mode="P"); putpalette(palette); save(path)` (robosat/tools/predict.py:105-113): 8-bit palette PNG,
+ * palette_rgb_host uint8 [entries][3]; level = zlib level (0-9, <0 default). encode returns the byte count or a negative code. */
+int64_t rsb_png_encode_p8(const uint8_t* pixels_host, int32_t w, int32_t h, const uint8_t* palette_rgb_host, int32_t entries, int32_t level,
+                          uint8_t* out_host, int64_t capacity);
+int rsb_png_write_p8(const char* path, const uint8_t* pixels_host, int32_t w, int32_t h, const uint8_t* palette_rgb_host, int32_t entries,
+                     int32_t level);
 
 /* ---------------------------------------------------------------------------------------------
  * Losses and metrics on fp32 NCHW logits + int64 targets [N][H][W].

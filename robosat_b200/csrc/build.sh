@@ -9,5 +9,7 @@ for f in rsb_host rsb_conv rsb_conv_row rsb_elementwise rsb_loss rsb_train rsb_w
   $NVCC $FLAGS -c $f.cu -o $f.o 2> $f.ptxas.log || { cat $f.ptxas.log; exit 1; }
   OBJS="$OBJS $f.o"
 done
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../librsb200.so $OBJS -cudart static
+# host-side PNG codec (plain C++ over zlib)
+${CXX:-g++} -O3 -std=c++17 -fPIC -I/usr/local/cuda/include -c rsb_png.cpp -o rsb_png.o
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../librsb200.so $OBJS rsb_png.o -cudart static -lz
 echo "built $(cd .. && pwd)/librsb200.so"

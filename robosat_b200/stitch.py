@@ -10,6 +10,7 @@ assembled by one kernel (`rsb_stitch_halo`) straight into the predictor's input 
 canvas, 9x fewer decodes, and the (S+2o)^2 buffered images never cross PCIe.
 """
 
+import os
 from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
@@ -27,8 +28,22 @@ def neighbour_keys(tile):
     return [Tile(x=int(tile.x) + dx, y=int(tile.y) + dy, z=int(tile.z)) for dx, dy in NEIGHBOURS]
 
 
+NATIVE_PNG = os.environ.get("RSB_PNG_DECODER", "native") != "pil"
+
+
 def decode_rgb(path, size):
-    """`Image.open(path).convert("RGB")` as uint8 [S, S, 3] (robosat/tiles.py:150-159, 181)."""
+    """`Image.open(path).convert("RGB")` as uint8 [S, S, 3] (robosat/tiles.py:150-159, 181).
+
+    8-bit PNG tiles go through the library's own decoder (`rsb_png_read_rgb`: file read + inflate + unfilter in C, no
+    interpreter lock held, so the pool threads decode in parallel); every other format (JPEG, WebP, 16-bit / interlaced PNG)
+    is PIL's job exactly as in the reference."""
+    if NATIVE_PNG and path.lower().endswith(".png"):
+        arr = np.empty((size, size, 3), dtype=np.uint8)
+        rc = _lib.load().rsb_png_read_rgb(os.fsencode(path), arr.ctypes.data, size, size)
+        if rc == 0:
+            return arr
+        if rc != _lib.RSB_E_UNSUPPORTED:
+            raise _lib.RsbError("decoding %s failed: %s" % (path, _lib.last_error()))
     arr = np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
     assert arr.shape == (size, size, 3), "tile %s is %s, expected %dx%d" % (path, arr.shape, size, size)
     return arr

@@ -38,12 +38,30 @@ def add_parser(subparser):
     parser.set_defaults(func=main)
 
 
+NATIVE_PNG = os.environ.get("RSB_PNG_ENCODER", "native") != "pil"
+_PALETTE_BYTES = {}
+
+
 def _save_png(root, palette, x, y, z, quantized, stats=None):
+    """probs/z/x/y.png: P-mode PNG with the 256-entry palette (predict.py:105-113). Default: the library's encoder
+    (`rsb_png_write_p8`, zlib level 6, no interpreter lock held -> the pool threads encode in parallel); pixel content and palette
+    are identical to the reference's file, the compressed bytes are not. RSB_PNG_ENCODER=pil writes through PIL with
+    optimize=True exactly like the reference."""
     t0 = time.perf_counter()
-    out = Image.fromarray(quantized, mode="P")
-    out.putpalette(palette)
     os.makedirs(os.path.join(root, str(z), str(x)), exist_ok=True)
-    out.save(os.path.join(root, str(z), str(x), str(y) + ".png"), optimize=True)
+    path = os.path.join(root, str(z), str(x), str(y) + ".png")
+    if NATIVE_PNG:
+        from robosat_b200 import _lib
+
+        pal = _PALETTE_BYTES.get(id(palette))
+        if pal is None:
+            pal = _PALETTE_BYTES.setdefault(id(palette), bytes(palette[:768]))
+        q = quantized if quantized.flags["C_CONTIGUOUS"] else quantized.copy()
+        _lib.check(_lib.load().rsb_png_write_p8(os.fsencode(path), q.ctypes.data, q.shape[1], q.shape[0], pal, len(pal) // 3, 6), "rsb_png_write_p8")
+    else:
+        out = Image.fromarray(quantized, mode="P")
+        out.putpalette(palette)
+        out.save(path, optimize=True)
     if stats is not None:
         stats["png_cpu_s"] = stats.get("png_cpu_s", 0.0) + (time.perf_counter() - t0)  # summed over pool threads (GIL-protected add)
 
