@@ -12,6 +12,7 @@ Bottleneck stack it calls), ConvRelu robosat/unet.py:44, DecoderBlock robosat/un
 """
 
 import ctypes
+import math
 import os
 from collections import OrderedDict
 
@@ -52,7 +53,7 @@ def split_fp16(w):
     2^e moves the largest |w| into [2^13, 2^14) so the lo parts (2^-11 of their hi) of all but vanishing weights are normal
     fp16 numbers; the kernel multiplies the fp32 accumulator by acc_scale = 2^-e (exact)."""
     m = float(w.abs().max())
-    e = 0 if m == 0.0 else 13 - int(torch.floor(torch.log2(torch.tensor(m, dtype=torch.float64))))
+    e = 0 if m == 0.0 else 13 - int(math.floor(math.log2(m)))
     ws = w.double() * (2.0 ** e)
     hi = ws.to(torch.float16)
     lo = (ws - hi.double()).to(torch.float16)
@@ -79,7 +80,7 @@ def pack_upsample_phases(w):
             taps = []
             for th in (0, 1):
                 for tw in (0, 1):
-                    acc = torch.zeros(co, ci, dtype=w.dtype)
+                    acc = torch.zeros(co, ci, dtype=w.dtype, device=w.device)
                     for kh in groups[a][th]:
                         for kw in groups[b][tw]:
                             acc += w[:, :, kh, kw]
@@ -94,7 +95,7 @@ def pack_stem(w):
     Input row 2*o + kh - 3 = 2*(o + t - 2) + ph with kh + 1 = 2*t + ph; the s2d channel is (ph*2+pw)*3 + c.
     """
     co = w.shape[0]
-    out = torch.zeros(co, 4, 4, 16, dtype=w.dtype)
+    out = torch.zeros(co, 4, 4, 16, dtype=w.dtype, device=w.device)
     for t in range(4):
         for ph in range(2):
             kh = 2 * t + ph - 1
@@ -112,7 +113,7 @@ def pack_stem(w):
 def pack_window3(w):
     """3x3 conv on 32 channels read as 3 row-taps of a 4-pixel window (4th pixel weight zero): K = 3*128."""
     co, ci, _, _ = w.shape
-    out = torch.zeros(co, 3, 4, ci, dtype=w.dtype)
+    out = torch.zeros(co, 3, 4, ci, dtype=w.dtype, device=w.device)
     out[:, :, :3, :] = w.permute(0, 2, 3, 1)
     return out.reshape(co, 3 * 4 * ci).contiguous()
 
@@ -351,8 +352,12 @@ class UNetEngine:
         self.ops = []  # ("conv", ConvOp) | ("prepass",) | ("maxpool", src, dst, N, H, W, C, k, s, p)
         self.feats = OrderedDict()  # name -> (tensor, (N, H, W, C) logical view) for layer-wise checks
         self._keep = []
-        # packing runs on the host: accept state_dicts living on any device (e.g. straight out of the NCCL broadcast)
-        self._build({k: v.detach().cpu() for k, v in _strip(state_dict).items()})
+        # Weight preparation (BN folding in float64, tap pre-summing, hi/lo split, packing) is a one-off setup step made of a few
+        # hundred small tensor ops over 39 M weights: it runs on the plan's device (under torchrun the host has
+        # OMP_NUM_THREADS=1, where the same ops took 17 s per plan), on the host only for the GPU-less plan_only mode.
+        # state_dicts may live on any device (e.g. straight out of the NCCL broadcast).
+        where = torch.device("cpu") if plan_only else self.device
+        self._build({k: v.detach().to(where) for k, v in _strip(state_dict).items()})
 
     # ---------------------------------------------------------------- helpers
     def _buf(self, *shape, dtype=torch.float16):

@@ -16,7 +16,7 @@ def norm(name):
     args = [a.strip() for a in m.group(2).split(",")]
     conv = {"true": "1", "false": "0"}
     args = [conv.get(a, a) for a in args]
-    keep = 4 if m.group(1) == "conv_tc_kernel" else 3
+    keep = 5 if m.group(1) == "conv_tc_kernel" else 3
     return "%s<%s>" % (m.group(1), ",".join(args[:keep]))
 
 
@@ -36,7 +36,8 @@ def main():
 
     names = open(order).read().split("LAUNCH_ORDER ")[-1].strip().split(",")
     agg = {}
-    md = ["# Round 1 — one predict step under `ncu --set full --clock-control none` (batch 32 x 3x512x512), per launch", "",
+    title = sys.argv[5] if len(sys.argv) > 5 else "one predict step"
+    md = ["# %s under `ncu --set full --clock-control none` (batch 32 x 3x512x512), per launch" % title, "",
           "Cold-cache, serialised launches: use the shares and the per-launch counters, not the absolute times (bench.py times the real step).", "",
           "| # | layer | kernel | us | tensor pipe % | DRAM MB (r+w) | L2->SM GB (TMA) | DRAM % |", "|---|---|---|---|---|---|---|---|"]
     for i, r in enumerate(data):
