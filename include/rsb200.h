@@ -121,10 +121,20 @@ typedef struct rsb_conv_desc {
     int64_t out_plane;
     int64_t res_plane;
     float acc_scale;
+
+    /* K chunking (mode 0; meant for split precision with long K loops): the tensor core truncates its fp32 accumulator after
+     * every MMA, so a tile's K loop is cut into chunks of `kchunk` 64-element K blocks whose results the epilogue adds with
+     * round-to-nearest fp32 adds through `scratch` (>= grid x 128 x block_n x 4 bytes, see rsb_conv_scratch_bytes; private to
+     * the launch, reusable by the next launch on the same stream). 0: no chunking. */
+    int32_t kchunk;
+    float* scratch;
+    int64_t scratch_bytes;
 } rsb_conv_desc;
 
 typedef struct rsb_conv_plan rsb_conv_plan;
 
+/* upper bound of the scratch a chunked plan with this block_n needs on the current device (SMs x 128 x block_n x 4 bytes) */
+int64_t rsb_conv_scratch_bytes(int32_t block_n);
 int rsb_conv_plan_create(const rsb_conv_desc* desc, rsb_conv_plan** out_plan);
 void rsb_conv_plan_destroy(rsb_conv_plan* plan);
 /* number of CTAs / tiles the plan launches (for tests and occupancy accounting) */
@@ -260,6 +270,13 @@ int rsb_metrics_count(const float* logits, const int64_t* targets, int64_t* coun
  * betas (b1,b2), eps, no weight decay, no amsgrad; `step` is the 1-based step count for bias correction. */
 int rsb_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float b1,
                   float b2, float eps, int32_t step, void* stream);
+
+/* Same update behind an overflow guard for mixed-precision training (no host synchronisation): if `grad` holds an inf / NaN the
+ * whole step is skipped on the device (parameters and moments untouched). guard_state: int32[4] on the device, zero-initialised by
+ * the caller once -- [0] scratch flag, [1] steps skipped so far (bias corrections use step - skipped), [2] flag of the last
+ * finished step (poll it to adapt the loss scale), [3] steps seen. With no skipped step the result equals rsb_adam_step bit for bit. */
+int rsb_adam_step_guarded(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float b1,
+                          float b2, float eps, int32_t step, int32_t* guard_state, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Training path (robosat/tools/train.py:163-201: net.train() forward, loss.backward()). Activations and activation

@@ -72,6 +72,9 @@ class ConvDesc(ctypes.Structure):
         ("out_plane", ctypes.c_int64),
         ("res_plane", ctypes.c_int64),
         ("acc_scale", ctypes.c_float),
+        ("kchunk", ctypes.c_int32),
+        ("scratch", ctypes.c_void_p),
+        ("scratch_bytes", ctypes.c_int64),
     ]
 
 
@@ -114,6 +117,7 @@ SIGNATURES = {
     "rsb_abi_layout": (None, [ctypes.POINTER(_i32)]),
     "rsb_last_error": (ctypes.c_char_p, []),
     "rsb_device_ok": (ctypes.c_int, []),
+    "rsb_conv_scratch_bytes": (_i64, [_i32]),
     "rsb_conv_plan_create": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(_vp)]),
     "rsb_conv_plan_destroy": (None, [_vp]),
     "rsb_conv_plan_info": (ctypes.c_int, [_vp] + [ctypes.POINTER(_i32)] * 4),
@@ -144,6 +148,7 @@ SIGNATURES = {
     "rsb_lovasz": (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _i32, _i32, _vp]),
     "rsb_metrics_count": (ctypes.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "rsb_adam_step": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp]),
+    "rsb_adam_step_guarded": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
     "rsb_bn_stats": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "rsb_bn_stats_finalize": (ctypes.c_int, [_vp] * 11 + [_i64, _i32, _f32, _f32, _vp]),
     "rsb_bn_finalize": (ctypes.c_int, [_vp] * 10 + [_i32, _i64, _f32, _f32, _vp]),

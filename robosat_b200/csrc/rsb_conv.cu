@@ -56,6 +56,12 @@ struct alignas(64) ConvKParams {
     const float* head_b;
     float* head_out;
     float acc_scale;
+    // K chunking (strict precision, long K loops): the tensor core truncates its fp32 accumulator after every MMA, a bias
+    // that grows with the number of accumulated MMAs. A tile's K loop is therefore cut into chunks of `kchunk` K blocks; each
+    // chunk accumulates in its own tensor-memory stage and the epilogue warps add the chunk results with round-to-nearest fp32
+    // adds, parked in a per-CTA scratch tile between chunks (thread-private addresses, L2 resident). 0 = one chunk.
+    int32_t kchunk;
+    float* scratch;  // [grid][128][BLOCK_N] fp32
 };
 
 // TWO: the tile is computed by a CTA pair (cluster of 2, tcgen05 cta_group::2): rank r owns 128 of the pair's 256 tile
@@ -63,8 +69,15 @@ struct alignas(64) ConvKParams {
 // 16 KB + BLOCK_N*64 B of shared memory per K block instead of 16 KB + BLOCK_N*128 B.
 // SPLIT: strict precision. Every operand is a (hi, lo) pair of fp16 planes; a pipeline stage holds both planes of the A box
 // and of the weight tile (one rank-5 / rank-3 TMA box each) and every K step issues three MMAs: hi*lo, lo*hi, hi*hi.
-template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO = false, bool SPLIT = false>
+// SPLIT == 2 (narrow tiles, BLOCK_N <= 64): the weight planes sit back to back in shared memory, so ONE MMA of width
+// 2*BLOCK_N computes A_hi x [W_hi | W_lo] into [main | cross] accumulator columns and a second one of width BLOCK_N adds
+// A_lo x W_hi onto the cross columns: two MMAs per K step instead of three (an M128 MMA costs the same ~66 cycles for any
+// N <= 128: it is bound by the shared-memory read of the A operand), and the small cross terms no longer share -- and
+// truncate -- the main accumulator. The epilogue adds main + cross in fp32.
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO = false, int SPLIT = 0>
 struct ConvCfg {
+    static_assert(SPLIT != 2 || (BLOCK_N <= 64 && !TWO), "the N-concatenated split schedule is for narrow single-CTA tiles");
+    static constexpr int kAccCols = SPLIT == 2 ? 2 * BLOCK_N : BLOCK_N;  // tensor-memory columns of one accumulator stage
     static constexpr int kPlanes = SPLIT ? 2 : 1;
     static constexpr int kBRows = TWO ? BLOCK_N / 2 : BLOCK_N;
     static constexpr int kBBytes = kBRows * kBlockK * 2;                 // one plane
@@ -93,7 +106,7 @@ struct ConvCfg {
     static constexpr int kAvail = kMaxSmem - 1024 - kBarBytes - kEpiBytes;
     static constexpr int kStages = (kAvail / kStageBytes) > 8 ? 8 : (kAvail / kStageBytes);
     static_assert(kStages >= 2, "pipeline too shallow");
-    static constexpr int kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+    static constexpr int kTmemCols = (2 * kAccCols <= 32) ? 32 : (2 * kAccCols <= 64 ? 64 : (2 * kAccCols <= 128 ? 128 : (2 * kAccCols <= 256 ? 256 : 512)));
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024;
 };
 
@@ -126,7 +139,7 @@ __device__ __forceinline__ int item_tile(const ConvKParams& p, int it, int rank)
     return ((it / per) * 2 + rank) * per + it % per;
 }
 
-template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, bool SPLIT>
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, int SPLIT>
 __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::kThreads), 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
     using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>;
     const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
@@ -235,6 +248,7 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::
         // ------------------------------------------------------------------ MMA issuer
         if (rank == 0 && elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(TWO ? 2 * kBlockM : kBlockM, BLOCK_N);
+            constexpr uint32_t idesc2 = make_idesc_f16(kBlockM, 2 * BLOCK_N);  // SPLIT == 2: [W_hi | W_lo] in one MMA
             // operand descriptors of stage 0; stage s adds its byte offset >> 4 to the 14-bit start-address field
             const uint64_t da0 = make_sw128_kmajor_desc(smem_u32(smem_a));
             const uint64_t db0 = make_sw128_kmajor_desc(smem_u32(smem_b));
@@ -242,11 +256,14 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
+            const int kchunk = p.kchunk > 0 ? p.kchunk : p.kblocks;
             for (int it = item0; it < num_items; it += item_step) {
+              for (int kb0 = 0; kb0 < p.kblocks; kb0 += kchunk) {
                 mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-                for (int kb = 0; kb < p.kblocks; ++kb) {
+                const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
+                const int kb1 = kb0 + kchunk < p.kblocks ? kb0 + kchunk : p.kblocks;
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint64_t da = da0 + static_cast<uint64_t>(stage * (Cfg::kStageA >> 4));
@@ -254,8 +271,12 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // advance 16 fp16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
-                        const uint32_t first = (kb | k) != 0 ? 1u : 0u;
-                        if constexpr (SPLIT) {
+                        const uint32_t first = ((kb - kb0) | k) != 0 ? 1u : 0u;
+                        if constexpr (SPLIT == 2) {
+                            // columns [0, N) = A_hi W_hi, columns [N, 2N) = A_hi W_lo + A_lo W_hi
+                            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc2, first);
+                            umma_f16(d_tmem + BLOCK_N, da + (kABytes >> 4) + 2 * k, db + 2 * k, idesc, 1u);
+                        } else if constexpr (SPLIT == 1) {
                             // lo planes sit kABytes / kBBytes behind the hi planes; cross terms first (smallest magnitude)
                             const uint64_t dal = da + (kABytes >> 4), dbl = db + (Cfg::kBBytes >> 4);
                             if (TWO) {
@@ -280,13 +301,14 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::
                         phase ^= 1;
                     }
                 }
-                // accumulator complete -> epilogue
+                // accumulator (of this K chunk) complete -> epilogue
                 if (TWO) umma_commit_pair(&tmem_full_bar[acc]);
                 else umma_commit(&tmem_full_bar[acc]);
                 if (++acc == 2) {
                     acc = 0;
                     acc_phase ^= 1;
                 }
+              }
             }
         }
     } else {
@@ -339,9 +361,57 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::
             const TileCoord t = decode_tile(p, item_tile<TWO>(p, it, rank));
             const int w = t.w0 + tw, h = t.h0 + th, n = t.n0 + tn;
             const bool valid = (w < p.Wt) && (h < p.Ht) && (n < p.Nt);
+            // K chunking: every chunk but the last is added (fp32, round to nearest) into this thread's row of the CTA's scratch tile
+            const int nchunks = (MODE == 0 && p.kchunk > 0) ? (p.kblocks + p.kchunk - 1) / p.kchunk : 1;
+            float* srow = nullptr;
+            if (MODE == 0 && nchunks > 1) {
+                srow = p.scratch + (static_cast<size_t>(blockIdx.x) * kBlockM + row) * BLOCK_N;
+                for (int ch = 0; ch + 1 < nchunks; ++ch) {
+                    mbar_wait(&tmem_full_bar[acc], acc_phase);
+                    tc_fence_after();
+                    const uint32_t ta = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::kAccCols;
+                    // same column ownership as the final pass below: a thread only ever re-reads what it wrote itself
+#pragma unroll 1
+                    for (int cc = chunk0 * (Cfg::kChunk / 32); cc < BLOCK_N / 32; cc += ((cc + 1) % (Cfg::kChunk / 32) == 0) ? (Cfg::kChunkStride - 1) * (Cfg::kChunk / 32) + 1 : 1) {
+                        const int c = cc * 32;
+                        uint32_t r[32];
+                        tmem_ld_32x32(ta + c, r);
+                        if constexpr (SPLIT == 2) {
+                            uint32_t x[32];
+                            tmem_ld_32x32(ta + BLOCK_N + c, x);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(x[j]));
+                        } else {
+                            tmem_ld_wait();
+                        }
+                        float4* sp = reinterpret_cast<float4*>(srow + c);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float4 v4 = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                                    __uint_as_float(r[4 * j + 3]));
+                            if (ch > 0) {
+                                const float4 o = sp[j];
+                                v4.x += o.x;
+                                v4.y += o.y;
+                                v4.z += o.z;
+                                v4.w += o.w;
+                            }
+                            sp[j] = v4;
+                        }
+                    }
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) release_acc(acc);
+                    if (++acc == 2) {
+                        acc = 0;
+                        acc_phase ^= 1;
+                    }
+                }
+            }
             mbar_wait(&tmem_full_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::kAccCols;
 
             if constexpr (MODE == 0) {
                 const float* bptr = p.bias ? p.bias + t.n_blk * BLOCK_N : nullptr;
@@ -360,7 +430,26 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::
                         const int c = ck * Cfg::kChunk + half * 32;
                         uint32_t r[32];
                         tmem_ld_32x32(taddr + c, r);
-                        tmem_ld_wait();
+                        if constexpr (SPLIT == 2) {
+                            uint32_t x[32];
+                            tmem_ld_32x32(taddr + BLOCK_N + c, x);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(x[j]));
+                        } else {
+                            tmem_ld_wait();
+                        }
+                        if (srow != nullptr) {
+                            const float4* sp = reinterpret_cast<const float4*>(srow + c);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 o = sp[j];
+                                r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + o.x);
+                                r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + o.y);
+                                r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + o.z);
+                                r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + o.w);
+                            }
+                        }
                         if (ck + Cfg::kChunkStride >= Cfg::kNumChunks && half == Cfg::kChunk / 32 - 1) {
                             // accumulator fully drained into registers: hand the TMEM stage back to the MMA warp
                             tc_fence_before();
@@ -447,7 +536,15 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::
                 static_assert(MODE == 0 || BLOCK_N == 32, "head mode needs BLOCK_N == 32");
                 uint32_t r[32];
                 tmem_ld_32x32(taddr, r);
-                tmem_ld_wait();
+                if constexpr (SPLIT == 2) {
+                    uint32_t x[32];
+                    tmem_ld_32x32(taddr + BLOCK_N, x);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(x[j]));
+                } else {
+                    tmem_ld_wait();
+                }
                 float v[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -632,7 +729,7 @@ static int current_device() {
     return dev;
 }
 
-template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, bool SPLIT>
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, int SPLIT>
 struct ConvInst {
     using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>;
     static constexpr int kSmem = Cfg::kSmemBytes;
@@ -707,7 +804,7 @@ struct ConvInst {
 // what to do with the instantiation a plan selects
 enum ConvAction { kLaunch, kSmemOf, kPairClusters };
 
-template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, bool SPLIT>
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, int SPLIT>
 static int conv_act(ConvAction a, const rsb_conv_plan* plan, cudaStream_t stream) {
     using I = ConvInst<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>;
     switch (a) {
@@ -717,26 +814,28 @@ static int conv_act(ConvAction a, const rsb_conv_plan* plan, cudaStream_t stream
     }
 }
 
-template <bool SPLIT>
+// SPLIT: 0 = fast; 1 = strict. Narrow strict tiles (block_n <= 64, never paired) take the N-concatenated schedule (2).
+template <int SPLIT>
 static int conv_dispatch(ConvAction a, const rsb_conv_plan* plan, cudaStream_t stream) {
-    if (plan->mode == 1) return conv_act<32, 1, false, false, SPLIT>(a, plan, stream);
+    constexpr int NARROW = SPLIT ? 2 : 0;
+    if (plan->mode == 1) return conv_act<32, 1, false, false, NARROW>(a, plan, stream);
     if (plan->pair) {
         if (plan->block_n == 128) return plan->has_res ? conv_act<128, 0, true, true, SPLIT>(a, plan, stream) : conv_act<128, 0, false, true, SPLIT>(a, plan, stream);
         return plan->has_res ? conv_act<256, 0, true, true, SPLIT>(a, plan, stream) : conv_act<256, 0, false, true, SPLIT>(a, plan, stream);
     }
     if (plan->has_res) {
         switch (plan->block_n) {
-            case 32: return conv_act<32, 0, true, false, SPLIT>(a, plan, stream);
-            case 64: return conv_act<64, 0, true, false, SPLIT>(a, plan, stream);
+            case 32: return conv_act<32, 0, true, false, NARROW>(a, plan, stream);
+            case 64: return conv_act<64, 0, true, false, NARROW>(a, plan, stream);
             case 128: return conv_act<128, 0, true, false, SPLIT>(a, plan, stream);
             case 256:
-                if constexpr (!SPLIT) return conv_act<256, 0, true, false, false>(a, plan, stream);
+                if constexpr (!SPLIT) return conv_act<256, 0, true, false, 0>(a, plan, stream);
                 break;  // split + residual + 256 columns does not fit one SM (rejected by validate_desc)
         }
     } else {
         switch (plan->block_n) {
-            case 32: return conv_act<32, 0, false, false, SPLIT>(a, plan, stream);
-            case 64: return conv_act<64, 0, false, false, SPLIT>(a, plan, stream);
+            case 32: return conv_act<32, 0, false, false, NARROW>(a, plan, stream);
+            case 64: return conv_act<64, 0, false, false, NARROW>(a, plan, stream);
             case 128: return conv_act<128, 0, false, false, SPLIT>(a, plan, stream);
             case 256: return conv_act<256, 0, false, false, SPLIT>(a, plan, stream);
         }
@@ -745,7 +844,7 @@ static int conv_dispatch(ConvAction a, const rsb_conv_plan* plan, cudaStream_t s
 }
 
 static int conv_select(ConvAction a, const rsb_conv_plan* plan, cudaStream_t stream) {
-    return plan->split ? conv_dispatch<true>(a, plan, stream) : conv_dispatch<false>(a, plan, stream);
+    return plan->split ? conv_dispatch<1>(a, plan, stream) : conv_dispatch<0>(a, plan, stream);
 }
 
 extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_plan) {
@@ -869,6 +968,8 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
     kp.head_b = d->head_b;
     kp.head_out = d->head_out;
     kp.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
+    kp.kchunk = (d->kchunk > 0 && d->kchunk < kp.kblocks) ? d->kchunk : 0;
+    kp.scratch = d->scratch;
 
     plan->block_n = d->block_n;
     plan->mode = d->mode;
@@ -886,9 +987,19 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
         plan->grid = 2 * (kp.pair_tiles < clusters ? kp.pair_tiles : clusters);
     }
     plan->smem = conv_select(kSmemOf, plan, nullptr);
+    if (kp.kchunk > 0) {
+        const int64_t need = static_cast<int64_t>(plan->grid) * kBlockM * d->block_n * 4;
+        if (d->mode != 0 || !d->scratch || d->scratch_bytes < need || (reinterpret_cast<uintptr_t>(d->scratch) & 15)) {
+            delete plan;
+            return set_error(RSB_E_INVALID, "conv: kchunk needs mode 0 and a 16B-aligned scratch of >= %lld bytes (grid %d x 128 x block_n fp32)", (long long)need,
+                             plan->grid);
+        }
+    }
     *out_plan = plan;
     return RSB_OK;
 }
+
+extern "C" int64_t rsb_conv_scratch_bytes(int32_t block_n) { return static_cast<int64_t>(num_sms()) * kBlockM * block_n * 4; }
 
 extern "C" void rsb_conv_plan_destroy(rsb_conv_plan* plan) { delete plan; }
 

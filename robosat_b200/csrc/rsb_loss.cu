@@ -291,6 +291,51 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// Guarded variant (mixed-precision training): activation gradients are fp16 under a loss scale, so one overflowing batch puts
+// inf / NaN into the flat gradient arena -- and from there, permanently, into exp_avg, exp_avg_sq and the weights. The guard is
+// three launches on the same stream and no host synchronisation:
+//   state[0]  this step's "gradients are not finite" flag (set by grad_finite_kernel)
+//   state[1]  number of skipped steps so far (bias corrections use step - skipped, like a GradScaler-wrapped torch.optim.Adam)
+//   state[2]  flag of the most recent finished step (what the host polls, asynchronously, to adapt the loss scale)
+//   state[3]  steps seen
+__global__ void grad_finite_kernel(const float* __restrict__ g, int64_t n, int32_t* __restrict__ state) {
+    bool bad = false;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float x = g[i];
+        bad |= !(fabsf(x) <= 3.402823466e38f);  // inf or NaN
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(&state[0], 1);
+}
+
+__global__ void adam_guarded_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
+                                    float beta1, float beta2, float one_minus_beta1, float one_minus_beta2, float lr, float step_size_host,
+                                    float bc2_sqrt_host, float eps, int step, const int32_t* __restrict__ state) {
+    if (state[0]) return;  // skip the whole update: parameters and both moments stay untouched
+    float step_size = step_size_host, bc2_sqrt = bc2_sqrt_host;
+    if (state[1] > 0) {  // earlier steps were skipped: bias corrections count the steps actually taken
+        const int eff = step - state[1];
+        step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(beta1), eff)));
+        bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), eff)));
+    }
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float gi = g[i];
+        float mi = m[i], vi = v[i];
+        mi = mi + one_minus_beta1 * (gi - mi);
+        vi = vi * beta2 + one_minus_beta2 * (gi * gi);
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step_size * (mi / denom);
+        m[i] = mi;
+        v[i] = vi;
+    }
+}
+
+__global__ void adam_guard_bookkeep_kernel(int32_t* state) {
+    state[2] = state[0];
+    if (state[0]) state[1] += 1;
+    state[3] += 1;
+    state[0] = 0;
+}
+
 // =================================================================================================
 // LovaszLoss2d (losses.py:96-119): per image a descending sort of P = C*H*W margin errors, then the
 // Jaccard-gradient weights from two cumulative sums and dot(relu(errors_sorted), J).
@@ -655,6 +700,24 @@ extern "C" int rsb_adam_step(float* param, const float* grad, float* exp_avg, fl
                                                                                  step_size, bc2_sqrt, eps);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "adam launch");
+}
+
+extern "C" int rsb_adam_step_guarded(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float b1,
+                                     float b2, float eps, int32_t step, int32_t* guard_state, void* stream) {
+    if (!param || !grad || !exp_avg || !exp_avg_sq || n <= 0 || step < 1 || !guard_state) return set_error(RSB_E_INVALID, "adam_guarded: bad arguments");
+    const double bc1 = 1.0 - pow(static_cast<double>(b1), step);
+    const double bc2 = 1.0 - pow(static_cast<double>(b2), step);
+    const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+    const float bc2_sqrt = static_cast<float>(sqrt(bc2));
+    const float omb1 = static_cast<float>(1.0 - static_cast<double>(b1));
+    const float omb2 = static_cast<float>(1.0 - static_cast<double>(b2));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    grad_finite_kernel<<<blocks_for(n, 256), 256, 0, st>>>(grad, n, guard_state);
+    adam_guarded_kernel<<<blocks_for(n, 256), 256, 0, st>>>(param, grad, exp_avg, exp_avg_sq, n, b1, b2, omb1, omb2, lr, step_size, bc2_sqrt, eps, step,
+                                                            guard_state);
+    adam_guard_bookkeep_kernel<<<1, 1, 0, st>>>(guard_state);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "adam_guarded launch");
 }
 
 extern "C" int64_t rsb_lovasz_workspace_bytes(int32_t N, int32_t C, int32_t HW) {

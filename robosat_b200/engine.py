@@ -153,8 +153,9 @@ def choose_block_n(cout, m_tiles, phases, kblocks=8, sms=148, split=False):
 
     def cost(bn):
         tiles = m_tiles * phases * (cout // bn)
-        if split:  # three MMAs per K step, always the 4-warp epilogue
-            per_tile = max(kblocks * 12 * max(66, bn // 2), bn * 28) + 300
+        if split:  # three MMAs per K step (two for the N-concatenated narrow tiles), always the 4-warp epilogue
+            mma = 8 * 66 if bn <= 64 else 12 * max(66, bn // 2)
+            per_tile = max(kblocks * mma, bn * 28) + 300
         else:
             per_tile = max(kblocks * 4 * max(66, bn // 2), bn * (16 if bn >= 128 else 28)) + 300
         return -(-tiles // sms) * per_tile
@@ -257,7 +258,7 @@ def _src_parity(t, N, H, W, C, ph, pw, plane=0):
 
 def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out_pitches, out_scale=(1, 1),
                    residual=None, relu=True, block_n=None, head=None, out_offset_elems=0, cta_pair=None,
-                   split=False, acc_scale=1.0, out_plane=0, res_plane=0):
+                   split=False, acc_scale=1.0, out_plane=0, res_plane=0, scratch=None):
     """Fill an `rsb_conv_desc`. tile_space = (Wt, Ht, Nt); out_pitches = (pitch_w, pitch_h, pitch_n) in elements.
     split=True: strict precision -- weights fp16 [2][phases*Cout][K] (hi, lo planes), sources / out / residual carry
     plane strides, the accumulator is multiplied by acc_scale (see include/rsb200.h)."""
@@ -305,6 +306,17 @@ def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out
             else:
                 cta_pair = CTA_PAIR and m_tiles >= 2 and ((d.block_n == 256 and kblocks >= 6) or (d.block_n == 128 and kblocks >= 18))
         d.cta_pair = 1 if cta_pair else 0
+        if split and scratch is not None:
+            # long K loops are accumulated in chunks that the epilogue adds in round-to-nearest fp32 (the tensor core truncates
+            # its accumulator after every MMA: ~1.3e-8 relative per MMA, measured). Wide tiles chain 12 MMAs per K block on the
+            # main accumulator, the N-concatenated narrow tiles 4; chunks keep a chain at <= MAX_MMA_CHAIN MMAs.
+            kblocks = K // 64
+            per_kb = 12 if d.block_n >= 128 else 4
+            if MAX_MMA_CHAIN > 0 and kblocks * per_kb > 2 * MAX_MMA_CHAIN - MAX_MMA_CHAIN // 2:
+                nchunks = -(-kblocks * per_kb // MAX_MMA_CHAIN)
+                d.kchunk = -(-kblocks // nchunks)
+                d.scratch = scratch.data_ptr()
+                d.scratch_bytes = scratch.numel() * scratch.element_size()
     else:
         head_w, head_b, head_out, classes = head
         d.mode = 1
@@ -316,6 +328,7 @@ def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out
 
 
 PRECISIONS = ("strict", "fast")
+MAX_MMA_CHAIN = int(os.environ.get("RSB_MAX_MMA_CHAIN", "192"))  # 0 disables K chunking (A/B measurements)
 
 
 def default_precision():
@@ -384,6 +397,13 @@ class UNetEngine:
         hi, lo, scale = split_fp16(w)
         return self._dev(torch.stack([hi, lo]), torch.float16), scale
 
+    def _scratch(self):
+        """one fp32 scratch tile per SM for the K-chunked accumulation, shared by all layers (launches are stream ordered)"""
+        if getattr(self, "_scratch_buf", None) is None:
+            n = 148 * 128 * 256 if self.plan_only else int(_lib.load().rsb_conv_scratch_bytes(256)) // 4
+            self._scratch_buf = self._buf(n, dtype=torch.float32)
+        return self._scratch_buf
+
     def _dense(self, t, N, H, W, C):
         return _src_dense(t, N, H, W, C, self._plane(t))
 
@@ -395,7 +415,8 @@ class UNetEngine:
         bd = self._dev(b, torch.float32) if b is not None else None
         desc = make_conv_desc(srcs, segs, wd, bd, cout, phases, tile_space, out, out_pitches, residual=residual,
                               split=self.strict, acc_scale=scale, out_plane=self._plane(out) if out is not None else 0,
-                              res_plane=self._plane(residual) if residual is not None else 0, **kw)
+                              res_plane=self._plane(residual) if residual is not None else 0,
+                              scratch=self._scratch() if self.strict else None, **kw)
         op = ConvOp(name, desc, (wd, bd), create_plan=not self.plan_only)
         self.ops.append(("conv", op))
         return op

@@ -13,7 +13,9 @@ from robosat_b200 import _lib
 
 
 class Adam(torch.optim.Optimizer):
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, guard=True):
+        """guard=True (default): a step whose gradients contain inf / NaN (an fp16 activation-gradient overflow under the loss
+        scale) is skipped on the device -- weights and moments stay untouched -- and counted; `LossScaler` halves the scale."""
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False)
         super().__init__(params, defaults)
         ps = [p for g in self.param_groups for p in g["params"]]
@@ -36,6 +38,7 @@ class Adam(torch.optim.Optimizer):
         self._params = ps
         self._touched = [False] * len(ps)
         self._step = 0
+        self._guard = torch.zeros(4, dtype=torch.int32, device=dev) if guard else None
 
     @property
     def flat_grad(self):
@@ -53,9 +56,23 @@ class Adam(torch.optim.Optimizer):
         assert closure is None
         self._step += 1
         g = self.param_groups[0]
+        if self._guard is not None:
+            _lib.check(_lib.load().rsb_adam_step_guarded(self._flat_p.data_ptr(), self._flat_g.data_ptr(), self._flat_m.data_ptr(),
+                                                         self._flat_v.data_ptr(), self._flat_p.numel(), g["lr"], g["betas"][0], g["betas"][1], g["eps"],
+                                                         self._step, self._guard.data_ptr(), _lib.current_stream_ptr()), "rsb_adam_step_guarded")
+            return
         _lib.check(_lib.load().rsb_adam_step(self._flat_p.data_ptr(), self._flat_g.data_ptr(), self._flat_m.data_ptr(), self._flat_v.data_ptr(),
                                              self._flat_p.numel(), g["lr"], g["betas"][0], g["betas"][1], g["eps"], self._step,
                                              _lib.current_stream_ptr()), "rsb_adam_step")
+
+    @property
+    def guard_state(self):
+        """device int32[4]: [scratch flag, steps skipped, overflow flag of the last finished step, steps seen] (None without guard)"""
+        return self._guard
+
+    def skipped_steps(self):
+        """number of steps skipped because of non-finite gradients (synchronises; for logging / tests)"""
+        return 0 if self._guard is None else int(self._guard[1].item())
 
     def mark_used(self, mask):
         """mask[i] = parameter i takes part in the graph (gets gradients); others keep no optimiser state, like torch."""
@@ -82,3 +99,51 @@ class Adam(torch.optim.Optimizer):
             for key in ("lr", "betas", "eps"):
                 if key in saved:
                     g[key] = tuple(saved[key]) if key == "betas" else saved[key]
+
+
+class LossScaler:
+    """Dynamic loss scale for the fp16 activation gradients of `robosat_b200.UNet` in training mode (the reference trains in fp32
+    and needs none; train.py:179-188). The overflow decision itself is taken on the device by the guarded Adam step; this class
+    only ADAPTS the scale, reading the device flag through an asynchronous copy one step late -- no synchronisation on the
+    training stream. Overflow -> scale / 2 (never below `min_scale`); `growth_interval` clean steps -> scale * 2 (capped)."""
+
+    def __init__(self, net, optimizer, init_scale=4096.0, growth_interval=1000, min_scale=1.0, max_scale=65536.0):
+        self.net = net.module if hasattr(net, "module") else net
+        self.opt = optimizer
+        self.scale, self.growth_interval, self.min_scale, self.max_scale = float(init_scale), growth_interval, min_scale, max_scale
+        self._clean = 0
+        self._host = torch.zeros(4, dtype=torch.int32, pin_memory=True)
+        self._event = None
+        self._seen = 0
+        self.overflows = 0
+        self._apply()
+
+    def _apply(self):
+        self.net.loss_scale = self.scale
+        for eng in getattr(self.net, "_train_engines", {}).values():
+            eng.loss_scale = self.scale
+
+    def update(self):
+        """call once per training step, after optimizer.step()"""
+        if self.opt.guard_state is None:
+            return
+        if self._event is not None and self._event.query():
+            steps, flag = int(self._host[3]), int(self._host[2])
+            if steps > self._seen:  # a finished step we have not accounted for yet
+                self._seen = steps
+                if flag:
+                    self.overflows += 1
+                    self._clean = 0
+                    self.scale = max(self.min_scale, self.scale * 0.5)
+                    self._apply()
+                else:
+                    self._clean += 1
+                    if self._clean >= self.growth_interval and self.scale < self.max_scale:
+                        self._clean = 0
+                        self.scale = min(self.max_scale, self.scale * 2.0)
+                        self._apply()
+            self._event = None
+        if self._event is None:
+            self._host.copy_(self.opt.guard_state, non_blocking=True)
+            self._event = torch.cuda.Event()
+            self._event.record()

@@ -24,7 +24,7 @@ from robosat_b200.datasets import SlippyMapTilesConcatenation
 from robosat_b200.log import Log
 from robosat_b200.losses import CrossEntropyLoss2d, FocalLoss2d, LovaszLoss2d, mIoULoss2d
 from robosat_b200.metrics import Metrics
-from robosat_b200.optim import Adam
+from robosat_b200.optim import Adam, LossScaler
 from robosat_b200.transforms import (ConvertImageMode, ImageToTensor, JointCompose, JointRandomHorizontalFlip, JointRandomRotation,
                                      JointTransform, MaskToTensor)
 from robosat_b200.unet import UNet
@@ -114,7 +114,7 @@ def get_dataset_loaders(model, dataset, workers, rank=0, world=1):
     return train_loader, val_loader
 
 
-def _epoch(loader, num_classes, device, net, criterion, optimizer=None, world=1):
+def _epoch(loader, num_classes, device, net, criterion, optimizer=None, world=1, scaler=None):
     """One pass of train() (train.py:163-201) or validate() (train.py:204-238): same bookkeeping, batched metrics."""
     from robosat_b200.dist import allreduce_sum_
 
@@ -139,7 +139,9 @@ def _epoch(loader, num_classes, device, net, criterion, optimizer=None, world=1)
         if training:
             (loss / world if world > 1 else loss).backward()
             allreduce_sum_(optimizer.flat_grad, world)  # no-op on one GPU
-            optimizer.step()
+            optimizer.step()  # skipped on the device if the (summed) gradients are not finite: every rank takes the same decision
+            if scaler is not None:
+                scaler.update()
         running_loss += loss.detach()  # stays on the device: one read-back per epoch instead of one per batch
         metrics.add_batch(masks, outputs.detach())
     if world > 1:
@@ -201,6 +203,7 @@ def _run(rank, world, args, port):
 
     optimizer = Adam(net.parameters(), lr=model["opt"]["lr"])
     optimizer.mark_used([not n.startswith("module.resnet.fc.") for n, _ in net.named_parameters()])
+    scaler = LossScaler(net, optimizer)
 
     resume = 0
     if args.checkpoint:
@@ -252,7 +255,9 @@ def _run(rank, world, args, port):
         log.log("Epoch: {}/{}".format(epoch + 1, num_epochs))
         if world > 1:
             train_loader.sampler.set_epoch(epoch)
-        train_hist = _epoch(train_loader, num_classes, device, net, criterion, optimizer, world=world)
+        train_hist = _epoch(train_loader, num_classes, device, net, criterion, optimizer, world=world, scaler=scaler)
+        if scaler.overflows:
+            log.log("loss scale {:g} ({} overflow steps skipped so far)".format(scaler.scale, optimizer.skipped_steps()))
         log.log("Train    loss: {:.4f}, mIoU: {:.3f}, {} IoU: {:.3f}, MCC: {:.3f}".format(
             train_hist["loss"], train_hist["miou"], fg, train_hist["fg_iou"], train_hist["mcc"]))
         for k, v in train_hist.items():

@@ -23,13 +23,16 @@ def norm(name):
 def main():
     raw, order, out_json, out_md = sys.argv[1:5]
     rows = list(csv.reader(open(raw)))
-    hdr, data = rows[0], rows[2:]
+    hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
+    # ncu scales the unit of every column to the capture (us / ms, Mbyte / Gbyte ...): bring everything to us and MB (GB for TMA)
+    SCALE = {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "s": 1e6, "second": 1e6,
+             "byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3, "Tbyte": 1e6}
 
     def col(r, key):
         for h in ([key] if key in idx else []) + [h for h in hdr if h.endswith("." + key)]:
             try:
-                return float(r[idx[h]].replace(",", ""))
+                return float(r[idx[h]].replace(",", "")) * SCALE.get(units[idx[h]], 1.0)
             except ValueError:
                 continue
         return 0.0
@@ -45,7 +48,7 @@ def main():
         us = col(r, "gpu__time_duration.sum")
         mb = col(r, "dram__bytes_read.sum") + col(r, "dram__bytes_write.sum")
         tens = col(r, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")
-        l2 = col(r, "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum")
+        l2 = col(r, "l1tex__m_xbar2l1tex_read_bytes_mem_global_op_tma_ld.sum") / 1e3  # MB -> GB
         dpct = col(r, "dram__bytes_read.sum.pct_of_peak_sustained_elapsed") + col(r, "dram__bytes_write.sum.pct_of_peak_sustained_elapsed")
         a = agg.setdefault(k, {"mb": 0.0, "launches": 0, "us_total": 0.0})
         a["mb"] += mb

@@ -57,6 +57,11 @@ def _plane(t, split):
     return t.numel() // 2 if split else 0
 
 
+def _scratch(device, split):
+    """fp32 scratch for the K-chunked accumulation of long strict-precision K loops (the plan decides whether it is used)"""
+    return torch.zeros(148 * 128 * 256, dtype=torch.float32, device=device) if split else None
+
+
 class Case:
     def __init__(self, name, desc, keep, out, out_view, ref):
         self.name, self.desc, self.keep, self.out, self.out_view, self.ref = name, desc, keep, out, out_view, ref
@@ -90,6 +95,7 @@ def conv_case(kind, N, H, W, cin, cout, device, seed=0, residual=False, relu=Tru
     if residual:
         resd, res = _act_in(res, device, split)
     pl = _plane(xd, split)
+    scr = _scratch(device, split)
     if stride == 1:
         srcs = [E._src_dense(xd, N, H, W, cin, pl)]
         segs = [(0, kh - k // 2, kw - k // 2, cin // 64) for kh in range(k) for kw in range(k)]
@@ -105,7 +111,7 @@ def conv_case(kind, N, H, W, cin, cout, device, seed=0, residual=False, relu=Tru
             srcs = srcs[:1]
     desc = E.make_conv_desc(srcs, segs, wp, bd, cout, 1, (oW, oH, N), out, (cout, oW * cout, oH * oW * cout),
                             residual=resd, relu=relu, block_n=block_n, split=split, acc_scale=scale, out_plane=_plane(out, split),
-                            res_plane=_plane(resd, split) if residual else 0, cta_pair=cta_pair)
+                            res_plane=_plane(resd, split) if residual else 0, cta_pair=cta_pair, scratch=scr)
 
     def ref():
         y = F.conv2d(x, w, b.to(x.dtype) if bias else None, stride=stride, padding=k // 2)
@@ -113,7 +119,7 @@ def conv_case(kind, N, H, W, cin, cout, device, seed=0, residual=False, relu=Tru
             y = y + res
         return (F.relu(y) if relu else y).float()
 
-    return Case("%s%s_%dx%dx%d_%d-%d" % ("split_" if split else "", kind, N, H, W, cin, cout), desc, (xd, wp, bd, resd), out,
+    return Case("%s%s_%dx%dx%d_%d-%d" % ("split_" if split else "", kind, N, H, W, cin, cout), desc, (xd, wp, bd, resd, scr), out,
                 lambda t: _out_nchw(t, (N, oH, oW, cout)), ref)
 
 
@@ -135,14 +141,16 @@ def decoder_case(N, lh, lw, cins, cout, device, seed=0, block_n=None, split=Fals
     out = torch.zeros(*((2,) if split else ()), N, oH, oW, cout, dtype=torch.float16, device=device)
     srcs = [E._src_dense(t, N, lh, lw, c, _plane(t, split)) for t, c in zip(xds, cins)]
     segs = [(si, th - 1, tw - 1, c // 64) for th in range(2) for tw in range(2) for si, c in enumerate(cins)]
+    scr = _scratch(device, split)
     desc = E.make_conv_desc(srcs, segs, wp, None, cout, 4, (lw, lh, N), out, (cout, oW * cout, oH * oW * cout),
-                            out_scale=(2, 2), block_n=block_n, split=split, acc_scale=scale, out_plane=_plane(out, split), cta_pair=cta_pair)
+                            out_scale=(2, 2), block_n=block_n, split=split, acc_scale=scale, out_plane=_plane(out, split), cta_pair=cta_pair,
+                            scratch=scr)
 
     def ref():
         up = F.interpolate(torch.cat(xs, dim=1), scale_factor=2, mode="nearest")
         return F.relu(F.conv2d(up, w, None, padding=1)).float()
 
-    return Case("%sdecoder_%dx%dx%d_%s-%d" % ("split_" if split else "", N, lh, lw, "+".join(map(str, cins)), cout), desc, (xds, wp), out,
+    return Case("%sdecoder_%dx%dx%d_%s-%d" % ("split_" if split else "", N, lh, lw, "+".join(map(str, cins)), cout), desc, (xds, wp, scr), out,
                 lambda t: _out_nchw(t, (N, oH, oW, cout)), ref)
 
 
@@ -254,7 +262,9 @@ def split_cases(device):
         lambda: decoder_case(2, 8, 8, [128, 64], 64, device, seed=8, split=True),
         lambda: decoder_case(1, 16, 16, [128], 32, device, seed=9, split=True),
         lambda: decoder_case(3, 4, 4, [256, 256], 256, device, seed=10, block_n=128, split=True),
-        lambda: decoder_case(2, 4, 4, [2048, 256], 256, device, seed=15, split=True),     # dec0's K = 9216 per phase: long accumulation
+        lambda: decoder_case(2, 4, 4, [2048, 256], 256, device, seed=15, split=True),     # dec0's K = 9216 per phase: 9 K chunks
+        lambda: decoder_case(2, 4, 4, [2048, 256], 256, device, seed=15, split=True, cta_pair=False, block_n=128),  # chunked, one CTA per tile
+        lambda: conv_case("3x3", 2, 16, 16, 256, 256, device, seed=16, split=True),       # layer3 conv2: 36 K blocks -> 3 chunks, several tiles per CTA
         lambda: stem_case(2, 64, 64, device, seed=11, split=True),
         lambda: head_case(2, 32, 32, 2, device, seed=12, split=True),
         lambda: head_case(1, 32, 64, 6, device, seed=13, split=True),

@@ -90,6 +90,62 @@ def test_adam_matches_reference_fixture(cuda_device):
         np.testing.assert_allclose(p.cpu().numpy(), gold["adam_p%d" % (s + 1)], rtol=3e-7, atol=1e-9)
 
 
+def test_guarded_adam_skips_non_finite_steps_and_equals_plain_adam_otherwise(cuda_device):
+    """rsb_adam_step_guarded: bit-identical to rsb_adam_step while gradients are finite; a step with an inf / NaN gradient leaves
+    parameters and moments untouched, is counted, and later bias corrections use the number of steps actually taken (what
+    torch.optim.Adam behind a GradScaler does)."""
+    lib = _lib.load()
+    gold = np.load(os.path.join(GOLD, "losses.npz"))
+    st = _lib.current_stream_ptr()
+    p = torch.from_numpy(gold["adam_p0"]).to(cuda_device)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    state = torch.zeros(4, dtype=torch.int32, device=cuda_device)
+    grads = [torch.from_numpy(gold["adam_grads"][s]).to(cuda_device) for s in range(3)]
+    bad = grads[1].clone()
+    bad[7] = float("inf")
+    seq = [grads[0], bad, grads[1], grads[2]]  # host step counter 1, 2, 3, 4; effective steps 1, -, 2, 3
+    expect = ["adam_p1", "adam_p1", "adam_p2", "adam_p3"]
+    for i, (g, key) in enumerate(zip(seq, expect)):
+        _lib.check(lib.rsb_adam_step_guarded(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 1e-4, 0.9, 0.999, 1e-8, i + 1,
+                                             state.data_ptr(), st), "adam_guarded")
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(p.cpu().numpy(), gold[key], rtol=3e-7, atol=1e-9)
+        assert state.cpu().tolist() == [0, 1 if i >= 1 else 0, 1 if i == 1 else 0, i + 1]
+    assert torch.isfinite(m).all() and torch.isfinite(v).all()
+
+
+def test_loss_scaler_halves_on_overflow(cuda_device):
+    from robosat_b200.optim import Adam, LossScaler
+
+    w = torch.nn.Parameter(torch.ones(1024, device=cuda_device))
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = w
+            self.loss_scale = 4096.0
+            self._train_engines = {}
+
+    net = Net()
+    opt = Adam(net.parameters(), lr=1e-2)
+    scaler = LossScaler(net, opt, init_scale=4096.0, growth_interval=3)
+    before = w.detach().clone()
+    opt.zero_grad()
+    w.grad.fill_(float("nan"))
+    opt.step()
+    scaler.update()
+    torch.cuda.synchronize()
+    assert torch.equal(w.detach(), before) and opt.skipped_steps() == 1
+    for _ in range(5):  # clean steps: the (one step late) reading first halves the scale, then grows it again after 3 clean steps
+        opt.zero_grad()
+        w.grad.fill_(0.5)
+        opt.step()
+        scaler.update()
+        torch.cuda.synchronize()
+    assert scaler.overflows == 1 and net.loss_scale in (2048.0, 4096.0)
+    assert not torch.equal(w.detach(), before)
+
+
 def test_head_quantize_matches_numpy_digitize(cuda_device):
     """predict.py:87-103 on identical logits: bins may differ by one only where expf rounding moves p across an anchor."""
     lib = _lib.load()

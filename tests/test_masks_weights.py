@@ -50,6 +50,25 @@ def test_softvote_bit_identical_to_numpy(cuda_device):
         assert np.array_equal(got, _softvote_reference(list(q), w)), (K, w)
 
 
+def test_softvote_restatement_is_pinned_to_the_real_reference():
+    """tests/golden/masks.npz holds masks written by the unmodified `robosat.tools.masks.main` (make_golden_masks.py); the numpy
+    restatement used by the GPU test above reproduces them exactly, so that test is pinned to the reference, not to this file."""
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "masks.npz"))
+    for ci in range(5):
+        w = list(gold["w%d" % ci]) or None
+        assert np.array_equal(_softvote_reference(list(gold["q%d" % ci]), w), gold["mask%d" % ci]), ci
+
+
+@pytest.mark.gpu
+def test_softvote_matches_reference_fixture(cuda_device):
+    """`rsb_softvote` against the masks the real reference tool produced from the same probability PNGs (bit-identical, ties included)"""
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "masks.npz"))
+    for ci in range(5):
+        w = list(gold["w%d" % ci]) or None
+        got = masks.softvote_device(torch.from_numpy(gold["q%d" % ci]).to(cuda_device), w).cpu().numpy()
+        assert np.array_equal(got, gold["mask%d" % ci]), ci
+
+
 @pytest.mark.gpu
 def test_class_histogram_matches_bincount(cuda_device):
     rng = np.random.RandomState(1)

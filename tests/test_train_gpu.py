@@ -323,3 +323,132 @@ def test_fused_grad_accumulation_matches_autograd_accumulate(cuda_device):
     crit(net(x), masks).backward()
     assert all(p.grad is not None for _, p in used)
     assert (dict(net.named_parameters())["final.weight"].grad - ref["final.weight"]).abs().max().item() <= 1e-4 * ref["final.weight"].abs().max().item()
+
+
+def test_train_backward_vs_plain_fp32_autograd(cuda_device):
+    """The honest number next to the mask-frozen check above: parameter gradients of ONE step against plain fp32 autograd of the
+    oracle (train-mode BatchNorm, its own ReLU masks and max-pool arg-maxes). The fp16 forward flips a small fraction of masks
+    relative to an fp32 run and every flip changes gradient elements by O(1), so this is looser by construction -- it is the
+    error any reduced-precision forward (fp16 / bf16 / TF32 autocast) shows against an fp32 run. Printed and bounded."""
+    C, B, S = 2, 2, 128
+    sd0, x, params, eng = _engine_pair(C, B, S, cuda_device)
+    g = torch.Generator().manual_seed(3)
+    dlogits = torch.randn((B, C, S, S), generator=g) * 1e-3
+    eng.forward(x.to(cuda_device))
+    grads = eng.backward(dlogits.to(cuda_device))
+    torch.cuda.synchronize()
+    sd = {k: v.clone() for k, v in sd0.items()}
+    for k, v in sd.items():
+        if v.dtype == torch.float32 and "running" not in k:
+            v.requires_grad_(True)
+    lo = unet_oracle.unet_forward_train(sd, x)
+    (lo * dlogits).sum().backward()
+    rels, dots, n1, n2 = {}, 0.0, 0.0, 0.0
+    for k, v in sd.items():
+        if v.requires_grad and not k.startswith("resnet.fc"):
+            a, b = grads[k].cpu().double(), v.grad.double()
+            rels[k] = _rel(a, b)
+            dots += float((a * b).sum())
+            n1 += float((a * a).sum())
+            n2 += float((b * b).sum())
+    cosine = dots / (n1 ** 0.5 * n2 ** 0.5)
+    vals = sorted(rels.values())
+    worst = sorted(rels.items(), key=lambda kv: -kv[1])[:3]
+    print("gradient vs plain fp32 autograd: median rel-L2 %.3f, 90th pct %.3f, worst %s, cosine of the full gradient %.5f" % (
+        vals[len(vals) // 2], vals[int(0.9 * len(vals))], worst, cosine))
+    assert len(rels) == 168
+    assert cosine >= 0.97 and vals[len(vals) // 2] <= 0.2 and vals[-1] <= 0.8
+
+
+def test_config5_six_class_train_step_256_and_plan_for_batch8_1024(cuda_device):
+    """BASELINE config 5 (6 classes, 3x1024x1024, batch 8 per GPU): a 6-class train step at 256^2 against the oracle's loss, and
+    the batch-8 1024^2 training plan builds, fits and runs forward + backward (finite gradients everywhere)."""
+    from oracle import losses_oracle
+    from robosat_b200.losses import LovaszLoss2d
+    from robosat_b200.optim import Adam
+    from robosat_b200.unet import UNet
+
+    sd = synth.make_state_dict(6, seed=0)
+    net = torch.nn.DataParallel(UNet(6, pretrained=False), device_ids=[0]).to(cuda_device)
+    net.load_state_dict(sd)
+    opt = Adam(net.parameters(), lr=1e-4)
+    opt.mark_used([not n.startswith("module.resnet.fc.") for n, _ in net.named_parameters()])
+    crit = LovaszLoss2d().to(cuda_device)
+    x = synth.normalize_tiles(synth.make_tiles_u8(2, 256, seed=1))
+    masks = synth.make_masks(2, 256, 6, seed=3)
+    net.train()
+    opt.zero_grad()
+    loss = crit(net(x.to(cuda_device)), masks.to(cuda_device))
+    loss.backward()
+    opt.step()
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref_logits = unet_oracle.unet_forward_train({k: v.clone() for k, v in sd.items()}, x)
+    ref_loss = float(losses_oracle.lovasz_loss(ref_logits, masks))
+    print("6-class 256^2 Lovasz loss %.5f (oracle %.5f), skipped steps %d" % (loss.item(), ref_loss, opt.skipped_steps()))
+    assert abs(loss.item() - ref_loss) <= 5e-3 * abs(ref_loss) and opt.skipped_steps() == 0
+    del net, opt
+    torch.cuda.empty_cache()
+    params = {k[7:]: v.clone().to(cuda_device) for k, v in sd.items()}
+    eng = UNetTrainEngine(params, 6, 8, 1024, 1024, device=cuda_device, loss_scale=4096.0)
+    xb = synth.normalize_tiles(synth.make_tiles_u8(8, 1024, seed=2)).to(cuda_device)
+    logits = eng.forward(xb)
+    dl = torch.randn_like(logits) * 1e-6
+    grads = eng.backward(dl)
+    torch.cuda.synchronize()
+    assert torch.isfinite(logits).all() and all(torch.isfinite(v).all() for v in grads.values())
+    assert torch.cuda.max_memory_allocated() < 170e9
+
+
+def test_train_forward_512_matches_oracle(cuda_device):
+    """512^2 train-mode forward (the BASELINE config 3 extent, batch 2 of its 16) against the oracle's train-mode forward"""
+    sd0, x, params, eng = _engine_pair(2, 2, 512, cuda_device)
+    logits = eng.forward(x.to(cuda_device)).float().cpu()
+    sd = {k: v.clone() for k, v in sd0.items()}
+    with torch.no_grad():
+        ref = unet_oracle.unet_forward_train(sd, x)
+    r = _rel(logits, ref)
+    print("train-mode forward 2x3x512x512: rel-L2 of logits %.2e" % r)
+    assert r < 5e-3
+
+
+def test_second_forward_before_backward_is_refused(cuda_device):
+    """the training plan keeps ONE set of saved activations per input shape. A backward through a graph whose buffers a
+    later forward overwrote, or a second backward through the same graph, must raise instead of returning wrong gradients."""
+    from robosat_b200.losses import CrossEntropyLoss2d
+    from robosat_b200.unet import UNet
+
+    net = UNet(2, pretrained=False).to(cuda_device)
+    net.load_state_dict({k[7:]: v for k, v in synth.make_state_dict(2, seed=0).items()})
+    net.train()
+    crit = CrossEntropyLoss2d().to(cuda_device)
+    x = synth.normalize_tiles(synth.make_tiles_u8(2, 64, seed=4)).to(cuda_device)
+    masks = synth.make_masks(2, 64, 2, seed=5).to(cuda_device)
+    l1 = crit(net(x), masks)
+    l2 = crit(net(x), masks)
+    with pytest.raises(RuntimeError, match="second train-mode forward"):
+        l1.backward()
+    l2.backward(retain_graph=True)  # the latest graph is fine ...
+    with pytest.raises(RuntimeError, match="ran twice"):
+        l2.backward()               # ... once
+
+
+def test_inference_plans_follow_weight_updates_through_dataparallel(cuda_device):
+    """loading a checkpoint through the nn.DataParallel wrapper (the reference's usage, predict.py:63-68) or editing
+    weights in place must invalidate the cached inference plans (they hold folded fp16 copies of the weights)."""
+    from robosat_b200.unet import UNet
+
+    sd_a, sd_b = synth.make_state_dict(2, seed=0), synth.make_state_dict(2, seed=5)
+    x = synth.normalize_tiles(synth.make_tiles_u8(1, 64, seed=1))
+    net = torch.nn.DataParallel(UNet(2, pretrained=False), device_ids=[0]).to(cuda_device)
+    net.load_state_dict(sd_a)
+    net.eval()
+    with torch.no_grad():
+        a = net(x.to(cuda_device)).cpu()
+        net.load_state_dict(sd_b)          # goes through _load_from_state_dict of the wrapped module: no override is reached
+        b = net(x.to(cuda_device)).cpu()
+        ref_a, ref_b = unet_oracle.unet_forward(sd_a, x), unet_oracle.unet_forward(sd_b, x)
+        assert _rel(a, ref_a) < 2e-4 and _rel(b, ref_b) < 2e-4 and _rel(b, ref_a) > 1e-2
+        net.module.final.bias.add_(1.0)    # in-place edit in eval mode
+        c = net(x.to(cuda_device)).cpu()
+    assert torch.allclose(c, b + 1.0, atol=1e-3)
