@@ -328,7 +328,9 @@ def make_conv_desc(srcs, segs, weights, bias, cout, phases, tile_space, out, out
 
 
 PRECISIONS = ("strict", "fast")
-MAX_MMA_CHAIN = int(os.environ.get("RSB_MAX_MMA_CHAIN", "192"))  # 0 disables K chunking (A/B measurements)
+# 400: measured trade-off on B200 -- every chunk boundary moves one 128 x block_n fp32 tile through L2 in each direction, which
+# costs the L2-bound long-K layers ~3 % per boundary; at 192 the step was 1.6 % slower for the same whole-network error.
+MAX_MMA_CHAIN = int(os.environ.get("RSB_MAX_MMA_CHAIN", "400"))  # 0 disables K chunking (A/B measurements)
 
 
 def default_precision():

@@ -131,8 +131,10 @@ def test_rectangular_and_overlap_sized_input(precision, cuda_device):
 @pytest.mark.parametrize("precision", ["strict", "fast"])
 def test_full_size_batch_properties_512(precision, cuda_device):
     """BASELINE config 2 shape (batch 32 of 3x512x512): size-independent properties instead of a CPU re-run.
-    (a) batch independence: tile i alone == tile i inside the batch, bit for bit;
-    (b) replay idempotence: the same input twice gives identical logits;
+    (a) replay idempotence: the same input twice gives identical logits, bit for bit;
+    (b) batch independence: tile i in a batch of 2 == tile i inside the batch of 32 -- bit for bit in the fast precision (one
+        accumulation chain per output whatever the tiling); in the strict precision the plan's tile width / K-chunk choice
+        depends on the batch size and changes the ORDER of the fp32 partial sums, so the two agree to fp32 round-off (1e-5 rel);
     (c) a 2-tile subset agrees with the oracle."""
     sd = synth.make_state_dict(2, seed=0)
     u8 = synth.make_tiles_u8(32, 512, seed=1)
@@ -144,7 +146,10 @@ def test_full_size_batch_properties_512(precision, cuda_device):
     del eng
     eng2 = UNetEngine(sd, 2, 2, 512, 512, device=cuda_device, precision=precision)
     sub = eng2.forward(xd[4:6].contiguous()).clone()
-    assert torch.equal(sub, a[4:6])
+    if precision == "fast":
+        assert torch.equal(sub, a[4:6])
+    else:
+        assert (sub - a[4:6]).abs().max().item() <= 1e-5 * a.abs().max().item()
     with torch.no_grad():
         ref = unet_oracle.unet_forward(sd, synth.normalize_tiles(u8[4:6]))
     _check(sub.float().cpu(), ref, "512 subset", precision)
