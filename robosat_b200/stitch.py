@@ -31,14 +31,15 @@ def neighbour_keys(tile):
 NATIVE_PNG = os.environ.get("RSB_PNG_DECODER", "native") != "pil"
 
 
-def decode_rgb(path, size):
-    """`Image.open(path).convert("RGB")` as uint8 [S, S, 3] (robosat/tiles.py:150-159, 181).
+def decode_rgb(path, size, out=None):
+    """`Image.open(path).convert("RGB")` as uint8 [S, S, 3] (robosat/tiles.py:150-159, 181), optionally straight into `out`
+    (a [S, S, 3] uint8 view of pinned staging memory: no intermediate copy).
 
     8-bit PNG tiles go through the library's own decoder (`rsb_png_read_rgb`: file read + inflate + unfilter in C, no
     interpreter lock held, so the pool threads decode in parallel); every other format (JPEG, WebP, 16-bit / interlaced PNG)
     is PIL's job exactly as in the reference."""
     if NATIVE_PNG and path.lower().endswith(".png"):
-        arr = np.empty((size, size, 3), dtype=np.uint8)
+        arr = out if out is not None else np.empty((size, size, 3), dtype=np.uint8)
         rc = _lib.load().rsb_png_read_rgb(os.fsencode(path), arr.ctypes.data, size, size)
         if rc == 0:
             return arr
@@ -46,6 +47,9 @@ def decode_rgb(path, size):
             raise _lib.RsbError("decoding %s failed: %s" % (path, _lib.last_error()))
     arr = np.asarray(Image.open(path).convert("RGB"), dtype=np.uint8)
     assert arr.shape == (size, size, 3), "tile %s is %s, expected %dx%d" % (path, arr.shape, size, size)
+    if out is not None:
+        out[...] = arr
+        return out
     return arr
 
 
@@ -64,8 +68,13 @@ class DeviceTileCache:
         self._stamp = [0] * capacity
         self._clock = 0
         self._free = list(range(capacity - 1, -1, -1))
-        self._staging = torch.empty((min(capacity, 64), tile_size, tile_size, 3), dtype=torch.uint8, pin_memory=pin)
-        self._staged = torch.cuda.Event() if pin else None
+        # pinned staging, two halves used by alternating tickets: the pool threads decode STRAIGHT into it (no host copy) while the
+        # uploads of the previous ticket are still in flight from the other half
+        self._half = max(16, min(capacity, int(os.environ.get("RSB_STAGING_TILES", "160"))))
+        self._staging = torch.empty((2 * self._half, tile_size, tile_size, 3), dtype=torch.uint8, pin_memory=pin)
+        self._staging_np = self._staging.numpy()
+        self._uploaded = [torch.cuda.Event() if pin else None for _ in range(2)]
+        self._tickets = 0
         self._pool = ThreadPoolExecutor(max_workers=workers)
         self.decodes = 0
         self.hits = 0
@@ -101,33 +110,49 @@ class DeviceTileCache:
             else:
                 self._stamp[s] = self._clock
                 self.hits += 1
-        ticket = []
-        for t in missing:
+        half = self._tickets % 2
+        self._tickets += 1
+        if self._uploaded[half] is not None:
+            self._uploaded[half].synchronize()  # the uploads of the ticket that last used this half have left the staging memory
+        ticket = {"half": half, "items": []}
+        for j, t in enumerate(missing):
             s = self._take_slot(keep)
             self._slot[t], self._owner[s], self._stamp[s] = s, t, self._clock
-            ticket.append((s, self._pool.submit(decode_rgb, self.index[t], self.size)))
+            # the first `_half` tiles decode into this ticket's half of the pinned staging; an oversized ticket (the first batch
+            # of a run can miss 9 x batch tiles) decodes the rest into ordinary arrays and stages them at commit time
+            dst = self._staging_np[half * self._half + j] if j < self._half else None
+            ticket["items"].append((s, self._pool.submit(decode_rgb, self.index[t], self.size, dst), dst is not None))
         self.decodes += len(missing)
         return ticket
 
     def commit(self, ticket):
-        """Second half of `ensure`: wait for the decodes of `ticket`, stage them in pinned memory and enqueue their uploads on
-        the current stream (i.e. after every kernel already enqueued that still reads the slots being replaced)."""
+        """Second half of `ensure`: wait for the decodes of `ticket` and enqueue their uploads on the current stream (i.e. after
+        every kernel already enqueued that still reads the slots being replaced)."""
         import time
 
-        chunk = self._staging.shape[0]
-        for i in range(0, len(ticket), chunk):
-            part = ticket[i:i + chunk]
-            if self._staged is not None:
-                self._staged.synchronize()  # the previous upload has finished reading the staging buffer
-            stage = self._staging.numpy()
+        half, items = ticket["half"], ticket["items"]
+        base = half * self._half
+        t0 = time.perf_counter()
+        for j, (s, fut, direct) in enumerate(items):
+            if direct:
+                fut.result()
+                self.store[s].copy_(self._staging[base + j], non_blocking=True)
+        self.decode_wait_s += time.perf_counter() - t0
+        if self._uploaded[half] is not None:
+            self._uploaded[half].record(torch.cuda.current_stream(self.device))
+        extra = [(s, fut) for s, fut, direct in items if not direct]
+        for i in range(0, len(extra), self._half):  # oversized ticket: reuse the same half, synchronously
+            part = extra[i:i + self._half]
+            if self._uploaded[half] is not None:
+                self._uploaded[half].synchronize()
             t0 = time.perf_counter()
-            for j, (_, fut) in enumerate(part):
-                stage[j] = fut.result()
+            for j, (s, fut) in enumerate(part):
+                self._staging_np[base + j] = fut.result()
             self.decode_wait_s += time.perf_counter() - t0
             for j, (s, _) in enumerate(part):
-                self.store[s].copy_(self._staging[j], non_blocking=True)
-            if self._staged is not None:
-                self._staged.record(torch.cuda.current_stream(self.device))
+                self.store[s].copy_(self._staging[base + j], non_blocking=True)
+            if self._uploaded[half] is not None:
+                self._uploaded[half].record(torch.cuda.current_stream(self.device))
 
     def table(self, tiles):
         """int32 [len(tiles), 9] slot table for `rsb_stitch_halo` (-1 where the store has no such neighbour)."""

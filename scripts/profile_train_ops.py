@@ -31,10 +31,13 @@ for phase, ops, kw in (("fwd", eng.fwd_ops, {"x": x}), ("bwd", eng.bwd_ops, {"dl
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
         name = op[1].name if op[0] in ("conv", "wgrad") else ""
+        if op[0].startswith("bn_"):
+            b_ = op[1]
+            name = "%s M=%d C=%d (%.0f MB of fp16 z)" % (getattr(b_, "prefix", "?"), b_.M, b_.C, b_.M * b_.C * 2 / 1e6)
         agg[phase + ":" + op[0]] += ms
-        if op[0] in ("conv", "wgrad"):
+        if op[0] in ("conv", "wgrad") or op[0].startswith("bn_"):
             rows.append((ms, phase, op[0], name))
 print(json.dumps({k: round(v, 3) for k, v in sorted(agg.items(), key=lambda kv: -kv[1])}))
 rows.sort(reverse=True)
-for ms, phase, kind, name in rows[:40]:
+for ms, phase, kind, name in rows[:120]:
     print("%8.3f ms  %s %-6s %s" % (ms, phase, kind, name))

@@ -134,7 +134,7 @@ def test_full_size_batch_properties_512(precision, cuda_device):
     (a) replay idempotence: the same input twice gives identical logits, bit for bit;
     (b) batch independence: tile i in a batch of 2 == tile i inside the batch of 32 -- bit for bit in the fast precision (one
         accumulation chain per output whatever the tiling); in the strict precision the plan's tile width / K-chunk choice
-        depends on the batch size and changes the ORDER of the fp32 partial sums, so the two agree to fp32 round-off (1e-5 rel);
+        depends on the batch size and changes the ORDER of the fp32 partial sums, so the two agree to fp32 round-off (5e-5 rel);
     (c) a 2-tile subset agrees with the oracle."""
     sd = synth.make_state_dict(2, seed=0)
     u8 = synth.make_tiles_u8(32, 512, seed=1)
@@ -149,7 +149,7 @@ def test_full_size_batch_properties_512(precision, cuda_device):
     if precision == "fast":
         assert torch.equal(sub, a[4:6])
     else:
-        assert (sub - a[4:6]).abs().max().item() <= 1e-5 * a.abs().max().item()
+        assert (sub - a[4:6]).abs().max().item() <= 5e-5 * a.abs().max().item()
     with torch.no_grad():
         ref = unet_oracle.unet_forward(sd, synth.normalize_tiles(u8[4:6]))
     _check(sub.float().cpu(), ref, "512 subset", precision)
