@@ -169,4 +169,6 @@ def test_six_class_1024_forward(cuda_device):
     xb = x.repeat(8, 1, 1, 1).to(cuda_device)
     out = eng8.forward(xb)
     torch.cuda.synchronize()
-    assert torch.equal(out[0], out[7]) and torch.equal(out[0].cpu(), got[0])
+    assert torch.equal(out[0], out[7])  # same tile in two batch slots: identical
+    # batch-8 plan vs batch-1 plan: other tile widths / K chunks, i.e. another order of the fp32 partial sums (see the 512 test)
+    assert (out[0].cpu() - got[0]).abs().max().item() <= 5e-5 * got.abs().max().item()
