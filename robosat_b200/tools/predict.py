@@ -154,15 +154,26 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
                     pending.append(pool.submit(_save_png, args.probs, palette, int(tile.x), int(tile.y), int(tile.z), q.copy(), st))
 
             previous = None
+            tm = {"stitch_s": 0.0, "prefetch_s": 0.0, "launch_s": 0.0, "drain_s": 0.0}
+            clock = time.perf_counter
             if chunks:
                 stitcher.prefetch(chunks[0])
             for ci, tiles in enumerate(progress(chunks, len(chunks))):
+                t0 = clock()
                 stitcher.stitch(tiles, predictor.device_input())  # upload what was decoded ahead, assemble the buffered batch on the device
+                t1 = clock()
                 if ci + 1 < len(chunks):
                     stitcher.prefetch(chunks[ci + 1])  # decode batch i+1 on the pool threads while the GPU runs batch i
+                t2 = clock()
                 predictor.submit_device()
+                t3 = clock()
                 if previous is not None:
                     drain(previous)  # batch i-1 is collected while batch i runs
+                t4 = clock()
+                tm["stitch_s"] += t1 - t0
+                tm["prefetch_s"] += t2 - t1
+                tm["launch_s"] += t3 - t2
+                tm["drain_s"] += t4 - t3
                 previous = tiles
             if previous is not None:
                 drain(previous)
@@ -170,6 +181,9 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
             for f in pending:
                 f.result()
             st["png_drain_s"] = time.perf_counter() - t0
+            st["main_thread_s"] = tm  # host time of the loop's four steps (includes the blocked waits reported separately)
+            t0 = time.perf_counter()
+        st["pool_shutdown_s"] = time.perf_counter() - t0
         cache.close()
         st.update(decode_wait_s=cache.decode_wait_s, decodes=cache.decodes, cache_hits=cache.hits)
         if rank == 0 and os.environ.get("RSB_VERBOSE"):

@@ -28,5 +28,5 @@ pr.enable()
 run_shard(0, 1, args, dev, sd, 2, stats=st)
 pr.disable()
 print({k: (round(v, 4) if isinstance(v, float) else v) for k, v in st.items()})
-pstats.Stats(pr).sort_stats("cumulative").print_stats(28)
+pstats.Stats(pr).sort_stats("tottime").print_stats(18)
 shutil.rmtree(root, ignore_errors=True)
