@@ -236,6 +236,14 @@ int64_t rsb_png_encode_p8(const uint8_t* pixels_host, int32_t w, int32_t h, cons
 int rsb_png_write_p8(const char* path, const uint8_t* pixels_host, int32_t w, int32_t h, const uint8_t* palette_rgb_host, int32_t entries,
                      int32_t level);
 
+/* Whole-batch variants, fanned out over `threads` threads inside the library (one call per tile batch from the tools):
+ * read: rcs_host[i] receives the per-file code (RSB_E_UNSUPPORTED entries are left for another decoder); the return value is the
+ * worst real error. write: image i is pixels_host + i*image_stride; make_dirs != 0 creates the parent directories (z/x/). */
+int rsb_png_read_rgb_batch(const char* const* paths, int32_t n, uint8_t* const* outs_rgb_host, int32_t w_expected, int32_t h_expected,
+                           int32_t threads, int32_t* rcs_host);
+int rsb_png_write_p8_batch(const char* const* paths, int32_t n, const uint8_t* pixels_host, int64_t image_stride, int32_t w, int32_t h,
+                           const uint8_t* palette_rgb_host, int32_t entries, int32_t level, int32_t threads, int32_t make_dirs);
+
 /* ---------------------------------------------------------------------------------------------
  * Losses and metrics on fp32 NCHW logits + int64 targets [N][H][W].
  */

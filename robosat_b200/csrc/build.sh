@@ -11,5 +11,5 @@ for f in rsb_host rsb_conv rsb_conv_row rsb_elementwise rsb_loss rsb_train rsb_w
 done
 # host-side PNG codec (plain C++ over zlib)
 ${CXX:-g++} -O3 -std=c++17 -fPIC -I/usr/local/cuda/include -c rsb_png.cpp -o rsb_png.o
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../librsb200.so $OBJS rsb_png.o -cudart static -lz
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../librsb200.so $OBJS rsb_png.o -cudart static -lz -lpthread
 echo "built $(cd .. && pwd)/librsb200.so"

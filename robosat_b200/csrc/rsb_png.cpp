@@ -11,6 +11,11 @@
 #include <string.h>
 #include <zlib.h>
 
+#include <sys/stat.h>
+
+#include <atomic>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/rsb200.h"
@@ -212,4 +217,65 @@ extern "C" int rsb_png_read_rgb(const char* path, uint8_t* out_rgb, int32_t w_ex
     std::vector<uint8_t> buf;
     if (!read_file(path, buf)) return set_error(RSB_E_INVALID, "png_read: cannot read %s", path);
     return rsb_png_decode_rgb(buf.data(), int64_t(buf.size()), out_rgb, w_expected, h_expected);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Batch entry points: one call per tile batch, fanned out over `threads` std::threads inside the library. The Python tools
+// submit ONE job per batch to their pool instead of one future per tile (2 x 1024 futures per 1024 tiles cost the main thread
+// of `rs predict` more than the GPU needed for the network -- profiles/r2_cfg4.md).
+namespace {
+
+template <typename F>
+void parallel_for(int n, int threads, F&& fn) {
+    if (threads < 1) threads = 1;
+    if (threads > n) threads = n;
+    if (threads <= 1) {
+        for (int i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    pool.reserve(size_t(threads));
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&]() {
+            for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i);
+        });
+    for (auto& th : pool) th.join();
+}
+
+// mkdir -p of the directory part of `path`
+void make_parent_dirs(const char* path) {
+    std::string p(path);
+    for (size_t i = 1; i < p.size(); ++i) {
+        if (p[i] == '/') {
+            p[i] = 0;
+            mkdir(p.c_str(), 0777);  // EEXIST is fine; a real failure shows up when the file is opened
+            p[i] = '/';
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int rsb_png_read_rgb_batch(const char* const* paths, int32_t n, uint8_t* const* outs_rgb, int32_t w_expected, int32_t h_expected,
+                                      int32_t threads, int32_t* rcs) {
+    if (!paths || !outs_rgb || !rcs || n < 0) return set_error(RSB_E_INVALID, "png_read_batch: bad arguments");
+    parallel_for(n, threads, [&](int i) { rcs[i] = rsb_png_read_rgb(paths[i], outs_rgb[i], w_expected, h_expected); });
+    int worst = RSB_OK;
+    for (int i = 0; i < n; ++i)
+        if (rcs[i] != RSB_OK && rcs[i] != RSB_E_UNSUPPORTED) worst = rcs[i];
+    return worst;  // per-file codes in rcs (RSB_E_UNSUPPORTED entries are the caller's to decode with another library)
+}
+
+extern "C" int rsb_png_write_p8_batch(const char* const* paths, int32_t n, const uint8_t* pixels, int64_t image_stride, int32_t w, int32_t h,
+                                      const uint8_t* palette_rgb, int32_t entries, int32_t level, int32_t threads, int32_t make_dirs) {
+    if (!paths || !pixels || n < 0 || image_stride < int64_t(w) * h) return set_error(RSB_E_INVALID, "png_write_batch: bad arguments");
+    std::vector<int> rc(size_t(n), RSB_OK);
+    parallel_for(n, threads, [&](int i) {
+        if (make_dirs) make_parent_dirs(paths[i]);
+        rc[size_t(i)] = rsb_png_write_p8(paths[i], pixels + int64_t(i) * image_stride, w, h, palette_rgb, entries, level);
+    });
+    for (int i = 0; i < n; ++i)
+        if (rc[size_t(i)] != RSB_OK) return set_error(rc[size_t(i)], "png_write_batch: writing %s failed", paths[i]);
+    return RSB_OK;
 }

@@ -53,6 +53,31 @@ def decode_rgb(path, size, out=None):
     return arr
 
 
+def decode_many(jobs, size, threads):
+    """jobs: [(path, out uint8 [S, S, 3])]. 8-bit PNG files are decoded by ONE library call that fans them out over `threads`
+    threads of its own (no interpreter lock, no per-file Python work); anything it reports as unsupported, and every non-PNG
+    file, goes through `decode_rgb` (PIL) like in the reference."""
+    import ctypes
+
+    rest = []
+    png = [(p, o) for p, o in jobs if NATIVE_PNG and p.lower().endswith(".png")]
+    rest.extend((p, o) for p, o in jobs if not (NATIVE_PNG and p.lower().endswith(".png")))
+    if png:
+        n = len(png)
+        paths = (ctypes.c_char_p * n)(*[os.fsencode(p) for p, _ in png])
+        outs = (ctypes.c_void_p * n)(*[o.ctypes.data for _, o in png])
+        rcs = (ctypes.c_int32 * n)()
+        rc = _lib.load().rsb_png_read_rgb_batch(paths, n, outs, size, size, threads, rcs)
+        if rc != 0:
+            bad = [png[i][0] for i in range(n) if rcs[i] not in (0, _lib.RSB_E_UNSUPPORTED)]
+            raise _lib.RsbError("decoding %s failed (rc=%d)" % (bad[:3], rc))
+        rest.extend(png[i] for i in range(n) if rcs[i] == _lib.RSB_E_UNSUPPORTED)
+    for p, o in rest:
+        arr = np.asarray(Image.open(p).convert("RGB"), dtype=np.uint8)
+        assert arr.shape == (size, size, 3), "tile %s is %s, expected %dx%d" % (p, arr.shape, size, size)
+        o[...] = arr
+
+
 class DeviceTileCache:
     """Decoded tiles resident on `device`; `ensure` decodes + uploads what is missing, evicting least-recently-used slots."""
 
@@ -75,7 +100,8 @@ class DeviceTileCache:
         self._staging_np = self._staging.numpy()
         self._uploaded = [torch.cuda.Event() if pin else None for _ in range(2)]
         self._tickets = 0
-        self._pool = ThreadPoolExecutor(max_workers=workers)
+        self.decode_threads = workers  # threads the library uses per ticket (C++ threads; the Python pool only carries the call)
+        self._pool = ThreadPoolExecutor(max_workers=2)
         self.decodes = 0
         self.hits = 0
         self.decode_wait_s = 0.0  # time the caller was blocked waiting for decodes (what is left on the critical path)
@@ -114,16 +140,18 @@ class DeviceTileCache:
         self._tickets += 1
         if self._uploaded[half] is not None:
             self._uploaded[half].synchronize()  # the uploads of the ticket that last used this half have left the staging memory
-        ticket = {"half": half, "items": []}
+        items, jobs = [], []
         for j, t in enumerate(missing):
             s = self._take_slot(keep)
             self._slot[t], self._owner[s], self._stamp[s] = s, t, self._clock
             # the first `_half` tiles decode into this ticket's half of the pinned staging; an oversized ticket (the first batch
             # of a run can miss 9 x batch tiles) decodes the rest into ordinary arrays and stages them at commit time
-            dst = self._staging_np[half * self._half + j] if j < self._half else None
-            ticket["items"].append((s, self._pool.submit(decode_rgb, self.index[t], self.size, dst), dst is not None))
+            dst = self._staging_np[half * self._half + j] if j < self._half else np.empty((self.size, self.size, 3), dtype=np.uint8)
+            items.append((s, dst, j < self._half))
+            jobs.append((self.index[t], dst))
         self.decodes += len(missing)
-        return ticket
+        # ONE pool job per ticket: the library fans the PNG files out over its own threads (rsb_png_read_rgb_batch)
+        return {"half": half, "items": items, "future": self._pool.submit(decode_many, jobs, self.size, self.decode_threads) if jobs else None}
 
     def commit(self, ticket):
         """Second half of `ensure`: wait for the decodes of `ticket` and enqueue their uploads on the current stream (i.e. after
@@ -132,24 +160,22 @@ class DeviceTileCache:
 
         half, items = ticket["half"], ticket["items"]
         base = half * self._half
-        t0 = time.perf_counter()
-        for j, (s, fut, direct) in enumerate(items):
+        if ticket["future"] is not None:
+            t0 = time.perf_counter()
+            ticket["future"].result()
+            self.decode_wait_s += time.perf_counter() - t0
+        for j, (s, _, direct) in enumerate(items):
             if direct:
-                fut.result()
                 self.store[s].copy_(self._staging[base + j], non_blocking=True)
-        self.decode_wait_s += time.perf_counter() - t0
         if self._uploaded[half] is not None:
             self._uploaded[half].record(torch.cuda.current_stream(self.device))
-        extra = [(s, fut) for s, fut, direct in items if not direct]
+        extra = [(s, arr) for s, arr, direct in items if not direct]
         for i in range(0, len(extra), self._half):  # oversized ticket: reuse the same half, synchronously
             part = extra[i:i + self._half]
             if self._uploaded[half] is not None:
                 self._uploaded[half].synchronize()
-            t0 = time.perf_counter()
-            for j, (s, fut) in enumerate(part):
-                self._staging_np[base + j] = fut.result()
-            self.decode_wait_s += time.perf_counter() - t0
-            for j, (s, _) in enumerate(part):
+            for j, (s, arr) in enumerate(part):
+                self._staging_np[base + j] = arr
                 self.store[s].copy_(self._staging[base + j], non_blocking=True)
             if self._uploaded[half] is not None:
                 self._uploaded[half].record(torch.cuda.current_stream(self.device))

@@ -66,6 +66,30 @@ def _save_png(root, palette, x, y, z, quantized, stats=None):
         stats["png_cpu_s"] = stats.get("png_cpu_s", 0.0) + (time.perf_counter() - t0)  # summed over pool threads (GIL-protected add)
 
 
+def _save_batch(root, palette, tiles, quantized, threads, stats=None):
+    """The PNG files of one batch through ONE library call (`rsb_png_write_p8_batch`: `threads` C++ threads, directories created
+    by the library); RSB_PNG_ENCODER=pil loops over `_save_png` with PIL instead. tiles: [(x, y, z)], quantized: uint8 [n, H, W]."""
+    if not NATIVE_PNG:
+        for (x, y, z), q in zip(tiles, quantized):
+            _save_png(root, palette, x, y, z, q, stats)
+        return
+    import ctypes
+
+    from robosat_b200 import _lib
+
+    t0 = time.perf_counter()
+    n = len(tiles)
+    pal = _PALETTE_BYTES.get(id(palette))
+    if pal is None:
+        pal = _PALETTE_BYTES.setdefault(id(palette), bytes(palette[:768]))
+    paths = (ctypes.c_char_p * n)(*[os.fsencode(os.path.join(root, str(z), str(x), str(y) + ".png")) for x, y, z in tiles])
+    q = quantized if quantized.flags["C_CONTIGUOUS"] else quantized.copy()
+    _lib.check(_lib.load().rsb_png_write_p8_batch(paths, n, q.ctypes.data, q.shape[1] * q.shape[2], q.shape[2], q.shape[1], pal, len(pal) // 3, 6,
+                                                  threads, 1), "rsb_png_write_p8_batch")
+    if stats is not None:
+        stats["png_cpu_s"] = stats.get("png_cpu_s", 0.0) + (time.perf_counter() - t0)  # wall time of the batch calls
+
+
 def run_shard(rank, world, args, device, sd, num_classes, stats=None):
     """This rank's share of the `rs predict` batch loop (predict.py:75-113): enumerate -> [decode -> halo stitch -> net -> bins]
     -> PNG. No collective in here: `sd` is the (already broadcast) state_dict. `stats` (optional dict) receives the stage
@@ -145,13 +169,13 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
         chunks = [mine[i:i + args.batch_size] for i in range(0, len(mine), args.batch_size)]
         st.update(tiles=len(mine), batches=len(chunks), decode_threads=decode_threads)
         st["setup_s"] = time.perf_counter() - t_start  # enumerate + plan (weight folding / packing) + buffers, before the first batch
-        with ThreadPoolExecutor(max_workers=pool_threads) as pool:
+        with ThreadPoolExecutor(max_workers=4) as pool:  # carries one library call per batch; the library brings its own threads
             pending = []
 
             def drain(tiles):
                 quantized = collect(predictor)
-                for tile, q in zip(tiles, quantized[:len(tiles)]):
-                    pending.append(pool.submit(_save_png, args.probs, palette, int(tile.x), int(tile.y), int(tile.z), q.copy(), st))
+                coords = [(int(t.x), int(t.y), int(t.z)) for t in tiles]
+                pending.append(pool.submit(_save_batch, args.probs, palette, coords, quantized[:len(tiles)].copy(), pool_threads, st))
 
             previous = None
             tm = {"stitch_s": 0.0, "prefetch_s": 0.0, "launch_s": 0.0, "drain_s": 0.0}
