@@ -182,14 +182,20 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
             clock = time.perf_counter
             if chunks:
                 stitcher.prefetch(chunks[0])
+            marks = []
             for ci, tiles in enumerate(progress(chunks, len(chunks))):
                 t0 = clock()
+                if stats is not None:  # device timeline of the batch: uploads + stitch + network + head, and the idle gap before it
+                    marks.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
+                    marks[-1][0].record()
                 stitcher.stitch(tiles, predictor.device_input())  # upload what was decoded ahead, assemble the buffered batch on the device
                 t1 = clock()
                 if ci + 1 < len(chunks):
                     stitcher.prefetch(chunks[ci + 1])  # decode batch i+1 on the pool threads while the GPU runs batch i
                 t2 = clock()
                 predictor.submit_device()
+                if stats is not None:
+                    marks[-1][1].record()
                 t3 = clock()
                 if previous is not None:
                     drain(previous)  # batch i-1 is collected while batch i runs
@@ -206,6 +212,10 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
                 f.result()
             st["png_drain_s"] = time.perf_counter() - t0
             st["main_thread_s"] = tm  # host time of the loop's four steps (includes the blocked waits reported separately)
+            if marks:
+                torch.cuda.synchronize(device)
+                st["device_busy_s"] = sum(a.elapsed_time(b) for a, b in marks) / 1e3           # uploads + stitch + net + head, per batch, summed
+                st["device_idle_s"] = sum(marks[i][1].elapsed_time(marks[i + 1][0]) for i in range(len(marks) - 1)) / 1e3  # stream empty between batches
             t0 = time.perf_counter()
         st["pool_shutdown_s"] = time.perf_counter() - t0
         cache.close()
