@@ -93,13 +93,18 @@ class DeviceTileCache:
         self._stamp = [0] * capacity
         self._clock = 0
         self._free = list(range(capacity - 1, -1, -1))
-        # pinned staging, two halves used by alternating tickets: the pool threads decode STRAIGHT into it (no host copy) while the
-        # uploads of the previous ticket are still in flight from the other half
-        self._half = max(16, min(capacity, int(os.environ.get("RSB_STAGING_TILES", "160"))))
-        self._staging = torch.empty((2 * self._half, tile_size, tile_size, 3), dtype=torch.uint8, pin_memory=pin)
+        # pinned staging, three regions used by successive tickets: the pool threads decode STRAIGHT into one (no host copy)
+        # while an earlier ticket waits to be committed in the second and the uploads of a third are still in flight
+        self._half = max(16, min(capacity, int(os.environ.get("RSB_STAGING_TILES", "128"))))
+        self._regions = 3
+        self._staging = torch.empty((self._regions * self._half, tile_size, tile_size, 3), dtype=torch.uint8, pin_memory=pin)
         self._staging_np = self._staging.numpy()
-        self._uploaded = [torch.cuda.Event() if pin else None for _ in range(2)]
+        self._uploaded = [torch.cuda.Event() if pin else None for _ in range(self._regions)]
         self._tickets = 0
+        self._protected = {}  # ticket number -> tiles a prefetched-but-not-yet-stitched batch needs (never evicted meanwhile)
+        # uploads run on their own stream, behind the last kernel that read the store, so they overlap the previous batch's network
+        self._copy_stream = torch.cuda.Stream(device=self.device) if pin else None
+        self._store_read = torch.cuda.Event() if pin else None
         self.decode_threads = workers  # threads the library uses per ticket (C++ threads; the Python pool only carries the call)
         self._pool = ThreadPoolExecutor(max_workers=2)
         self.decodes = 0
@@ -127,7 +132,7 @@ class DeviceTileCache:
         earlier batches, so the decode of batch i+1 runs while the GPU computes batch i (decode off the critical path)."""
         self._clock += 1
         want = [t for t in dict.fromkeys(tiles) if t in self.index]
-        keep = set(want)
+        keep = set(want).union(*self._protected.values()) if self._protected else set(want)
         missing = []
         for t in want:
             s = self._slot.get(t)
@@ -136,8 +141,10 @@ class DeviceTileCache:
             else:
                 self._stamp[s] = self._clock
                 self.hits += 1
-        half = self._tickets % 2
+        number = self._tickets
+        half = number % self._regions
         self._tickets += 1
+        self._protected[number] = set(want)
         if self._uploaded[half] is not None:
             self._uploaded[half].synchronize()  # the uploads of the ticket that last used this half have left the staging memory
         items, jobs = [], []
@@ -151,7 +158,8 @@ class DeviceTileCache:
             jobs.append((self.index[t], dst))
         self.decodes += len(missing)
         # ONE pool job per ticket: the library fans the PNG files out over its own threads (rsb_png_read_rgb_batch)
-        return {"half": half, "items": items, "future": self._pool.submit(decode_many, jobs, self.size, self.decode_threads) if jobs else None}
+        return {"number": number, "half": half, "items": items,
+                "future": self._pool.submit(decode_many, jobs, self.size, self.decode_threads) if jobs else None}
 
     def commit(self, ticket):
         """Second half of `ensure`: wait for the decodes of `ticket` and enqueue their uploads on the current stream (i.e. after
@@ -164,21 +172,35 @@ class DeviceTileCache:
             t0 = time.perf_counter()
             ticket["future"].result()
             self.decode_wait_s += time.perf_counter() - t0
-        for j, (s, _, direct) in enumerate(items):
-            if direct:
-                self.store[s].copy_(self._staging[base + j], non_blocking=True)
-        if self._uploaded[half] is not None:
-            self._uploaded[half].record(torch.cuda.current_stream(self.device))
+        main = torch.cuda.current_stream(self.device) if self._copy_stream is not None else None
+
+        def upload(pairs):
+            if self._copy_stream is None:
+                for s, j in pairs:
+                    self.store[s].copy_(self._staging[base + j], non_blocking=True)
+                return
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._store_read)  # every stitch kernel enqueued so far has finished reading the store
+                for s, j in pairs:
+                    self.store[s].copy_(self._staging[base + j], non_blocking=True)
+                self._uploaded[half].record(self._copy_stream)
+            main.wait_event(self._uploaded[half])  # the next stitch kernel (on the caller's stream) sees the new tiles
+
+        upload([(s, j) for j, (s, _, direct) in enumerate(items) if direct])
         extra = [(s, arr) for s, arr, direct in items if not direct]
-        for i in range(0, len(extra), self._half):  # oversized ticket: reuse the same half, synchronously
+        for i in range(0, len(extra), self._half):  # oversized ticket (first batch of a run): reuse the region, synchronously
             part = extra[i:i + self._half]
             if self._uploaded[half] is not None:
                 self._uploaded[half].synchronize()
             for j, (s, arr) in enumerate(part):
                 self._staging_np[base + j] = arr
-                self.store[s].copy_(self._staging[base + j], non_blocking=True)
-            if self._uploaded[half] is not None:
-                self._uploaded[half].record(torch.cuda.current_stream(self.device))
+            upload([(s, j) for j, (s, _) in enumerate(part)])
+        self._protected.pop(ticket["number"], None)  # the caller builds its slot table next; later prefetches may evict again
+
+    def mark_store_read(self):
+        """call after enqueuing a kernel that reads the store (the stitch kernel): later uploads wait for it"""
+        if self._store_read is not None:
+            self._store_read.record(torch.cuda.current_stream(self.device))
 
     def table(self, tiles):
         """int32 [len(tiles), 9] slot table for `rsb_stitch_halo` (-1 where the store has no such neighbour)."""
@@ -199,20 +221,21 @@ class HaloStitcher:
         self._dtable = torch.empty((batch, 9), dtype=torch.int32, device=cache.device)
         self._used = [torch.cuda.Event() if cache.device.type == "cuda" else None for _ in range(2)]
         self._n = 0
-        self._ticket = None
+        self._pending = {}
 
     def prefetch(self, tiles):
-        """Start decoding what `stitch(tiles, ...)` will need (call right after the previous `stitch`)."""
-        self._ticket = (tiles, self.cache.prefetch([k for t in tiles for k in neighbour_keys(t)]))
+        """Start decoding what `stitch(tiles, ...)` will need. Up to two batches may be prefetched ahead of the one being
+        stitched (the cache keeps their tiles resident until their own `stitch`)."""
+        self._pending[id(tiles)] = (tiles, self.cache.prefetch([k for t in tiles for k in neighbour_keys(t)]))
 
     def stitch(self, tiles, out):
         """tiles: <= batch Tile keys (missing rows of a ragged last batch become black); out: device uint8 [batch, F, F, 3]."""
         assert len(tiles) <= self.batch and tuple(out.shape) == (self.batch, self.full, self.full, 3) and out.dtype == torch.uint8
-        if self._ticket is not None and self._ticket[0] is tiles:
-            self.cache.commit(self._ticket[1])  # decodes started by prefetch(tiles)
+        pending = self._pending.pop(id(tiles), None)
+        if pending is not None and pending[0] is tiles:
+            self.cache.commit(pending[1])  # decodes started by prefetch(tiles)
         else:
             self.cache.ensure([k for t in tiles for k in neighbour_keys(t)])
-        self._ticket = None
         i = self._n % 2
         self._n += 1
         if self._used[i] is not None:
@@ -223,6 +246,7 @@ class HaloStitcher:
         self._dtable.copy_(host, non_blocking=True)
         _lib.check(_lib.load().rsb_stitch_halo(self.cache.store.data_ptr(), self._dtable.data_ptr(), out.data_ptr(), self.batch, self.cache.size,
                                                self.overlap, _lib.current_stream_ptr()), "rsb_stitch_halo")
+        self.cache.mark_store_read()
         if self._used[i] is not None:
             self._used[i].record(torch.cuda.current_stream(self.cache.device))
         return out

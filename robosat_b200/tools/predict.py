@@ -180,8 +180,10 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
             previous = None
             tm = {"stitch_s": 0.0, "prefetch_s": 0.0, "launch_s": 0.0, "drain_s": 0.0}
             clock = time.perf_counter
-            if chunks:
-                stitcher.prefetch(chunks[0])
+            # decode runs up to two batches ahead of the GPU when the cache can keep three batches' neighbourhoods resident
+            ahead = 2 if capacity >= 27 * args.batch_size else 1
+            for c in chunks[:ahead]:
+                stitcher.prefetch(c)
             marks = []
             for ci, tiles in enumerate(progress(chunks, len(chunks))):
                 t0 = clock()
@@ -190,8 +192,8 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
                     marks[-1][0].record()
                 stitcher.stitch(tiles, predictor.device_input())  # upload what was decoded ahead, assemble the buffered batch on the device
                 t1 = clock()
-                if ci + 1 < len(chunks):
-                    stitcher.prefetch(chunks[ci + 1])  # decode batch i+1 on the pool threads while the GPU runs batch i
+                if ci + ahead < len(chunks):
+                    stitcher.prefetch(chunks[ci + ahead])  # decode batch i+ahead on the library's threads while the GPU runs batch i
                 t2 = clock()
                 predictor.submit_device()
                 if stats is not None:
