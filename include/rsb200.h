@@ -338,6 +338,12 @@ int rsb_unpack_grads(const float* packed_grad, const int32_t* map4, float* grad,
  * dy is addressed like fwd->out (same pitches / phase strides). Replaces autograd's conv weight gradients (train.py:186). */
 typedef struct rsb_wgrad_plan rsb_wgrad_plan;
 int rsb_wgrad_plan_create(const rsb_conv_desc* fwd, const void* dy, float* dw_packed, rsb_wgrad_plan** out_plan);
+/* Deterministic split-K: bytes of scratch the plan needs (0 when it has a single pixel slice), and the call that hands it over.
+ * With a scratch every slice stores its partial gradient and a second kernel adds the slices in index order (bit-identical from
+ * run to run); without one the slices add into dw_packed with fp32 atomics. The scratch is private to a launch and may be shared
+ * by all plans that run on one stream. */
+int64_t rsb_wgrad_plan_scratch_bytes(const rsb_wgrad_plan* plan);
+int rsb_wgrad_plan_set_scratch(rsb_wgrad_plan* plan, float* scratch, int64_t scratch_bytes);
 void rsb_wgrad_plan_destroy(rsb_wgrad_plan* plan);
 int rsb_wgrad_run(const rsb_wgrad_plan* plan, void* stream);
 

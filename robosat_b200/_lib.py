@@ -164,6 +164,8 @@ SIGNATURES = {
     "rsb_pack_weights": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rsb_unpack_grads": (ctypes.c_int, [_vp, _vp, _vp, _i64, _f32, _vp]),
     "rsb_wgrad_plan_create": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, ctypes.POINTER(_vp)]),
+    "rsb_wgrad_plan_scratch_bytes": (_i64, [_vp]),
+    "rsb_wgrad_plan_set_scratch": (ctypes.c_int, [_vp, _vp, _i64]),
     "rsb_wgrad_plan_destroy": (None, [_vp]),
     "rsb_wgrad_run": (ctypes.c_int, [_vp, _vp]),
     "rsb_debug_umma": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp] + [_i32] * 8 + [_vp]),

@@ -187,7 +187,9 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::
     }
     tc_fence_before();
     if (TWO) cluster_sync_all();  // the peer's barriers must be initialised before anything arrives on them remotely
-    else __syncthreads();
+    // (pair: the cluster barrier already orders the allocator's shared-memory write of the TMEM address; the CTA barrier is
+    // there for tools that only track CTA-scope barriers -- compute-sanitizer racecheck reported the read below otherwise)
+    __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
 

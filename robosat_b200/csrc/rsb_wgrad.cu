@@ -51,6 +51,10 @@ struct alignas(64) WgradKParams {
     int32_t Cout;
     int64_t K;  // packed row length = 64 * kblocks
     float* dw;  // [phases*Cout][K] fp32
+    // deterministic split-K: slice s stores its partial gradient to partial + s * slice_stride (plain stores), and
+    // wgrad_reduce_kernel adds the slices in index order. NULL: fp32 atomic adds straight into dw (order-dependent last bits).
+    float* partial;
+    int64_t slice_stride;
 };
 
 struct WgItem {
@@ -205,13 +209,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             tc_fence_after();
             const int co = it.co_blk * 128 + row;
             const bool valid = co < p.Cout && has_work;
-            float* drow = p.dw + (static_cast<int64_t>(it.phase) * p.Cout + co) * p.K + static_cast<int64_t>(kb_lo) * 64;
+            // one writer per element when there is a single slice or a partial buffer per slice: plain stores, no atomics
+            const bool plain = p.slices == 1 || p.partial != nullptr;
+            float* dbase = (p.partial != nullptr && p.slices > 1) ? p.partial + static_cast<int64_t>(it.slice) * p.slice_stride : p.dw;
+            float* drow = dbase + (static_cast<int64_t>(it.phase) * p.Cout + co) * p.K + static_cast<int64_t>(kb_lo) * 64;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * kWgAccCols;
             for (int c = 0; c < nkb * 64; c += 32) {
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + c, r);
                 tmem_ld_wait();
-                if (valid) {
+                if (valid && plain) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4*>(drow + c + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                                                               __uint_as_float(r[j + 3]));
+                } else if (valid) {
                     // split-K reduction: 16-byte vector reductions (no return value) into the packed fp32 gradient
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -235,6 +247,23 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     if (warp_idx == 1) {
         tc_fence_after();
         tmem_dealloc<512>(tmem_base);
+    }
+}
+
+// dw[i] = partial[0][i] + partial[1][i] + ... in slice order: the deterministic second stage of the split-K reduction
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int64_t n4, int slices, int64_t stride4) {
+    const float4* p4 = reinterpret_cast<const float4*>(partial);
+    float4* d4 = reinterpret_cast<float4*>(dw);
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float4 a = p4[i];
+        for (int s = 1; s < slices; ++s) {
+            const float4 b = p4[i + s * stride4];
+            a.x += b.x;
+            a.y += b.y;
+            a.z += b.z;
+            a.w += b.w;
+        }
+        d4[i] = a;
     }
 }
 
@@ -344,21 +373,51 @@ extern "C" int rsb_wgrad_plan_create(const rsb_conv_desc* d, const void* dy, flo
     return RSB_OK;
 }
 
+extern "C" int64_t rsb_wgrad_plan_scratch_bytes(const rsb_wgrad_plan* plan) {
+    if (!plan) return 0;
+    return plan->kp.slices > 1 ? plan->dw_bytes * plan->kp.slices : 0;
+}
+
+extern "C" int rsb_wgrad_plan_set_scratch(rsb_wgrad_plan* plan, float* scratch, int64_t scratch_bytes) {
+    if (!plan) return set_error(RSB_E_INVALID, "wgrad: null plan");
+    const int64_t need = rsb_wgrad_plan_scratch_bytes(plan);
+    if (need == 0) return RSB_OK;  // a single slice writes every element exactly once: already deterministic
+    if (!scratch || scratch_bytes < need || (reinterpret_cast<uintptr_t>(scratch) & 15))
+        return set_error(RSB_E_INVALID, "wgrad: deterministic split-K needs a 16B-aligned scratch of >= %lld bytes", (long long)need);
+    plan->kp.partial = scratch;
+    plan->kp.slice_stride = plan->dw_bytes / 4;
+    return RSB_OK;
+}
+
 extern "C" void rsb_wgrad_plan_destroy(rsb_wgrad_plan* plan) { delete plan; }
 
 extern "C" int rsb_wgrad_run(const rsb_wgrad_plan* plan, void* stream_) {
     if (!plan) return set_error(RSB_E_INVALID, "wgrad: null plan");
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};  // per device: one process may drive several GPUs
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (!attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(wgrad)");
-        attr_set = true;
+        attr_set[dev] = true;
     }
-    cudaError_t e = cudaMemsetAsync(plan->kp.dw, 0, plan->dw_bytes, stream);
-    if (e != cudaSuccess) return set_cuda_error(e, "wgrad memset");
+    const bool atomics = plan->kp.slices > 1 && plan->kp.partial == nullptr;
+    cudaError_t e = cudaSuccess;
+    if (atomics) {  // the plain-store paths write every element of their destination
+        e = cudaMemsetAsync(plan->kp.dw, 0, plan->dw_bytes, stream);
+        if (e != cudaSuccess) return set_cuda_error(e, "wgrad memset");
+    }
     wgrad_tc_kernel<<<plan->grid, kWgThreads, kWgSmem, stream>>>(plan->kp);
     e = cudaGetLastError();
     if (e != cudaSuccess) return set_cuda_error(e, "wgrad_tc_kernel launch");
+    if (plan->kp.slices > 1 && plan->kp.partial != nullptr) {
+        const int64_t n4 = plan->dw_bytes / 16;
+        int blocks = static_cast<int>((n4 + 255) / 256);
+        if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
+        wgrad_reduce_kernel<<<blocks, 256, 0, stream>>>(plan->kp.partial, plan->kp.dw, n4, plan->kp.slices, plan->kp.slice_stride / 4);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return set_cuda_error(e, "wgrad_reduce_kernel launch");
+    }
     return RSB_OK;
 }

@@ -17,6 +17,7 @@ Activation gradients are fp16 and carry `loss_scale`; parameter gradients are fp
 """
 
 import ctypes
+import os
 from collections import OrderedDict
 
 import numpy as np
@@ -250,6 +251,24 @@ class UNetTrainEngine:
         self.units[name] = u
         self.fwd_ops.append(("conv", u.fwd))
         return u
+
+    def _wgrad_scratch_for(self, plan):
+        """Deterministic split-K (default; RSB_WGRAD_DETERMINISTIC=0 restores fp32 atomics): one scratch for the per-slice partial
+        gradients, shared by every wgrad plan of the engine (launches are stream ordered) and grown to the largest request."""
+        if os.environ.get("RSB_WGRAD_DETERMINISTIC", "1") == "0":
+            return
+        lib = _lib.load()
+        plans = self.__dict__.setdefault("_wgrad_plans", [])
+        plans.append(plan)
+        need = int(lib.rsb_wgrad_plan_scratch_bytes(plan))
+        buf = self.__dict__.get("_wgrad_scratch")
+        if need and (buf is None or buf.numel() * 4 < need):
+            buf = self._wgrad_scratch = torch.empty((need + 3) // 4, dtype=torch.float32, device=self.device)
+            for pl in plans[:-1]:  # plans created earlier move to the larger buffer
+                if lib.rsb_wgrad_plan_scratch_bytes(pl):
+                    _lib.check(lib.rsb_wgrad_plan_set_scratch(pl, buf.data_ptr(), buf.numel() * 4), "rsb_wgrad_plan_set_scratch")
+        if need:
+            _lib.check(lib.rsb_wgrad_plan_set_scratch(plan, buf.data_ptr(), buf.numel() * 4), "rsb_wgrad_plan_set_scratch")
 
     def _wgrad_ops(self, u, dy):
         """weight gradient of unit u from dy (addressed like u's forward output), unpacked into the OIHW gradient"""
@@ -568,6 +587,7 @@ class UNetTrainEngine:
                     u.wgrad_plan = ctypes.c_void_p()
                     _lib.check(lib.rsb_wgrad_plan_create(ctypes.byref(u.desc), dy.data_ptr() + 2 * u.out_offset, u.dw_packed.data_ptr(),
                                                          ctypes.byref(u.wgrad_plan)), "rsb_wgrad_plan_create[%s]" % u.name)
+                    self._wgrad_scratch_for(u.wgrad_plan)
                 _lib.check(lib.rsb_wgrad_run(u.wgrad_plan, st), "rsb_wgrad_run[%s]" % u.name)
             elif k == "prepass":
                 kind = 0 if x.dtype == torch.float32 else 1

@@ -452,3 +452,20 @@ def test_inference_plans_follow_weight_updates_through_dataparallel(cuda_device)
         net.module.final.bias.add_(1.0)    # in-place edit in eval mode
         c = net(x.to(cuda_device)).cpu()
     assert torch.allclose(c, b + 1.0, atol=1e-3)
+
+
+def test_backward_is_deterministic(cuda_device):
+    """Deterministic split-K of the weight gradients (rsb_wgrad_plan_set_scratch: per-slice partials added in slice order by a
+    second kernel): two backward passes over the same activations give bit-identical parameter gradients."""
+    sd0, x, params, eng = _engine_pair(2, 2, 128, cuda_device)
+    g = torch.Generator().manual_seed(3)
+    dlogits = (torch.randn((2, 2, 128, 128), generator=g) * 1e-3).to(cuda_device)
+    runs = []
+    for _ in range(2):
+        eng.forward(x.to(cuda_device))
+        grads = eng.backward(dlogits)
+        torch.cuda.synchronize()
+        runs.append({k: v.clone() for k, v in grads.items()})
+    assert getattr(eng, "_wgrad_scratch", None) is not None, "no wgrad plan needed a scratch: the test would be vacuous"
+    for k in runs[0]:
+        assert torch.equal(runs[0][k], runs[1][k]), k
