@@ -332,6 +332,11 @@ int rsb_pack_weights(const float* src, const int32_t* map4, void* dst, int64_t n
 /* packed fp32 gradient -> OIHW fp32 gradient: grad[map4[4i+j]] += packed_grad[i] * mul (the transpose of rsb_pack_weights) */
 int rsb_unpack_grads(const float* packed_grad, const int32_t* map4, float* grad, int64_t n, float mul, void* stream);
 
+/* the same reduction without atomics (deterministic): element i of the compact list writes grad[dst_idx[i]] = mul * (sum of the
+ * packed gradient elements inv4[4i..4i+3], entries < 0 skipped, added in index order); inv4 is the inverse of map4 */
+int rsb_unpack_grads_gather(const float* packed_grad, const int32_t* dst_idx, const int32_t* inv4, float* grad, int64_t n, float mul,
+                            void* stream);
+
 /* Weight gradient of the convolution described by `fwd` (same sources / segments / phases / tile space), on tensor cores:
  *   dw_packed[phase*Cout + co][k] = sum_pixels dy_phase[pixel][co] * x_segment(k)[pixel + (dh,dw)][k % 64-block]   (fp32)
  * i.e. the gradient in the forward kernel's packed weight layout (rsb_unpack_grads folds it back to OIHW).

@@ -163,6 +163,7 @@ SIGNATURES = {
     "rsb_final_backward": (ctypes.c_int, [_vp] * 7 + [_f32, _i32, _i32, _i32, _vp]),
     "rsb_pack_weights": (ctypes.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "rsb_unpack_grads": (ctypes.c_int, [_vp, _vp, _vp, _i64, _f32, _vp]),
+    "rsb_unpack_grads_gather": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _vp]),
     "rsb_wgrad_plan_create": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _vp, _vp, ctypes.POINTER(_vp)]),
     "rsb_wgrad_plan_scratch_bytes": (_i64, [_vp]),
     "rsb_wgrad_plan_set_scratch": (ctypes.c_int, [_vp, _vp, _i64]),

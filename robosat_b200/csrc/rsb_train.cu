@@ -585,6 +585,22 @@ __global__ void unpack_scatter_kernel(const float* __restrict__ packed_grad, con
     }
 }
 
+// Deterministic form of the same scatter: one thread per OIHW gradient element, which GATHERS its (at most four) packed
+// contributions in index order -- the nearest-x2 phases route every 3x3 weight into four packed elements, and adding those with
+// atomics made the last bits of the decoder gradients depend on the thread schedule.
+__global__ void unpack_gather_kernel(const float* __restrict__ packed_grad, const int32_t* __restrict__ dst_idx, const int32_t* __restrict__ inv,
+                                     float* __restrict__ grad, int64_t n, float mul) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int4 m = __ldg(reinterpret_cast<const int4*>(inv) + i);
+        float g = 0.f;
+        if (m.x >= 0) g += packed_grad[m.x];
+        if (m.y >= 0) g += packed_grad[m.y];
+        if (m.z >= 0) g += packed_grad[m.z];
+        if (m.w >= 0) g += packed_grad[m.w];
+        grad[dst_idx[i]] = g * mul;
+    }
+}
+
 // dst_i[j] += alpha * src_i[j] over a table of (src, dst, n) fp32 segments, one block per segment: the whole network's
 // parameter gradients are added into the caller's .grad tensors in one launch (instead of one autograd add per tensor).
 __global__ void multi_axpy_kernel(const int64_t* __restrict__ table, float alpha) {
@@ -766,6 +782,16 @@ extern "C" int rsb_unpack_grads(const float* packed_grad, const int32_t* map4, f
     unpack_scatter_kernel<<<tr_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(packed_grad, map4, grad, n, mul);
     RSB_LAUNCH_CHECK("unpack_grads launch");
     return RSB_OK;
+}
+
+extern "C" int rsb_unpack_grads_gather(const float* packed_grad, const int32_t* dst_idx, const int32_t* inv4, float* grad, int64_t n, float mul,
+                                       void* stream) {
+    if (!packed_grad || !dst_idx || !inv4 || !grad || n <= 0) return set_error(RSB_E_INVALID, "unpack_grads_gather: bad arguments");
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 65535) blocks = 65535;
+    unpack_gather_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(packed_grad, dst_idx, inv4, grad, n, mul);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "unpack_gather launch");
 }
 
 extern "C" int rsb_multi_axpy(const int64_t* table, int32_t segments, float alpha, void* stream) {

@@ -534,14 +534,39 @@ class UNetTrainEngine:
                 if self._unpack_all is None:
                     self._grad(self.unpack_list[0][2])
                     self._unpack_all = []
+                    deterministic = os.environ.get("RSB_WGRAD_DETERMINISTIC", "1") != "0"
                     for ci, (chunk, used) in enumerate(self._dw_chunks):
                         gmap = torch.full((used, 4), -1, dtype=torch.int32, device=self.device)
                         for dwp, m, wname, c, off in self.unpack_list:
                             if c == ci:
                                 gmap[off:off + m.shape[0]] = torch.where(m >= 0, m + self._grad_offset[wname], m)
-                        self._unpack_all.append((gmap, chunk, used))
-                for gmap, chunk, used in self._unpack_all:
-                    _lib.check(lib.rsb_unpack_grads(chunk.data_ptr(), gmap.data_ptr(), self._grads_flat.data_ptr(), used, 1.0 / self.loss_scale, st), "rsb_unpack_grads")
+                        if deterministic:
+                            # invert the scatter map once: every OIHW gradient element gathers its <= 4 packed contributions in order
+                            flat = gmap.reshape(-1).long()
+                            valid = flat >= 0
+                            src = flat[valid]
+                            pk = (torch.arange(flat.numel(), device=self.device) // 4)[valid]
+                            order = torch.argsort(src, stable=True)
+                            src, pk = src[order], pk[order]
+                            uniq, counts = torch.unique_consecutive(src, return_counts=True)
+                            assert int(counts.max()) <= 4, "a weight receives more than 4 packed gradient contributions"
+                            start = torch.cumsum(counts, 0) - counts
+                            gid = torch.repeat_interleave(torch.arange(uniq.numel(), device=self.device), counts)
+                            rank = torch.arange(src.numel(), device=self.device) - start[gid]
+                            inv = torch.full((uniq.numel(), 4), -1, dtype=torch.int32, device=self.device)
+                            inv[gid, rank] = pk.int()
+                            self._unpack_all.append(("gather", uniq.int().contiguous(), inv.contiguous(), chunk))
+                            del gmap
+                        else:
+                            self._unpack_all.append(("scatter", gmap, None, chunk, used))
+                for item in self._unpack_all:
+                    if item[0] == "gather":
+                        _, dst_idx, inv, chunk = item
+                        _lib.check(lib.rsb_unpack_grads_gather(chunk.data_ptr(), dst_idx.data_ptr(), inv.data_ptr(), self._grads_flat.data_ptr(),
+                                                               dst_idx.numel(), 1.0 / self.loss_scale, st), "rsb_unpack_grads_gather")
+                    else:
+                        _, gmap, _, chunk, used = item
+                        _lib.check(lib.rsb_unpack_grads(chunk.data_ptr(), gmap.data_ptr(), self._grads_flat.data_ptr(), used, 1.0 / self.loss_scale, st), "rsb_unpack_grads")
             elif k == "bn_stats":
                 # batch sums + (in the reduction's last block) statistics, folded scale/shift and the running-stat update
                 b = op[1]
