@@ -201,6 +201,12 @@ int rsb_maxpool_nhwc(const void* src, void* dst, int32_t N, int32_t H, int32_t W
 int rsb_maxpool_nhwc_split(const void* src, int64_t src_plane, void* dst, int64_t dst_plane, int32_t N, int32_t H, int32_t W,
                            int32_t C, int32_t k, int32_t s, int32_t p, void* stream);
 
+/* Training-side augmentation (robosat/transforms.py:127-221 as composed in train.py:253-258): per sample an optional left-right flip
+ * followed by k counter-clockwise quarter turns, applied to the RGB tile uint8 [N][S][S][3] and its mask uint8 [N][S][S] (mask may be
+ * NULL); ops int32 [N] on the device, op = flip | (k << 1). out_mask is int64 (what the losses consume). Not in place. */
+int rsb_augment_dihedral(const uint8_t* img, const uint8_t* mask, const int32_t* ops, uint8_t* out_img, int64_t* out_mask, int32_t N, int32_t S,
+                         void* stream);
+
 /* Predict head. Replaces softmax(outputs, 1) ... np.digitize(foreground, linspace(0,1,256)).astype(uint8)
  * (predict.py:87, 93, 98-103) for the 2-class case, including the crop of the `overlap` border (datasets.py:133-136).
  * logits fp32 [N][2][H][W] -> quant uint8 [N][H-2o][W-2o]; probs_fg (fp32, same cropped shape) optional. */

@@ -149,6 +149,35 @@ __global__ void maxpool_nhwc_split_kernel(const __half* __restrict__ src, int64_
     *reinterpret_cast<uint4*>(dst + dst_plane + o) = *reinterpret_cast<const uint4*>(lo);
 }
 
+// Training-side augmentation on the device (robosat/transforms.py:127-221 as composed by train.py:253-258): per sample an optional
+// left-right flip followed by k counter-clockwise quarter turns (PIL's FLIP_LEFT_RIGHT / ROTATE_90), applied identically to the
+// RGB tile and its mask. op = flip | (k << 1). One thread per output pixel: 3 image bytes + 1 mask label (widened to int64, the
+// dtype the losses take -- MaskToTensor's job in the reference).
+__global__ void augment_dihedral_kernel(const uint8_t* __restrict__ img, const uint8_t* __restrict__ mask, const int32_t* __restrict__ ops,
+                                        uint8_t* __restrict__ out_img, int64_t* __restrict__ out_mask, int N, int S) {
+    const int64_t total = static_cast<int64_t>(N) * S * S;
+    for (int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; gid < total; gid += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int x = static_cast<int>(gid % S);
+        const int y = static_cast<int>((gid / S) % S);
+        const int n = static_cast<int>(gid / (static_cast<int64_t>(S) * S));
+        const int op = ops[n];
+        int sy = y, sx = x;
+        for (int k = (op >> 1) & 3; k > 0; --k) {  // undo the quarter turns: ROTATE_90 writes out[y][x] = in[x][S-1-y]
+            const int t = sy;
+            sy = sx;
+            sx = S - 1 - t;
+        }
+        if (op & 1) sx = S - 1 - sx;               // undo the flip: out[y][x] = in[y][S-1-x]
+        const int64_t src = (static_cast<int64_t>(n) * S + sy) * S + sx;
+        const uint8_t* s3 = img + src * 3;
+        uint8_t* d3 = out_img + gid * 3;
+        d3[0] = s3[0];
+        d3[1] = s3[1];
+        d3[2] = s3[2];
+        if (mask) out_mask[gid] = static_cast<int64_t>(mask[src]);
+    }
+}
+
 // number of anchors of np.linspace(0, 1, 256) that are <= x, compared in float64 like np.digitize does
 __device__ __forceinline__ int digitize256(float xf) {
     const double x = static_cast<double>(xf);
@@ -381,6 +410,16 @@ extern "C" int rsb_maxpool_nhwc(const void* src, void* dst, int32_t N, int32_t H
         static_cast<const __half*>(src), static_cast<__half*>(dst), N, H, W, C, k, s, p, OH, OW);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "maxpool launch");
+}
+
+extern "C" int rsb_augment_dihedral(const uint8_t* img, const uint8_t* mask, const int32_t* ops, uint8_t* out_img, int64_t* out_mask, int32_t N,
+                                    int32_t S, void* stream) {
+    if (!img || !ops || !out_img || N <= 0 || S <= 0 || (mask && !out_mask)) return set_error(RSB_E_INVALID, "augment_dihedral: bad arguments");
+    if (img == out_img) return set_error(RSB_E_INVALID, "augment_dihedral: cannot run in place");
+    const int64_t total = static_cast<int64_t>(N) * S * S;
+    augment_dihedral_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(img, mask, ops, out_img, out_mask, N, S);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? RSB_OK : set_cuda_error(e, "augment_dihedral launch");
 }
 
 extern "C" int rsb_head_quantize(const float* logits, uint8_t* quant, float* probs_fg, int32_t N, int32_t H, int32_t W,

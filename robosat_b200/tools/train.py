@@ -81,6 +81,16 @@ class _ResizeCrop:
         return image
 
 
+DEVICE_AUGMENT = os.environ.get("RSB_DEVICE_AUGMENT", "1") != "0"
+
+
+class _MaskToUint8:
+    def __call__(self, image):
+        import numpy as np
+
+        return torch.from_numpy(np.array(image, dtype=np.uint8))
+
+
 def get_dataset_loaders(model, dataset, workers, rank=0, world=1):
     from torch.utils.data import DataLoader
     from torch.utils.data.distributed import DistributedSampler
@@ -89,16 +99,27 @@ def get_dataset_loaders(model, dataset, workers, rank=0, world=1):
     batch_size = model["common"]["batch_size"]
     path = dataset["common"]["dataset"]
     mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
-    transform = JointCompose([
-        JointTransform(ConvertImageMode("RGB"), ConvertImageMode("P")),
-        JointTransform(_ResizeCrop(target_size, Image.BILINEAR), _ResizeCrop(target_size, Image.NEAREST)),
-        JointRandomHorizontalFlip(0.5),
-        JointRandomRotation(0.5, 90),
-        JointRandomRotation(0.5, 90),
-        JointRandomRotation(0.5, 90),
-        JointTransform(ImageToTensor(), MaskToTensor()),
-        JointTransform(_Normalize(mean, std), None),
-    ])
+    if DEVICE_AUGMENT:
+        # the workers only decode and resize; the random flip / quarter turns (train.py:253-258), ToTensor and Normalize run on the
+        # device on the whole uint8 batch (robosat_b200/augment.py, rsb_augment_dihedral, the pre-pass of the network)
+        from robosat_b200.transforms import ImageToUint8Tensor
+
+        transform = JointCompose([
+            JointTransform(ConvertImageMode("RGB"), ConvertImageMode("P")),
+            JointTransform(_ResizeCrop(target_size, Image.BILINEAR), _ResizeCrop(target_size, Image.NEAREST)),
+            JointTransform(ImageToUint8Tensor(), _MaskToUint8()),
+        ])
+    else:
+        transform = JointCompose([
+            JointTransform(ConvertImageMode("RGB"), ConvertImageMode("P")),
+            JointTransform(_ResizeCrop(target_size, Image.BILINEAR), _ResizeCrop(target_size, Image.NEAREST)),
+            JointRandomHorizontalFlip(0.5),
+            JointRandomRotation(0.5, 90),
+            JointRandomRotation(0.5, 90),
+            JointRandomRotation(0.5, 90),
+            JointTransform(ImageToTensor(), MaskToTensor()),
+            JointTransform(_Normalize(mean, std), None),
+        ])
     train_dataset = SlippyMapTilesConcatenation([os.path.join(path, "training", "images")], os.path.join(path, "training", "labels"), transform)
     val_dataset = SlippyMapTilesConcatenation([os.path.join(path, "validation", "images")], os.path.join(path, "validation", "labels"), transform)
     assert len(train_dataset) > 0, "at least one tile in training dataset"
@@ -122,10 +143,23 @@ def _epoch(loader, num_classes, device, net, criterion, optimizer=None, world=1,
     num_samples, running_loss = 0, torch.zeros((), dtype=torch.float32, device=device)
     metrics = Metrics(range(num_classes))
     net.train() if training else net.eval()
+    augmenter = None
     for images, masks, _tiles in loader:
         images = images.to(device, non_blocking=True)
         masks = masks.to(device, non_blocking=True)
-        assert images.size()[2:] == masks.size()[1:], "resolutions for images and masks are in sync"
+        if images.dtype == torch.uint8:
+            # raw uint8 NHWC tiles + uint8 masks from the workers: flip / rotate the batch on the device (the reference applies
+            # the same random transform to the training AND the validation set, train.py:248-268), masks become int64
+            if augmenter is None:
+                from robosat_b200.augment import DeviceAugmenter
+
+                augmenter = DeviceAugmenter(images.shape[0], images.shape[1], device=device)
+            assert images.shape[1:3] == masks.shape[1:], "resolutions for images and masks are in sync"
+            images, masks = augmenter.augment(images.contiguous(), masks.contiguous())
+            sizes_ok = images.shape[1:3] == masks.shape[1:]
+        else:
+            sizes_ok = images.size()[2:] == masks.size()[1:]
+        assert sizes_ok, "resolutions for images and masks are in sync"
         num_samples += int(images.size(0))
         if training:
             optimizer.zero_grad()

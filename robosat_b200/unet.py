@@ -136,13 +136,14 @@ class UNet(nn.Module):
     def _train_engine_for(self, x):
         from robosat_b200.train_engine import UNetTrainEngine
 
-        key = (tuple(x.shape), x.device.index)
+        key = (tuple(x.shape), x.dtype, x.device.index)
         eng = self._train_engines.get(key)
         if eng is None:
             # live references: the plan reads the current storage of every parameter / buffer at each step
             params = dict(self.named_parameters())
             params.update(dict(self.named_buffers()))
-            eng = UNetTrainEngine(params, self.num_classes, x.shape[0], x.shape[2], x.shape[3], device=x.device, loss_scale=self.loss_scale)
+            h, w = (x.shape[2], x.shape[3]) if x.dtype == torch.float32 else (x.shape[1], x.shape[2])
+            eng = UNetTrainEngine(params, self.num_classes, x.shape[0], h, w, device=x.device, loss_scale=self.loss_scale)
             self._train_engines[key] = eng
         return eng
 
@@ -168,7 +169,8 @@ class UNet(nn.Module):
         if not x.is_cuda:
             raise _lib.RsbError("robosat_b200.UNet runs on sm_100a kernels only (no CPU fallback); move the input to a CUDA device")
         if self.training:
-            assert x.dtype == torch.float32, "training takes the reference's normalised fp32 NCHW tensors"
+            # the reference's normalised fp32 NCHW tensors, or raw uint8 NHWC tiles (normalised by the pre-pass on the device)
+            assert x.dtype in (torch.float32, torch.uint8), "training takes fp32 NCHW (normalised) or uint8 NHWC (raw) tiles"
             named = [(n, p) for n, p in self.named_parameters()]
             return _TrainStep.apply(x, self, tuple(n for n, _ in named), *[p for _, p in named])
         return self._engine_for(x).forward(x.contiguous()).clone()
