@@ -171,6 +171,10 @@ typedef struct rsb_rowconv_desc {
     const float* head_b;
     float* head_out;
     int32_t rows_per_unit;   /* output rows per work unit (0 = default 32) */
+    /* strict precision (see rsb_conv_desc.split): mode 1, cin 32, 3x3 only -- src.plane gives the lo plane of the input,
+     * weights are fp16 [2][Cout][K] (hi, lo of w * 2^e), acc_scale = 2^-e */
+    int32_t split;
+    float acc_scale;
 } rsb_rowconv_desc;
 
 typedef struct rsb_rowconv_plan rsb_rowconv_plan;

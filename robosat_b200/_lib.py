@@ -107,6 +107,8 @@ class RowConvDesc(ctypes.Structure):
         ("head_b", ctypes.c_void_p),
         ("head_out", ctypes.c_void_p),
         ("rows_per_unit", ctypes.c_int32),
+        ("split", ctypes.c_int32),
+        ("acc_scale", ctypes.c_float),
     ]
 
 

@@ -49,6 +49,8 @@ struct alignas(64) RowKParams {
     const float* head_w;
     const float* head_b;
     float* head_out;
+    float acc_scale;      // strict precision: 2^-e of the weight scaling (1 otherwise)
+    int32_t plane_bytes;  // strict precision: byte distance between the hi and lo plane of a ring row (= cblocks * slot_bytes)
 };
 
 struct RowUnit {
@@ -96,12 +98,17 @@ struct RowCfg {
 // TAPS: 3 (3x3) or 2 (2x2 taps of the fused upsample); CBLOCKS: channel blocks per pixel; NSUB: column phases per tile.
 // They are compile-time so that the single MMA-issuing thread runs a fully unrolled instruction stream (its issue rate,
 // not the tensor pipe, bounds these small-N layers otherwise).
-template <int CBLK, int BLOCK_N, int MODE, int TAPS, int CBLOCKS, int NSUB>
+// SPLIT (strict precision, see rsb_conv.cu): every ring row and every weight block holds a hi and a lo fp16 plane; per K step
+// one MMA of width 2*BLOCK_N computes A_hi x [W_hi | W_lo] into [main | cross] columns and a second adds A_lo x W_hi onto the
+// cross columns; the epilogue adds main + cross in fp32. Instantiated for dec5 + final (the one strict layer whose resident
+// weights and 2-plane ring fit in shared memory).
+template <int CBLK, int BLOCK_N, int MODE, int TAPS, int CBLOCKS, int NSUB, bool SPLIT = false>
 __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_constant__ RowKParams p) {
     using Cfg = RowCfg<CBLK, BLOCK_N, MODE>;
+    constexpr int kAcc = SPLIT ? 2 * BLOCK_N : BLOCK_N;  // tensor-memory columns of one (stage, sub-tile) accumulator
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int row_bytes = p.slot_bytes * p.cblocks;            // one ring slot = all channel blocks of a row
+    const int row_bytes = p.slot_bytes * p.cblocks * (SPLIT ? 2 : 1);  // one ring slot = all channel blocks (and planes) of a row
     uint8_t* smem_rows = smem;
     uint8_t* smem_w = smem_rows + p.slots * row_bytes;
     const int nwblocks = p.nsub * p.taps_h * p.taps_w * p.cblocks;
@@ -122,7 +129,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         for (int i = threadIdx.x; i < p.head_classes * 32; i += blockDim.x) smem_head[i] = p.head_w[i];
         if (threadIdx.x < p.head_classes) smem_head[256 + threadIdx.x] = p.head_b[threadIdx.x];
     }
-    constexpr int kTmemCols = 4 * BLOCK_N <= 32 ? 32 : (4 * BLOCK_N <= 64 ? 64 : (4 * BLOCK_N <= 128 ? 128 : 256));  // 2 stages x 2 subs
+    constexpr int kTmemCols = 4 * kAcc <= 32 ? 32 : (4 * kAcc <= 64 ? 64 : (4 * kAcc <= 128 ? 128 : 256));  // 2 stages x 2 subs
 
     if (warp_idx == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA);
@@ -166,7 +173,8 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                         for (int t = 0; t < p.taps_h * p.taps_w; ++t) {
                             for (int cb = 0; cb < p.cblocks; ++cb) {
                                 const int blk = (s * p.taps_h * p.taps_w + t) * p.cblocks + cb;
-                                tma_load_2d(smem_w + blk * p.wblock_bytes, &p.tmB, wfull_bar, (t * p.cblocks + cb) * CBLK, brow);
+                                if constexpr (SPLIT) tma_load_3d(smem_w + blk * p.wblock_bytes, &p.tmB, wfull_bar, (t * p.cblocks + cb) * CBLK, brow, 0);
+                                else tma_load_2d(smem_w + blk * p.wblock_bytes, &p.tmB, wfull_bar, (t * p.cblocks + cb) * CBLK, brow);
                             }
                         }
                     }
@@ -178,9 +186,16 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                 for (int r = r_first; r <= r_last; ++r, ++q) {
                     const int slot = q % p.slots;
                     mbar_wait(&empty_bar[slot], ((q / p.slots) & 1) ^ 1);
-                    mbar_expect_tx(&full_bar[slot], p.cblocks * p.buf_w * Cfg::kPB);
-                    for (int cb = 0; cb < p.cblocks; ++cb)
-                        tma_load_4d(smem_rows + slot * row_bytes + cb * p.slot_bytes, &p.tmA, &full_bar[slot], cb * CBLK, u.w0 + p.dw0, r, u.n);
+                    mbar_expect_tx(&full_bar[slot], (SPLIT ? 2 : 1) * p.cblocks * p.buf_w * Cfg::kPB);
+                    for (int cb = 0; cb < p.cblocks; ++cb) {
+                        if constexpr (SPLIT) {
+                            tma_load_5d(smem_rows + slot * row_bytes + cb * p.slot_bytes, &p.tmA, &full_bar[slot], cb * CBLK, u.w0 + p.dw0, r, u.n, 0);
+                            tma_load_5d(smem_rows + slot * row_bytes + p.plane_bytes + cb * p.slot_bytes, &p.tmA, &full_bar[slot], cb * CBLK, u.w0 + p.dw0, r,
+                                        u.n, 1);
+                        } else {
+                            tma_load_4d(smem_rows + slot * row_bytes + cb * p.slot_bytes, &p.tmA, &full_bar[slot], cb * CBLK, u.w0 + p.dw0, r, u.n);
+                        }
+                    }
                 }
             }
         }
@@ -188,6 +203,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
         // ------------------------------------------------------------------ MMA issuer
         if (elect_one()) {
             constexpr uint32_t idesc = make_idesc_f16(kRowTile, BLOCK_N);
+            constexpr uint32_t idesc2 = make_idesc_f16(kRowTile, 2 * BLOCK_N);
             const uint64_t desc_hi = make_kmajor_desc<CBLK>(0);  // everything but the start address
             const uint32_t rows_base = smem_u32(smem_rows), w_base = smem_u32(smem_w);
             uint32_t qbase = 0, wq = 0;
@@ -220,7 +236,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                     for (int th = 0; th < TAPS; ++th) slot_addr[th] = rows_base + ((qrow + th) % p.slots) * row_bytes;
 #pragma unroll
                     for (int s = 0; s < NSUB; ++s) {
-                        const uint32_t d_tmem = tmem_base + (acc * NSUB + s) * BLOCK_N;
+                        const uint32_t d_tmem = tmem_base + (acc * NSUB + s) * kAcc;
 #pragma unroll
                         for (int th = 0; th < TAPS; ++th) {
 #pragma unroll
@@ -231,8 +247,17 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                                     const int blk = ((s * TAPS + th) * TAPS + tw) * CBLOCKS + cb;
                                     const uint64_t da = desc_hi | static_cast<uint64_t>(((slot_addr[th] + cb * p.slot_bytes + (tw + s) * kPB) & 0x3FFFF) >> 4);
                                     const uint64_t db = desc_hi | static_cast<uint64_t>(((w_base + blk * p.wblock_bytes) & 0x3FFFF) >> 4);
+                                    if constexpr (SPLIT) {
+                                        const uint64_t dal = desc_hi | static_cast<uint64_t>(((slot_addr[th] + p.plane_bytes + cb * p.slot_bytes + (tw + s) * kPB) & 0x3FFFF) >> 4);
 #pragma unroll
-                                    for (int k = 0; k < CBLK / 16; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (th | tw | cb | k) != 0 ? 1u : 0u);
+                                        for (int k = 0; k < CBLK / 16; ++k) {
+                                            umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc2, (th | tw | cb | k) != 0 ? 1u : 0u);  // [main | cross]
+                                            umma_f16(d_tmem + BLOCK_N, dal + 2 * k, db + 2 * k, idesc, 1u);                         // cross += A_lo W_hi
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int k = 0; k < CBLK / 16; ++k) umma_f16(d_tmem, da + 2 * k, db + 2 * k, idesc, (th | tw | cb | k) != 0 ? 1u : 0u);
+                                    }
                                 }
                             }
                         }
@@ -266,7 +291,7 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                 tc_fence_after();
                 const int w = u.w0 + q4 * 32 + lane;
                 for (int s = 0; s < p.nsub; ++s) {
-                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + (acc * p.nsub + s) * BLOCK_N;
+                    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q4 * 32) << 16) + (acc * p.nsub + s) * kAcc;
                     const int phase = (p.nphase_a * p.nsub > 1) ? (u.a * 2 + s) : 0;
                     if constexpr (MODE == 0) {
 #pragma unroll 1
@@ -313,7 +338,15 @@ __global__ void __launch_bounds__(kRowThreads, 1) conv_row_kernel(const __grid_c
                         // head: ReLU(acc) [32 ch] -> fp32 1x1 conv to `classes` logits, NCHW fp32 store (unet.py:141)
                         uint32_t r[32];
                         tmem_ld_32x32(taddr, r);
-                        tmem_ld_wait();
+                        if constexpr (SPLIT) {
+                            uint32_t xr[32];
+                            tmem_ld_32x32(taddr + BLOCK_N, xr);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint((__uint_as_float(r[j]) + __uint_as_float(xr[j])) * p.acc_scale);
+                        } else {
+                            tmem_ld_wait();
+                        }
                         float v[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -362,16 +395,19 @@ using namespace rsb;
 struct rsb_rowconv_plan {
     RowKParams kp;
     int cblk, block_n, mode, grid, smem;
+    bool split;
 };
 
-template <int CBLK, int BLOCK_N, int MODE, int TAPS, int CBLOCKS, int NSUB>
+template <int CBLK, int BLOCK_N, int MODE, int TAPS, int CBLOCKS, int NSUB, bool SPLIT = false>
 static int launch_row(const rsb_rowconv_plan* plan, cudaStream_t stream) {
-    auto kern = conv_row_kernel<CBLK, BLOCK_N, MODE, TAPS, CBLOCKS, NSUB>;
-    static int attr_smem = 0;
-    if (plan->smem > attr_smem) {
+    auto kern = conv_row_kernel<CBLK, BLOCK_N, MODE, TAPS, CBLOCKS, NSUB, SPLIT>;
+    static int attr_smem[64] = {};  // per device
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (plan->smem > attr_smem[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, plan->smem);
         if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv_row)");
-        attr_smem = plan->smem;
+        attr_smem[dev] = plan->smem;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(plan->grid);
@@ -402,6 +438,10 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     if (d->mode == 1 && (d->Cout != 32 || d->nsub != 1 || d->nphase_a != 1 || d->head_classes < 1 || d->head_classes > 8 || !d->head_w || !d->head_b || !d->head_out))
         return set_error(RSB_E_INVALID, "rowconv: bad head arguments");
     if (d->mode == 0 && !d->out) return set_error(RSB_E_INVALID, "rowconv: null out");
+    const bool split = d->split != 0;
+    if (split && !(d->mode == 1 && d->cin == 32 && d->taps_h == 3 && d->src.plane > 0 && (d->src.plane * 2) % 16 == 0))
+        return set_error(RSB_E_INVALID, "rowconv: the strict-precision line buffer exists for the 3x3 32 -> 32 head layer only (needs src.plane)");
+    const int planes = split ? 2 : 1;
     int rc = rsb_device_ok();
     if (rc) return rc;
 
@@ -419,7 +459,9 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     kp.buf_w = kRowTile + d->taps_w + d->nsub - 2;
     const int pb = cblk * 2;
     kp.slot_bytes = ((kp.buf_w * pb + 1023) / 1024) * 1024;
-    kp.wblock_bytes = d->Cout * pb;
+    kp.wblock_bytes = planes * d->Cout * pb;
+    kp.plane_bytes = kp.slot_bytes * cblocks;
+    kp.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
     kp.Wt = d->Wt;
     kp.Ht = d->Ht;
     kp.Nt = d->Nt;
@@ -435,17 +477,18 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     const int swz = cblk * 2;  // 64-byte or 128-byte swizzle
     {
         const rsb_conv_src& s = d->src;
-        const uint64_t dims[4] = {(uint64_t)d->cin, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)s.N};
-        const uint64_t strides[3] = {(uint64_t)s.pitch_w * 2, (uint64_t)s.pitch_h * 2, (uint64_t)s.pitch_n * 2};
-        const uint32_t box[4] = {(uint32_t)cblk, (uint32_t)kp.buf_w, 1, 1};
-        rc = encode_tiled_f16(&kp.tmA, 4, s.ptr, dims, strides, box, swz);
+        const uint64_t dims[5] = {(uint64_t)d->cin, (uint64_t)s.W, (uint64_t)s.H, (uint64_t)s.N, 2};
+        const uint64_t strides[4] = {(uint64_t)s.pitch_w * 2, (uint64_t)s.pitch_h * 2, (uint64_t)s.pitch_n * 2, (uint64_t)s.plane * 2};
+        const uint32_t box[5] = {(uint32_t)cblk, (uint32_t)kp.buf_w, 1, 1, 1};  // strict: one plane per load (each lands 1024-aligned)
+        rc = encode_tiled_f16(&kp.tmA, split ? 5 : 4, s.ptr, dims, strides, box, swz);
     }
     if (!rc) {
         const int K = d->taps_h * d->taps_w * d->cin;
-        const uint64_t dims[2] = {(uint64_t)K, (uint64_t)d->nphase_a * d->nsub * d->Cout};
-        const uint64_t strides[1] = {(uint64_t)K * 2};
-        const uint32_t box[2] = {(uint32_t)cblk, (uint32_t)d->Cout};
-        rc = encode_tiled_f16(&kp.tmB, 2, d->weights, dims, strides, box, swz);
+        const uint64_t rows = (uint64_t)d->nphase_a * d->nsub * d->Cout;
+        const uint64_t dims[3] = {(uint64_t)K, rows, 2};
+        const uint64_t strides[2] = {(uint64_t)K * 2, rows * (uint64_t)K * 2};
+        const uint32_t box[3] = {(uint32_t)cblk, (uint32_t)d->Cout, 2};  // strict: [W_hi rows | W_lo rows] back to back
+        rc = encode_tiled_f16(&kp.tmB, split ? 3 : 2, d->weights, dims, strides, box, swz);
     }
     if (!rc && d->mode == 0) {
         const int sy = d->out_sy > 0 ? d->out_sy : 1, sx = d->out_sx > 0 ? d->out_sx : 1;
@@ -469,12 +512,13 @@ extern "C" int rsb_rowconv_plan_create(const rsb_rowconv_desc* d, rsb_rowconv_pl
     plan->cblk = cblk;
     plan->block_n = d->Cout;
     plan->mode = d->mode;
+    plan->split = split;
     // shared memory: weights + epilogue staging are fixed; the ring takes the rest. Small layers run several CTAs per SM
     // (each with its own ring) so that TMA latency and the single MMA-issuing thread of one CTA are hidden by the others.
     const int stage = d->mode == 0 ? 4 * 2 * 32 * (d->Cout >= 64 ? 64 : 32) * 2 : 0;
     const int fixed = d->nsub * d->taps_h * d->taps_w * cblocks * kp.wblock_bytes + stage + 512 + 1088 + 1024;
-    const int row_bytes = kp.slot_bytes * cblocks;
-    const int tmem_cols = 4 * d->Cout <= 128 ? 128 : 256;
+    const int row_bytes = kp.slot_bytes * cblocks * planes;
+    const int tmem_cols = 4 * planes * d->Cout <= 128 ? 128 : 256;
     int ctas = 1;
     for (int c = 3; c >= 2; --c) {
         if (c * tmem_cols <= 512 && fixed + (d->taps_h + 3) * row_bytes <= 232448 / c - 1024) {
@@ -517,6 +561,10 @@ extern "C" int rsb_rowconv_run(const rsb_rowconv_plan* plan, void* stream_) {
     cudaStream_t st = static_cast<cudaStream_t>(stream_);
     const RowKParams& k = plan->kp;
     const int key = ((((plan->cblk * 100 + plan->block_n) * 10 + plan->mode) * 10 + k.taps_h) * 10 + k.cblocks) * 10 + k.nsub;
+    if (plan->split) {
+        if (key == 32321311) return launch_row<32, 32, 1, 3, 1, 1, true>(plan, st);  // dec5 + final, strict precision
+        return set_error(RSB_E_INVALID, "rowconv: no strict-precision kernel instance for this layer");
+    }
     switch (key) {  // CBLK BLOCK_N MODE TAPS CBLOCKS NSUB
         case 32321311: return launch_row<32, 32, 1, 3, 1, 1>(plan, st);  // dec5 + final
         case 64321311: return launch_row<64, 32, 1, 3, 1, 1>(plan, st);

@@ -218,7 +218,7 @@ class RowConvOp:
 
 
 def make_rowconv_desc(src, cin, weights, bias, cout, tile_space, out, out_pitches, upsample=False, relu=True, head=None,
-                      out_offset_elems=0, rows_per_unit=0):
+                      out_offset_elems=0, rows_per_unit=0, split=False, acc_scale=1.0):
     """3x3 stride-1 conv (upsample=False) or the fused nearest-x2 + 3x3 (upsample=True: 2x2 taps, 4 phases) on the
     line-buffer kernel. weights: fp16 [phases*Cout][taps*cin] in the packed layout of pack_conv / pack_upsample_phases."""
     d = RowConvDesc()
@@ -228,7 +228,10 @@ def make_rowconv_desc(src, cin, weights, bias, cout, tile_space, out, out_pitche
     d.dh0 = d.dw0 = -1
     d.nsub = d.nphase_a = 2 if upsample else 1
     phases = 4 if upsample else 1
-    assert weights.dtype == torch.float16 and tuple(weights.shape) == (phases * cout, d.taps_h * d.taps_w * cin), tuple(weights.shape)
+    d.split = 1 if split else 0
+    d.acc_scale = acc_scale
+    wshape = (phases * cout, d.taps_h * d.taps_w * cin)
+    assert weights.dtype == torch.float16 and tuple(weights.shape) == ((2,) + wshape if split else wshape), tuple(weights.shape)
     d.weights = weights.data_ptr()
     d.bias = bias.data_ptr() if bias is not None else None
     d.Cout = cout
@@ -358,7 +361,9 @@ class UNetEngine:
         self.precision = precision or default_precision()
         assert self.precision in PRECISIONS, self.precision
         self.strict = self.precision == "strict"
-        # line-buffer kernel for the >= 128-pixel-wide, small-Cout layers (layer1 3x3, dec4, dec5 + final); single-plane only
+        # line-buffer kernel for the >= 128-pixel-wide, small-Cout layers (layer1 3x3, dec4, dec5 + final). In strict precision
+        # only dec5 + final has one (resident weights + a 2-plane row ring must fit in shared memory)
+        self.use_row_head = use_row
         self.use_row = use_row and not self.strict
         if not plan_only:
             _lib.require_device()
@@ -559,11 +564,12 @@ class UNetEngine:
         self.logits = self._buf(N, self.C, H, W, dtype=torch.float32)
         head_w = dev(sd["final.weight"].float().reshape(self.C, 32), torch.float32)
         head_b = dev(sd["final.bias"].float(), torch.float32)
-        if self.use_row and W >= 128:
+        if self.use_row_head and W >= 128:
             # the real pixels of the W-padded dec4 buffer as a dense view: column -1 / W are outside the view (zero fill)
-            src = ConvSrc(self.dec4.data_ptr() + 2 * 32, 32, Wq * 32, H * Wq * 32, 32, W, H, N)
-            self._add_row("dec5+final", make_rowconv_desc(src, 32, dev(pack_conv(w5), torch.float16), None, 32, (W, H, N), None, None,
-                                                          head=(head_w, head_b, self.logits, self.C)))
+            src = ConvSrc(self.dec4.data_ptr() + 2 * 32, 32, Wq * 32, H * Wq * 32, 32, W, H, N, self._plane(self.dec4))
+            w5p, w5scale = self._wts(pack_conv(w5))
+            self._add_row("dec5+final", make_rowconv_desc(src, 32, w5p, None, 32, (W, H, N), None, None,
+                                                          head=(head_w, head_b, self.logits, self.C), split=self.strict, acc_scale=w5scale))
         else:
             src = ConvSrc(self.dec4.data_ptr(), 32, Wq * 32, H * Wq * 32, 128, W, H, N, self._plane(self.dec4))
             segs = [(0, kh - 1, 0, 2) for kh in range(3)]

@@ -310,23 +310,29 @@ def row_up_case(N, lh, lw, cin, cout, device, seed=0, rows_per_unit=0):
     return Case("rowup_%dx%dx%d_%d-%d" % (N, lh, lw, cin, cout), desc, (xd, wp), out, lambda t: _out_nchw(t, (N, oH, oW, cout)), ref)
 
 
-def row_head_case(N, H, W, classes, device, seed=0, rows_per_unit=0):
+def row_head_case(N, H, W, classes, device, seed=0, rows_per_unit=0, split=False):
     g = torch.Generator().manual_seed(seed)
-    x = _rand((N, 32, H, W), g).half().float()
+    x = _rand((N, 32, H, W), g)
     w5 = _rand((32, 32, 3, 3), g, (2.0 / 288) ** 0.5)
     wf = _rand((classes, 32, 1, 1), g, 0.3)
     bf = _rand((classes,), g, 0.1)
-    xd = _nhwc_half(x, device)
-    wp = E.pack_conv(w5).half().to(device)
+    xd, x = _act_in(x, device, split)
+    scale = 1.0
+    if split:
+        wp, scale, _ = _wsplit(E.pack_conv(w5.double()), device)
+        w5 = w5.double()
+    else:
+        wp = E.pack_conv(w5).half().to(device)
+        w5 = w5.half().float()
     hw, hb = wf.reshape(classes, 32).contiguous().to(device), bf.to(device)
     logits = torch.zeros(N, classes, H, W, dtype=torch.float32, device=device)
-    desc = E.make_rowconv_desc(E._src_dense(xd, N, H, W, 32), 32, wp, None, 32, (W, H, N), None, None, head=(hw, hb, logits, classes),
-                               rows_per_unit=rows_per_unit)
+    desc = E.make_rowconv_desc(E._src_dense(xd, N, H, W, 32, _plane(xd, split)), 32, wp, None, 32, (W, H, N), None, None, head=(hw, hb, logits, classes),
+                               rows_per_unit=rows_per_unit, split=split, acc_scale=scale)
 
     def ref():
-        return F.conv2d(F.relu(F.conv2d(x, w5.half().float(), None, padding=1)), wf, bf)
+        return F.conv2d(F.relu(F.conv2d(x, w5, None, padding=1)), wf.to(x.dtype), bf.to(x.dtype)).float()
 
-    return Case("rowhead_%dx%dx%d_c%d" % (N, H, W, classes), desc, (xd, wp, hw, hb), logits, lambda t: t.float().cpu(), ref)
+    return Case("%srowhead_%dx%dx%d_c%d" % ("split_" if split else "", N, H, W, classes), desc, (xd, wp, hw, hb), logits, lambda t: t.float().cpu(), ref)
 
 
 def row_cases(device):
@@ -339,4 +345,13 @@ def row_cases(device):
         lambda: row_up_case(1, 8, 128, 64, 64, device, seed=36),
         lambda: row_head_case(2, 36, 192, 2, device, seed=37),                         # dec5 + final
         lambda: row_head_case(1, 16, 128, 6, device, seed=38, rows_per_unit=5),
+    ]
+
+
+def row_split_cases(device):
+    """strict-precision line buffer (dec5 + final): hi/lo planes in the row ring, N-concatenated MMAs"""
+    return [
+        lambda: row_head_case(2, 36, 192, 2, device, seed=37, split=True),
+        lambda: row_head_case(1, 16, 128, 6, device, seed=38, rows_per_unit=5, split=True),
+        lambda: row_head_case(1, 40, 300, 2, device, seed=39, split=True),   # partial last strip
     ]

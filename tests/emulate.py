@@ -128,22 +128,29 @@ def run_rowdesc(d):
     """CPU semantics of rsb_rowconv_run (line-buffer kernel): same arithmetic as run_desc, described by taps instead of segments"""
     nph = d.nphase_a * d.nsub
     K = d.taps_h * d.taps_w * d.cin
-    wts = _view(d.weights, (nph * d.Cout, K), (K, 1)).astype(np.float32)
+    split = bool(getattr(d, "split", 0))
+    wts = _pair(d.weights, nph * d.Cout * K if split else 0, (nph * d.Cout, K), (K, 1))
+    if not split:
+        wts = wts.astype(np.float32)
+    scale = np.float32(d.acc_scale if split and d.acc_scale != 0 else 1.0)
     bias = _view(d.bias, (d.Cout,), (1,), np.float32) if d.bias else None
     src = d.src
-    sv = _view(src.ptr, (src.N, src.H, src.W, d.cin), (src.pitch_n, src.pitch_h, src.pitch_w, 1))
+    sv = _pair(src.ptr, src.plane if split else 0, (src.N, src.H, src.W, d.cin), (src.pitch_n, src.pitch_h, src.pitch_w, 1))
+    if not split:
+        sv = sv.astype(np.float32)
     for a in range(d.nphase_a):
         for s_ in range(d.nsub):
-            acc = np.zeros((d.Nt, d.Ht, d.Wt, d.Cout), dtype=np.float32)
+            acc = np.zeros((d.Nt, d.Ht, d.Wt, d.Cout), dtype=np.float64 if split else np.float32)
             for th in range(d.taps_h):
                 for tw in range(d.taps_w):
                     hh = np.arange(d.Ht)[:, None] + d.dh0 + a + th
                     ww = np.arange(d.Wt)[None, :] + d.dw0 + s_ + tw
                     inb = (hh >= 0) & (hh < src.H) & (ww >= 0) & (ww < src.W)
-                    g = sv[:, np.clip(hh, 0, src.H - 1), np.clip(ww, 0, src.W - 1), :].astype(np.float32) * inb[None, :, :, None]
+                    g = sv[:, np.clip(hh, 0, src.H - 1), np.clip(ww, 0, src.W - 1), :] * inb[None, :, :, None]
                     k0 = (th * d.taps_w + tw) * d.cin
                     wseg = wts[(a * d.nsub + s_) * d.Cout:(a * d.nsub + s_ + 1) * d.Cout, k0:k0 + d.cin]
                     acc += np.tensordot(g[:d.Nt], wseg, axes=([3], [1]))
+            acc = acc.astype(np.float32) * scale
             if bias is not None:
                 acc += bias
             if d.relu:

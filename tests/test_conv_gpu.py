@@ -200,3 +200,21 @@ def test_row_conv_case_matches_cpu_reference(i, cuda_device):
         op.run(_lib.current_stream_ptr())
         torch.cuda.synchronize()
         assert (case.result() - ref).abs().max().item() <= tol, case.name
+
+
+@pytest.mark.parametrize("i", range(len(conv_cases.row_split_cases(None))))
+def test_row_split_case_matches_fp64_reference(i, cuda_device):
+    """strict-precision line-buffer kernel (dec5 + final): hi/lo row ring, [W_hi | W_lo] in one MMA + A_lo W_hi in a second"""
+    from robosat_b200.engine import RowConvOp
+
+    case = conv_cases.row_split_cases(cuda_device)[i]()
+    ref = case.ref()
+    op = RowConvOp(case.name, case.desc)
+    scale = max(1.0, ref.abs().max().item())
+    for _ in range(2):
+        case.out.zero_()
+        op.run(_lib.current_stream_ptr())
+        torch.cuda.synchronize()
+        err = (case.result() - ref).abs().max().item()
+        print("%s: max|err| %.3e (%.2e of range)" % (case.name, err, err / scale))
+        assert err <= 1e-5 * scale, case.name

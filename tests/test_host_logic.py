@@ -38,6 +38,26 @@ def test_row_conv_descriptor_semantics(i):
     assert (got - ref).abs().max().item() <= 6e-3 * max(1.0, ref.abs().max().item() / 8), case.name
 
 
+@pytest.mark.parametrize("i", range(len(conv_cases.row_split_cases("cpu"))))
+def test_row_split_descriptor_semantics(i):
+    case = conv_cases.row_split_cases("cpu")[i]()
+    emulate.run_rowdesc(case.desc)
+    got, ref = case.result(), case.ref()
+    assert (got - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item()), case.name
+
+
+def test_strict_plan_uses_the_line_buffer_for_the_head_only():
+    sd = synth.make_state_dict(2, seed=0)
+    eng = UNetEngine(sd, 2, 1, 64, 512, device="cpu", plan_only=True, precision="strict")
+    kinds = [(op[1].name, type(op[1]).__name__) for op in eng.ops if op[0] == "conv"]
+    assert [n for n, k in kinds if k == "RowConvOp"] == ["dec5+final"]
+    x = synth.normalize_tiles(synth.make_tiles_u8(1, 512, seed=1)[:, :64].contiguous())
+    got = emulate.run_engine(eng, x)
+    with torch.no_grad():
+        ref = unet_oracle.unet_forward(sd, x)
+    assert ((got - ref).pow(2).sum().sqrt() / ref.pow(2).sum().sqrt()).item() < 2e-5
+
+
 def test_engine_graph_with_line_buffer_layers_matches_oracle():
     """512-wide input: layer1 3x3, dec4 and dec5 + final take the line-buffer plan; same result as the oracle"""
     sd = synth.make_state_dict(2, seed=0)
