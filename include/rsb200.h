@@ -311,6 +311,17 @@ int rsb_bn_finalize(const double* sums, const float* gamma, const float* beta, f
 int rsb_bn_stats_finalize(const void* z, double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                           int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int64_t M, int32_t C, float eps,
                           float momentum, void* stream);
+/* "_chained" variants (what the training plan uses): the same arithmetic, but (a) launched with programmatic stream serialization
+ * so a chain of small kernels does not pay a full launch gap per link, and (b) without the per-call memset: `sums` must be
+ * zero-initialised ONCE by the caller and is left zeroed by the reduction's last block. */
+int rsb_bn_stats_finalize_chained(const void* z, double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                  int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int64_t M, int32_t C, float eps,
+                                  float momentum, void* stream);
+int rsb_bn_apply_chained(const void* z, const float* scale, const float* shift, const void* residual, void* y, int64_t M, int32_t C,
+                         int32_t relu, void* stream);
+int rsb_bn_backward_chained(const void* dy, const void* y, const void* z, const float* mean, const float* invstd, const float* gamma,
+                            const float* mask_scale, const float* mask_shift, double* sums, void* dz, void* g_out, float* dgamma, float* dbeta,
+                            float inv_loss_scale, int64_t M, int32_t C, void* stream);
 /* y = relu?(z*scale + shift (+ residual)) */
 int rsb_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y, int64_t M, int32_t C,
                  int32_t relu, void* stream);

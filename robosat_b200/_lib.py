@@ -156,6 +156,9 @@ SIGNATURES = {
     "rsb_adam_step_guarded": (ctypes.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _i32, _vp, _vp]),
     "rsb_bn_stats": (ctypes.c_int, [_vp, _vp, _i64, _i32, _vp]),
     "rsb_bn_stats_finalize": (ctypes.c_int, [_vp] * 11 + [_i64, _i32, _f32, _f32, _vp]),
+    "rsb_bn_stats_finalize_chained": (ctypes.c_int, [_vp] * 11 + [_i64, _i32, _f32, _f32, _vp]),
+    "rsb_bn_apply_chained": (ctypes.c_int, [_vp] * 5 + [_i64, _i32, _i32, _vp]),
+    "rsb_bn_backward_chained": (ctypes.c_int, [_vp] * 13 + [_f32, _i64, _i32, _vp]),
     "rsb_bn_finalize": (ctypes.c_int, [_vp] * 10 + [_i32, _i64, _f32, _f32, _vp]),
     "rsb_bn_apply": (ctypes.c_int, [_vp] * 5 + [_i64, _i32, _i32, _vp]),
     "rsb_bn_backward": (ctypes.c_int, [_vp] * 13 + [_f32, _i64, _i32, _vp]),

@@ -28,6 +28,31 @@ static inline unsigned reduce_blocks(int64_t M, int C) {
     return tr_blocks((M + rows_per_iter * 4 - 1) / (rows_per_iter * 4), 1, 148 * 8);
 }
 
+// Programmatic dependent launch: the training step is a chain of ~650 mostly small kernels, so the launch gap (scheduling the
+// next grid only after the previous one has drained) is a visible part of it. Chained kernels are launched with the
+// programmatic-stream-serialization attribute; each lets its successor be scheduled as soon as its own blocks are resident
+// (launch_dependents) and touches global memory only after the predecessor has completed and flushed (wait). For a normal
+// launch both instructions are no-ops.
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chained(bool chained, void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = chained ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ void load8(const __half* p, float (&v)[8]) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(p));
     const __half2* h = reinterpret_cast<const __half2*>(&q);
@@ -73,6 +98,7 @@ struct RedTail {
     float* dgamma;
     float* dbeta;
     float eps, momentum, inv_scale;
+    int self_clean;  // the last block leaves the accumulator slots and the arrival counter zeroed for the next call (no memset launch)
 };
 
 __device__ __forceinline__ double red_slots(const double* sums, int which, int c, int C) {
@@ -92,6 +118,7 @@ __global__ void __launch_bounds__(256, 3) channel_reduce_kernel(const __half* __
                                                              const float* __restrict__ msc = nullptr, const float* __restrict__ msh = nullptr) {
     __shared__ float sh0[256 * 8];
     __shared__ float sh1[256 * 8];
+    pdl_sync();
     const int tpr = C / 8;
     const int rows_per_iter = 256 / tpr;
     const int col = (threadIdx.x % tpr) * 8;
@@ -211,7 +238,15 @@ __global__ void __launch_bounds__(256, 3) channel_reduce_kernel(const __half* __
             coef[C + c] = -ga * is * is * mgz;                        // B
             coef[2 * C + c] = -ga * is * mg + ga * is * is * mu * mgz;  // D
         }
+        if (tail.self_clean) {
+#pragma unroll
+            for (int sl = 0; sl < kRedSlots; ++sl) {
+                sums[(static_cast<int64_t>(sl) * 2 + 0) * C + c] = 0.0;
+                sums[(static_cast<int64_t>(sl) * 2 + 1) * C + c] = 0.0;
+            }
+        }
     }
+    if (tail.self_clean && threadIdx.x == 0) *reinterpret_cast<unsigned*>(sums + static_cast<int64_t>(kRedSlots) * 2 * C) = 0u;
 }
 
 // mean / invstd / folded scale+shift from the batch sums, running-stat update (momentum, unbiased variance)
@@ -242,6 +277,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float*
 // thread keeps the same 8 channels for its whole loop and holds their coefficients in registers.
 __global__ void bn_apply_kernel(const __half* __restrict__ z, const float* __restrict__ scale, const float* __restrict__ shift,
                                 const __half* __restrict__ res, __half* __restrict__ y, int64_t M, int C, int relu) {
+    pdl_sync();
     const int C8 = C / 8;
     const int64_t total = M * C8;
     const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -273,6 +309,7 @@ template <bool ZMASK>
 __global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, const __half* __restrict__ z,
                                                               const float* __restrict__ coef, __half* __restrict__ dz, __half* __restrict__ g_out,
                                                               int64_t M, int C, const float* __restrict__ msc, const float* __restrict__ msh) {
+    pdl_sync();
     const int C8 = C / 8;
     const int64_t total = M * C8;
     const int64_t i0 = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -327,6 +364,7 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const __half* __re
 // out = a * (y > 0) (+ b): ReLU backward with an optional second gradient stream (skip connection fan-in)
 __global__ void relu_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__ b, const __half* __restrict__ y,
                                 __half* __restrict__ out, int64_t total8) {
+    pdl_sync();
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         float g[8], yy[8];
         load8(a + i * 8, g);
@@ -634,14 +672,16 @@ extern "C" int rsb_bn_stats(const void* z, double* sums, int64_t M, int32_t C, v
     return RSB_OK;
 }
 
-extern "C" int rsb_bn_stats_finalize(const void* z, double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
-                                     int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int64_t M, int32_t C, float eps,
-                                     float momentum, void* stream) {
+static int bn_stats_finalize_impl(const void* z, double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                  int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int64_t M, int32_t C, float eps,
+                                  float momentum, void* stream, bool chained) {
     if (!z || !sums || !gamma || !beta || !mean || !invstd || !scale || !shift || M <= 0 || bad_c(C) || C < 64)
         return set_error(RSB_E_INVALID, "bn_stats_finalize: bad arguments (C in 64..2048, power of two)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * kRedSlots + 2), st);
-    if (e != cudaSuccess) return set_cuda_error(e, "bn_stats_finalize memset");
+    if (!chained) {
+        cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * kRedSlots + 2), st);
+        if (e != cudaSuccess) return set_cuda_error(e, "bn_stats_finalize memset");
+    }
     RedTail tail = {};
     tail.gamma = gamma;
     tail.beta = beta;
@@ -654,9 +694,26 @@ extern "C" int rsb_bn_stats_finalize(const void* z, double* sums, const float* g
     tail.shift = shift;
     tail.eps = eps;
     tail.momentum = momentum;
-    channel_reduce_kernel<0><<<reduce_blocks(M, C), 256, 0, st>>>(static_cast<const __half*>(z), nullptr, nullptr, sums, M, C, tail);
-    RSB_LAUNCH_CHECK("bn_stats_finalize launch");
+    tail.self_clean = chained ? 1 : 0;
+    cudaError_t e = launch_chained(chained, channel_reduce_kernel<0, false>, reduce_blocks(M, C), 256, st, static_cast<const __half*>(z),
+                                   static_cast<const __half*>(nullptr), static_cast<const __half*>(nullptr), sums, M, static_cast<int>(C), tail,
+                                   static_cast<const float*>(nullptr), static_cast<const float*>(nullptr));
+    if (e != cudaSuccess) return set_cuda_error(e, "bn_stats_finalize launch");
     return RSB_OK;
+}
+
+extern "C" int rsb_bn_stats_finalize(const void* z, double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                     int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int64_t M, int32_t C, float eps,
+                                     float momentum, void* stream) {
+    return bn_stats_finalize_impl(z, sums, gamma, beta, running_mean, running_var, num_batches, mean, invstd, scale, shift, M, C, eps, momentum, stream,
+                                  false);
+}
+
+extern "C" int rsb_bn_stats_finalize_chained(const void* z, double* sums, const float* gamma, const float* beta, float* running_mean,
+                                             float* running_var, int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift,
+                                             int64_t M, int32_t C, float eps, float momentum, void* stream) {
+    return bn_stats_finalize_impl(z, sums, gamma, beta, running_mean, running_var, num_batches, mean, invstd, scale, shift, M, C, eps, momentum, stream,
+                                  true);
 }
 
 extern "C" int rsb_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
@@ -670,25 +727,38 @@ extern "C" int rsb_bn_finalize(const double* sums, const float* gamma, const flo
     return RSB_OK;
 }
 
-extern "C" int rsb_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y, int64_t M, int32_t C,
-                            int32_t relu, void* stream) {
+static int bn_apply_impl(const void* z, const float* scale, const float* shift, const void* residual, void* y, int64_t M, int32_t C, int32_t relu,
+                         void* stream, bool chained) {
     if (!z || !scale || !shift || !y || M <= 0 || C <= 0 || (C % 8)) return set_error(RSB_E_INVALID, "bn_apply: bad arguments");
-    bn_apply_kernel<<<tr_blocks(M * (C / 8), 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __half*>(z), scale, shift, static_cast<const __half*>(residual), static_cast<__half*>(y), M, C, relu);
-    RSB_LAUNCH_CHECK("bn_apply launch");
+    cudaError_t e = launch_chained(chained, bn_apply_kernel, tr_blocks(M * (C / 8), 256), 256, static_cast<cudaStream_t>(stream),
+                                   static_cast<const __half*>(z), scale, shift, static_cast<const __half*>(residual), static_cast<__half*>(y), M,
+                                   static_cast<int>(C), static_cast<int>(relu));
+    if (e != cudaSuccess) return set_cuda_error(e, "bn_apply launch");
     return RSB_OK;
 }
 
-extern "C" int rsb_bn_backward(const void* dy, const void* y, const void* z, const float* mean, const float* invstd, const float* gamma,
-                               const float* mask_scale, const float* mask_shift, double* sums, void* dz, void* g_out, float* dgamma, float* dbeta,
-                               float inv_loss_scale, int64_t M, int32_t C, void* stream) {
+extern "C" int rsb_bn_apply(const void* z, const float* scale, const float* shift, const void* residual, void* y, int64_t M, int32_t C,
+                            int32_t relu, void* stream) {
+    return bn_apply_impl(z, scale, shift, residual, y, M, C, relu, stream, false);
+}
+
+extern "C" int rsb_bn_apply_chained(const void* z, const float* scale, const float* shift, const void* residual, void* y, int64_t M, int32_t C,
+                                    int32_t relu, void* stream) {
+    return bn_apply_impl(z, scale, shift, residual, y, M, C, relu, stream, true);
+}
+
+static int bn_backward_impl(const void* dy, const void* y, const void* z, const float* mean, const float* invstd, const float* gamma,
+                            const float* mask_scale, const float* mask_shift, double* sums, void* dz, void* g_out, float* dgamma, float* dbeta,
+                            float inv_loss_scale, int64_t M, int32_t C, void* stream, bool chained) {
     if (!dy || !z || !mean || !invstd || !gamma || !sums || !dz || !dgamma || !dbeta || M <= 0 || bad_c(C) || C < 64)
         return set_error(RSB_E_INVALID, "bn_backward: bad arguments");
     if ((mask_scale != nullptr) != (mask_shift != nullptr) || (mask_scale && y))
         return set_error(RSB_E_INVALID, "bn_backward: pass either y, or mask_scale + mask_shift, or neither");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * kRedSlots + 2), st);
-    if (e != cudaSuccess) return set_cuda_error(e, "bn_backward memset");
+    if (!chained) {
+        cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * kRedSlots + 2), st);
+        if (e != cudaSuccess) return set_cuda_error(e, "bn_backward memset");
+    }
     RedTail tail = {};
     tail.gamma = gamma;
     tail.mean = const_cast<float*>(mean);
@@ -696,22 +766,41 @@ extern "C" int rsb_bn_backward(const void* dy, const void* y, const void* z, con
     tail.dgamma = dgamma;
     tail.dbeta = dbeta;
     tail.inv_scale = inv_loss_scale;
+    tail.self_clean = chained ? 1 : 0;
     const __half* dyh = static_cast<const __half*>(dy);
     const __half* yh = static_cast<const __half*>(y);
     const __half* zh = static_cast<const __half*>(z);
     const float* coef = reinterpret_cast<const float*>(sums + static_cast<int64_t>(kRedSlots) * 2 * C + 2);
     const unsigned ablocks = tr_blocks((M * (C / 8) + 1) / 2, 256);
+    const __half* nullh = nullptr;
+    const float* nullf = nullptr;
+    cudaError_t e;
     if (mask_scale) {
-        channel_reduce_kernel<1, true><<<reduce_blocks(M, C), 256, 0, st>>>(dyh, nullptr, zh, sums, M, C, tail, mask_scale, mask_shift);
-        bn_bwd_apply_kernel<true><<<ablocks, 256, 0, st>>>(dyh, nullptr, zh, coef, static_cast<__half*>(dz), static_cast<__half*>(g_out), M, C,
-                                                            mask_scale, mask_shift);
+        e = launch_chained(chained, channel_reduce_kernel<1, true>, reduce_blocks(M, C), 256, st, dyh, nullh, zh, sums, M, static_cast<int>(C), tail, mask_scale,
+                           mask_shift);
+        if (e == cudaSuccess)
+            e = launch_chained(chained, bn_bwd_apply_kernel<true>, ablocks, 256, st, dyh, nullh, zh, coef, static_cast<__half*>(dz), static_cast<__half*>(g_out),
+                               M, static_cast<int>(C), mask_scale, mask_shift);
     } else {
-        channel_reduce_kernel<1, false><<<reduce_blocks(M, C), 256, 0, st>>>(dyh, yh, zh, sums, M, C, tail);
-        bn_bwd_apply_kernel<false><<<ablocks, 256, 0, st>>>(dyh, yh, zh, coef, static_cast<__half*>(dz), static_cast<__half*>(g_out), M, C, nullptr,
-                                                             nullptr);
+        e = launch_chained(chained, channel_reduce_kernel<1, false>, reduce_blocks(M, C), 256, st, dyh, yh, zh, sums, M, static_cast<int>(C), tail, nullf, nullf);
+        if (e == cudaSuccess)
+            e = launch_chained(chained, bn_bwd_apply_kernel<false>, ablocks, 256, st, dyh, yh, zh, coef, static_cast<__half*>(dz), static_cast<__half*>(g_out),
+                               M, static_cast<int>(C), nullf, nullf);
     }
-    RSB_LAUNCH_CHECK("bn_backward launch");
+    if (e != cudaSuccess) return set_cuda_error(e, "bn_backward launch");
     return RSB_OK;
+}
+
+extern "C" int rsb_bn_backward(const void* dy, const void* y, const void* z, const float* mean, const float* invstd, const float* gamma,
+                               const float* mask_scale, const float* mask_shift, double* sums, void* dz, void* g_out, float* dgamma, float* dbeta,
+                               float inv_loss_scale, int64_t M, int32_t C, void* stream) {
+    return bn_backward_impl(dy, y, z, mean, invstd, gamma, mask_scale, mask_shift, sums, dz, g_out, dgamma, dbeta, inv_loss_scale, M, C, stream, false);
+}
+
+extern "C" int rsb_bn_backward_chained(const void* dy, const void* y, const void* z, const float* mean, const float* invstd, const float* gamma,
+                                       const float* mask_scale, const float* mask_shift, double* sums, void* dz, void* g_out, float* dgamma,
+                                       float* dbeta, float inv_loss_scale, int64_t M, int32_t C, void* stream) {
+    return bn_backward_impl(dy, y, z, mean, invstd, gamma, mask_scale, mask_shift, sums, dz, g_out, dgamma, dbeta, inv_loss_scale, M, C, stream, true);
 }
 
 extern "C" int rsb_relu_backward(const void* a, const void* b, const void* y, void* out, int64_t n, void* stream) {
