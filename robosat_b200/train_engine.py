@@ -25,6 +25,9 @@ import torch
 
 from robosat_b200 import _lib
 from robosat_b200._lib import ConvSrc
+
+# BatchNorm kernels chained by programmatic dependent launch, accumulators cleaned by the kernels themselves (no memset launches)
+BN_CHAINED = os.environ.get("RSB_BN_CHAINED", "0") == "1"
 from robosat_b200.engine import ConvOp, _src_dense, _src_parity, make_conv_desc
 
 RESNET50_BLOCKS = (3, 4, 6, 3)
@@ -571,7 +574,7 @@ class UNetTrainEngine:
                 # batch sums + (in the reduction's last block) statistics, folded scale/shift and the running-stat update
                 b = op[1]
                 pf = b.prefix
-                _lib.check(lib.rsb_bn_stats_finalize_chained(b.z.data_ptr(), b.sums.data_ptr(), P[pf + ".weight"].data_ptr(), P[pf + ".bias"].data_ptr(),
+                _lib.check((lib.rsb_bn_stats_finalize_chained if BN_CHAINED else lib.rsb_bn_stats_finalize)(b.z.data_ptr(), b.sums.data_ptr(), P[pf + ".weight"].data_ptr(), P[pf + ".bias"].data_ptr(),
                                                      P[pf + ".running_mean"].data_ptr(), P[pf + ".running_var"].data_ptr(),
                                                      P[pf + ".num_batches_tracked"].data_ptr(), b.mean.data_ptr(), b.invstd.data_ptr(),
                                                      b.scale.data_ptr(), b.shift.data_ptr(), b.M, b.C, BN_EPS, BN_MOMENTUM, st), "rsb_bn_stats_finalize_chained")
@@ -579,14 +582,14 @@ class UNetTrainEngine:
                 pass  # fused into the bn_stats launch (kept as an op for the CPU emulation of the plan)
             elif k == "bn_apply":
                 _, b, res, y, relu = op
-                _lib.check(lib.rsb_bn_apply_chained(b.z.data_ptr(), b.scale.data_ptr(), b.shift.data_ptr(), res.data_ptr() if res is not None else None,
+                _lib.check((lib.rsb_bn_apply_chained if BN_CHAINED else lib.rsb_bn_apply)(b.z.data_ptr(), b.scale.data_ptr(), b.shift.data_ptr(), res.data_ptr() if res is not None else None,
                                             y.data_ptr(), b.M, b.C, 1 if relu else 0, st), "rsb_bn_apply")
             elif k == "bn_bwd":
                 _, b, dy, y, dz, g = op
                 pf = b.prefix
                 # y = half(relu(z*scale + shift)) with no identity branch: the mask is re-derived from z, y is not read
                 zmask = y is not None and getattr(b, "plain_relu_y", None) is y
-                _lib.check(lib.rsb_bn_backward_chained(dy.data_ptr(), y.data_ptr() if (y is not None and not zmask) else None, b.z.data_ptr(),
+                _lib.check((lib.rsb_bn_backward_chained if BN_CHAINED else lib.rsb_bn_backward)(dy.data_ptr(), y.data_ptr() if (y is not None and not zmask) else None, b.z.data_ptr(),
                                                b.mean.data_ptr(), b.invstd.data_ptr(), P[pf + ".weight"].data_ptr(),
                                                b.scale.data_ptr() if zmask else None, b.shift.data_ptr() if zmask else None,
                                                b.sums.data_ptr(), dz.data_ptr(), g.data_ptr() if g is not None else None,
