@@ -27,7 +27,8 @@ def make_app(predictor, url_template, token, size, session=None):
     from flask import Flask, abort, render_template, send_file
     from PIL import Image
 
-    app = Flask("robosat.tools.serve")
+    # the page template ships with this package (robosat_b200/tools/templates/map.html); the tile route does not need it
+    app = Flask(__name__, template_folder=os.path.join(os.path.dirname(os.path.abspath(__file__)), "templates"))
 
     @app.route("/")
     def index():

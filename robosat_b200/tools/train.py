@@ -97,6 +97,11 @@ def get_dataset_loaders(model, dataset, workers, rank=0, world=1):
 
     target_size = (model["common"]["image_size"],) * 2
     batch_size = model["common"]["batch_size"]
+    if world > 1 and os.environ.get("RSB_BATCH_PER_GPU", "0") != "1":
+        # `batch_size` of the TOML is the GLOBAL batch, split over the GPUs like nn.DataParallel's scatter does in the reference
+        # (train.py:69,180), so lr / logged losses / dropped ragged tails stay comparable for the same configuration;
+        # RSB_BATCH_PER_GPU=1 gives every rank the full batch_size instead (BASELINE cfg 5 states its batch per GPU).
+        batch_size = max(1, batch_size // world)
     path = dataset["common"]["dataset"]
     mean, std = [0.485, 0.456, 0.406], [0.229, 0.224, 0.225]
     if DEVICE_AUGMENT:
