@@ -214,10 +214,10 @@ def run_reference(args, rank):
     # DataParallel calls module.to(device)), so the GPUs are hidden from THIS process before torch initialises CUDA -- exactly
     # the situation of `cuda = false` on a GPU-less host (predict.py:47-63), where DataParallel is a pass-through.
     os.environ["CUDA_VISIBLE_DEVICES"] = ""
-    # a step is a bounded sample of the workload's batch: up to its 32 tiles, shrunk so that the whole run stays within ~640
-    # tiles (3-4 minutes at the 3-6 tiles/s the host cores reach; the per-tile CPU rate does not depend on the batch size
+    # a step is a bounded sample of the workload's batch: up to its 32 tiles, shrunk so that the whole run stays within ~400
+    # tiles (about 3 minutes at the 2-3 tiles/s the host cores reach; the per-tile CPU rate does not depend on the batch size
     # beyond a few tiles). The sample actually used is stated in cpu_baseline.sample.
-    per_step = args.tiles_per_step or max(1, min(BATCH, 640 // max(1, args.steps + args.warmup)))
+    per_step = args.tiles_per_step or max(1, min(BATCH, 400 // max(1, args.steps + args.warmup)))
     cb, s_per_step = cpu_reference_leg(args.steps, args.warmup, per_step)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "tiles/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3, "higher_is_better": True, "scaling": "weak",
