@@ -483,24 +483,45 @@ def cfg4_leg(dev, rank, world, dist, sd, tiles_per_gpu, batch=32, tile=512, over
     root = os.environ.get("RSB_CFG4_DIR") or os.path.join(tempfile.gettempdir(), "rsb_cfg4_%s" % os.environ.get("MASTER_PORT", "single"))
     tiles_dir, probs_dir = os.path.join(root, "tiles"), os.path.join(root, "probs")
     cols = max(1, tiles_per_gpu // 32)  # 32 rows (y) x `cols` columns (x) per rank: shard_range on the (z, x, y)-sorted list = this block
-    if rank == 0:
-        shutil.rmtree(root, ignore_errors=True)
-        os.makedirs(tiles_dir, exist_ok=True)
-    if world > 1:
-        dist.barrier()
+    def all_ok(ok, what):
+        """a failure on ONE rank (disk full, bad tile) must not leave the others waiting in a collective: every phase ends
+        with an all-reduce of an ok flag and all ranks leave together"""
+        flag = torch.tensor([1.0 if ok else 0.0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() < 1.0:
+            if rank == 0:
+                shutil.rmtree(root, ignore_errors=True)
+            raise RuntimeError("cfg4 leg: %s failed on at least one rank%s" % (what, "" if ok else " (this one: %s)" % err[0]))
+
+    err = [None]
+    try:
+        if rank == 0:
+            shutil.rmtree(root, ignore_errors=True)
+            os.makedirs(tiles_dir, exist_ok=True)
+    except Exception as exc:
+        err[0] = repr(exc)
+    all_ok(err[0] is None, "creating the scratch directory")
     threads = max(4, host_threads() // world)
     t0 = time.perf_counter()
-    synth.write_slippy_tiles(tiles_dir, 18, range(1000 + rank * cols, 1000 + (rank + 1) * cols), range(2000, 2032), size=tile, seed=7 + rank, workers=threads)
+    try:
+        synth.write_slippy_tiles(tiles_dir, 18, range(1000 + rank * cols, 1000 + (rank + 1) * cols), range(2000, 2032), size=tile, seed=7 + rank, workers=threads)
+    except Exception as exc:
+        err[0] = repr(exc)
     gen_s = time.perf_counter() - t0
     args = ap.Namespace(batch_size=batch, overlap=overlap, tile_size=tile, workers=0, tiles=tiles_dir, probs=probs_dir)
     os.environ["RSB_QUIET"] = "1"
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    all_ok(err[0] is None, "writing the synthetic tiles")  # doubles as the barrier before the timed region
     t0 = time.perf_counter()
-    st = run_shard(rank, world, args, dev, sd, CLASSES, stats={})
-    torch.cuda.synchronize()
+    st = None
+    try:
+        st = run_shard(rank, world, args, dev, sd, CLASSES, stats={})
+        torch.cuda.synchronize()
+    except Exception as exc:
+        err[0] = repr(exc)
     mine = time.perf_counter() - t0
+    all_ok(st is not None, "the shard loop")
     keys = ["wall_s", "decode_wait_s", "gpu_wait_s", "png_drain_s", "png_cpu_s", "setup_s"]
     vec = torch.tensor([mine] + [float(st.get(k, 0.0)) for k in keys] + [float(st["tiles"])], device=dev, dtype=torch.float64)
     mx = vec.clone()
@@ -641,7 +662,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training legs (configs[2], configs[4])")
     ap.add_argument("--no-cfg4", action="store_true", help="skip the slippy-map directory leg (configs[3])")
     ap.add_argument("--no-extras", action="store_true", help="headline + fast mode only")
-    ap.add_argument("--cfg4-tiles", type=int, default=1024, help="tiles per GPU in the synthetic slippy-map directory")
+    ap.add_argument("--cfg4-tiles", type=int, default=0, help="tiles per GPU in the synthetic slippy-map directory (0: 1024 up to 2 GPUs, 512 beyond)")
     ap.add_argument("--tiles-per-step", type=int, default=0, help="(--impl reference) tiles per step instead of the automatic bounded sample")
     ap.add_argument("--layers-out", default=None, help="write the per-layer timing tables (JSON) here (_strict / _fast suffix)")
     args = ap.parse_args()
@@ -682,7 +703,9 @@ def main():
             extras["train_cfg5"] = guarded(train_leg, dev, rank, world, dist, 6, 1024, 8, 5, 3,
                                            "rs train: ResNet50-UNet, 6-class, 3x1024x1024 synthetic, batch=8/GPU, data parallel over %dxB200 NVLink" % world)
         if not args.no_cfg4:
-            extras["cfg4"] = guarded(cfg4_leg, dev, rank, world, dist, sd, args.cfg4_tiles)
+            # 1 024 tiles (0.7 GB of PNGs) per GPU up to two GPUs, 512 beyond: the scratch directory lives under the temp dir
+            per_gpu = args.cfg4_tiles if args.cfg4_tiles > 0 else (1024 if world <= 2 else 512)
+            extras["cfg4"] = guarded(cfg4_leg, dev, rank, world, dist, sd, per_gpu)
 
     line = None
     if rank == 0:

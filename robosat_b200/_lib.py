@@ -175,11 +175,27 @@ SIGNATURES = {
     "rsb_wgrad_plan_set_scratch": (ctypes.c_int, [_vp, _vp, _i64]),
     "rsb_wgrad_plan_destroy": (None, [_vp]),
     "rsb_wgrad_run": (ctypes.c_int, [_vp, _vp]),
+}
+
+DEBUG_SIGNATURES = {  # librsb200_debug.so (include/rsb200_debug.h): bring-up probes, used by scripts/ only
     "rsb_debug_umma": (ctypes.c_int, [_vp, _i32, _i32, _vp, _vp] + [_i32] * 8 + [_vp]),
     "rsb_debug_mma_rate": (ctypes.c_int, [_vp] + [_i32] * 5 + [_vp]),
 }
 
 _lib = None
+_debug_lib = None
+
+
+def load_debug():
+    """the bring-up probe library (not part of the product): scripts/gpu_probe_umma.py, scripts/gpu_mma_rate.py"""
+    global _debug_lib
+    if _debug_lib is None:
+        lib = ctypes.CDLL(os.path.join(_HERE, "librsb200_debug.so"))
+        for name, (res, args) in DEBUG_SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _debug_lib = lib
+    return _debug_lib
 
 
 def load():

@@ -11,6 +11,7 @@
 #include <cuda_fp16.h>
 
 #include "../../include/rsb200.h"
+#include "../../include/rsb200_debug.h"
 #include "rsb_host.h"
 #include "rsb_ptx.cuh"
 

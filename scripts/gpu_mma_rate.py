@@ -11,7 +11,7 @@ for grid in (2, 148):
         for bn in (64, 128, 256):
             for flags in (0, 1, 2):
                 out.zero_()
-                _lib.check(lib.rsb_debug_mma_rate(out.data_ptr(), grid, pair, bn, 512, flags, st), "rate")
+                _lib.check(_lib.load_debug().rsb_debug_mma_rate(out.data_ptr(), grid, pair, bn, 512, flags, st), "rate")
                 torch.cuda.synchronize()
                 v = out[:grid:2 if pair else 1]
                 print("grid=%3d pair=%d N=%3d %-12s cycles/MMA min %.1f mean %.1f max %.1f" % (

@@ -18,7 +18,7 @@ st = _lib.current_stream_ptr()
 
 def run(**kw):
     out.zero_()
-    rc = lib.rsb_debug_umma(kw["a"].data_ptr(), kw["a"].shape[0], kw["a"].shape[1], Bd.data_ptr(), out.data_ptr(), kw["mode"], kw["a_rows"],
+    rc = _lib.load_debug().rsb_debug_umma(kw["a"].data_ptr(), kw["a"].shape[0], kw["a"].shape[1], Bd.data_ptr(), out.data_ptr(), kw["mode"], kw["a_rows"],
                             kw["a_blocks"], kw.get("row_offset", 0), kw.get("base_offset", 0), kw.get("lbo", 0), kw.get("sbo", 0),
                             kw.get("k_step", 0), st)
     if rc:
