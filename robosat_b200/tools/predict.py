@@ -107,10 +107,13 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
     palette = continuous_palette_for_color("pink", 256)
     # host cores of this rank, split between the PNG-encode pool and the decode pool (both run GIL-free C code)
     cores = max(2, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)) // max(world, 1))
-    # The codec threads are busy-looping C++ threads: leave the launching (main) thread and the driver's threads two cores, and
-    # do not take more than the GPU can consume (2 400 tiles/s x ~10 ms of decode + encode per tile = ~24 busy threads); with
-    # every hardware thread occupied the main thread was descheduled and the device ran empty (profiles/r2_cfg4.md)
-    pool_threads = int(os.environ.get("RSB_PNG_THREADS", "0")) or max(2, min(24, (cores - 2) // 2))
+    # The codec threads are busy C++ threads: leave the launching (main) thread and the driver's threads two cores and do not take
+    # more than the GPU can consume (2 400 tiles/s x ~7 ms of decode + encode per tile = ~18 busy threads); with every hardware
+    # thread occupied the main thread was descheduled and the device ran empty (profiles/r2_cfg4.md). Decoding a 512x512 RGB tile
+    # costs ~5.6 ms, encoding a probability mask 1-4 ms: two thirds of the budget decode, one third encodes.
+    budget = max(3, min(36, cores - 2))
+    pool_threads = int(os.environ.get("RSB_PNG_THREADS", "0")) or max(1, budget // 3)
+    default_decode_threads = int(os.environ.get("RSB_DECODE_THREADS", "0")) or max(2, budget - budget // 3)
     st.update(pool_threads=pool_threads, gpu_wait_s=0.0, png_cpu_s=0.0)
 
     def progress(it, total):
@@ -165,7 +168,7 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
         lo, hi = shard_range(len(order), rank, world)
         mine = order[lo:hi]
         capacity = max(9 * args.batch_size, int(os.environ.get("RSB_TILE_CACHE", "2048")))
-        decode_threads = args.workers if args.workers > 0 else pool_threads
+        decode_threads = args.workers if args.workers > 0 else default_decode_threads
         cache = DeviceTileCache(index, args.tile_size, capacity, device=device, workers=decode_threads)
         stitcher = HaloStitcher(cache, args.overlap, args.batch_size)
         predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device)
