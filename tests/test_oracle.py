@@ -104,3 +104,33 @@ def test_focal_and_miou_oracles_match_reference():
             ref = float(gold["miou%s_%s_loss" % (sub, tag)])
             assert abs(float(loss) - ref) <= 5e-6 * abs(ref)
             np.testing.assert_allclose(grad.numpy(), gold["miou%s_%s_grad" % (sub, tag)], rtol=5e-4, atol=1e-9)
+
+
+def test_predict_pipeline_restatement_matches_the_reference_tools_files(tmp_path):
+    """tests/golden/predict_bins.npz holds the probability bins the UNMODIFIED robosat.tools.predict.main wrote for the five-tile
+    synthetic directory (make_golden_predict.py). The pipeline restated from oracle pieces -- buffered tile, ToTensor / Normalize,
+    oracle forward, softmax, unbuffer, np.digitize -- reproduces them (identically on the build host; a few bin-edge pixels may move
+    with another oneDNN build), so the GPU test that uses this restatement is pinned to the reference tool itself."""
+    from PIL import Image
+
+    from robosat_b200.datasets import BufferedSlippyMapDirectory
+    from robosat_b200.transforms import ImageToUint8Tensor
+
+    gold = np.load(os.path.join(GOLD, "predict_bins.npz"))
+    coords = [(100, 200), (101, 200), (100, 201), (101, 201), (103, 205)]
+    u8 = synth.make_tiles_u8(5, 256, seed=9).numpy()
+    for (x, y), arr in zip(coords, u8):
+        os.makedirs(tmp_path / "17" / str(x), exist_ok=True)
+        Image.fromarray(arr).save(tmp_path / "17" / str(x) / ("%d.png" % y))
+    directory = BufferedSlippyMapDirectory(str(tmp_path), transform=ImageToUint8Tensor(), size=256, overlap=32)
+    sd = synth.make_state_dict(2, seed=0)
+    differing = 0
+    for i in range(len(directory)):
+        image, xyz = directory[i]
+        x, y, _ = (int(v) for v in xyz)
+        probs = unet_oracle.predict_probs(sd, synth.normalize_tiles(image.unsqueeze(0))).numpy()[0]
+        bins = np.digitize(directory.unbuffer(probs)[1], np.linspace(0, 1, 256)).astype(np.uint8)
+        d = np.abs(bins.astype(np.int32) - gold["bins_%d_%d" % (x, y)].astype(np.int32))
+        assert d.max() <= 1
+        differing += int((d > 0).sum())
+    assert differing <= 64, differing

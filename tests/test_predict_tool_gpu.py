@@ -72,3 +72,15 @@ def test_rs_predict_end_to_end(tmp_path, cuda_device, monkeypatch):
     # reference probability sits that close to a bin edge -- by exactly one bin, on a small fraction of the pixels.
     assert worst <= 1 and total_diff <= 0.02 * total_px
     assert argmax_flips <= max(2, 8 * total_px // 131072)
+
+    # and against the files the UNMODIFIED reference tool wrote for the same directory / checkpoint (tests/golden/make_golden_predict.py
+    # ran robosat.tools.predict.main in the build container): same palette, same bins up to one bin at bin edges
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "predict_bins.npz"))
+    worst_ref, diff_ref = 0, 0
+    for (x, y) in coords:
+        out = Image.open(probs_dir / "17" / str(x) / ("%d.png" % y))
+        assert out.getpalette()[:768] == gold["palette"].tolist()
+        d = np.abs(np.array(out).astype(np.int32) - gold["bins_%d_%d" % (x, y)].astype(np.int32))
+        worst_ref, diff_ref = max(worst_ref, int(d.max())), diff_ref + int((d > 0).sum())
+    print("rs predict vs the reference tool's own output: worst bin difference %d, pixels whose bin differs %d / %d" % (worst_ref, diff_ref, total_px))
+    assert worst_ref <= 1 and diff_ref <= 0.02 * total_px
