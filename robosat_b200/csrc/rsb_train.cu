@@ -22,10 +22,10 @@ static inline unsigned tr_blocks(int64_t total, int block, int cap = 148 * 16) {
     return static_cast<unsigned>(b);
 }
 
-// grid of the channel reductions: every block folds >= 4 row groups (2 per iteration in flight), at most 8 blocks per SM
+// grid of the channel reductions: every block folds >= 8 row groups (4 per iteration in flight), at most 4 blocks per SM
 static inline unsigned reduce_blocks(int64_t M, int C) {
     const int rows_per_iter = 256 / (C / 8);
-    return tr_blocks((M + rows_per_iter * 4 - 1) / (rows_per_iter * 4), 1, 148 * 8);
+    return tr_blocks((M + rows_per_iter * 8 - 1) / (rows_per_iter * 8), 1, 148 * 4);
 }
 
 // Programmatic dependent launch: the training step is a chain of ~650 mostly small kernels, so the launch gap (scheduling the
@@ -113,7 +113,7 @@ __device__ __forceinline__ double red_slots(const double* sums, int which, int c
 static constexpr float kHalfPositive = 0x1p-25f;
 
 template <int KIND, bool ZMASK = false>
-__global__ void __launch_bounds__(256, 3) channel_reduce_kernel(const __half* __restrict__ a, const __half* __restrict__ y, const __half* __restrict__ z,
+__global__ void __launch_bounds__(256, 2) channel_reduce_kernel(const __half* __restrict__ a, const __half* __restrict__ y, const __half* __restrict__ z,
                                                              double* __restrict__ sums, int64_t M, int C, const RedTail tail,
                                                              const float* __restrict__ msc = nullptr, const float* __restrict__ msh = nullptr) {
     __shared__ float sh0[256 * 8];
@@ -149,6 +149,44 @@ __global__ void __launch_bounds__(256, 3) channel_reduce_kernel(const __half* __
         }
     };
     int64_t r = static_cast<int64_t>(blockIdx.x) * rows_per_iter + rsub;
+    // Main loop: FOUR row groups per iteration, all 16-byte loads issued (raw, 4 registers each) before the first conversion:
+    // 8-12 loads x 16 B in flight per thread. With two in flight a block kept ~8 KB outstanding and the passes ran at 37-53 % of
+    // the HBM peak (Little's law wants ~45 KB per SM); see profiles/r2_train.md.
+    auto raw = [](const __half* p) { return __ldg(reinterpret_cast<const uint4*>(p)); };
+    auto cvt = [](const uint4& q, float (&v)[8]) {
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h[i]);
+            v[2 * i] = f.x;
+            v[2 * i + 1] = f.y;
+        }
+    };
+    const bool use_y = !ZMASK && y != nullptr;
+    for (; r + 3 * step < M; r += 4 * step) {
+        uint4 qa[4], qz[4], qy[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qa[u] = raw(a + (r + u * step) * C + col);
+        if (KIND == 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) qz[u] = raw(z + (r + u * step) * C + col);
+            if (use_y) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) qy[u] = raw(y + (r + u * step) * C + col);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float v0[8], z0[8], y0[8];
+            cvt(qa[u], v0);
+            if (KIND == 1) {
+                cvt(qz[u], z0);
+                if (ZMASK) zmask(z0, y0);
+                else if (use_y) cvt(qy[u], y0);
+            }
+            fold(v0, z0, y0, ZMASK || y != nullptr);
+        }
+    }
     for (; r + step < M; r += 2 * step) {
         float v0[8], v1[8], z0[8], z1[8], y0[8], y1[8];
         load8(a + r * C + col, v0);
@@ -288,10 +326,19 @@ __global__ void bn_apply_kernel(const __half* __restrict__ z, const float* __res
         sc[e] = scale[col + e];
         sh[e] = shift[col + e];
     }
-    for (int64_t i = i0; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    auto finish = [&](int64_t i, const uint4& qz, const uint4& qr) {
         float v[8], r[8];
-        load8(z + i * 8, v);
-        if (res) load8(res + i * 8, r);
+        const __half2* hz = reinterpret_cast<const __half2*>(&qz);
+        const __half2* hr = reinterpret_cast<const __half2*>(&qr);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(hz[e]), g = __half22float2(hr[e]);
+            v[2 * e] = f.x;
+            v[2 * e + 1] = f.y;
+            r[2 * e] = g.x;
+            r[2 * e + 1] = g.y;
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             float o = fmaf(v[e], sc[e], sh[e]);
@@ -299,6 +346,22 @@ __global__ void bn_apply_kernel(const __half* __restrict__ z, const float* __res
             v[e] = relu ? fmaxf(o, 0.f) : o;
         }
         store8(y + i * 8, v);
+    };
+    int64_t i = i0;
+    // four 16-byte units (eight with a residual) in flight per thread before the first conversion
+    for (; i + 3 * stride < total; i += 4 * stride) {
+        uint4 qz[4], qr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qz[u] = __ldg(reinterpret_cast<const uint4*>(z + (i + u * stride) * 8));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qr[u] = res ? __ldg(reinterpret_cast<const uint4*>(res + (i + u * stride) * 8)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) finish(i + u * stride, qz[u], qr[u]);
+    }
+    for (; i < total; i += stride) {
+        const uint4 qz = __ldg(reinterpret_cast<const uint4*>(z + i * 8));
+        const uint4 qr = res ? __ldg(reinterpret_cast<const uint4*>(res + i * 8)) : make_uint4(0, 0, 0, 0);
+        finish(i, qz, qr);
     }
 }
 
@@ -306,7 +369,7 @@ __global__ void bn_apply_kernel(const __half* __restrict__ z, const float* __res
 // optionally also writes g (identity-branch gradient). Per-channel coefficients live in registers (see bn_apply_kernel);
 // two 16-byte units per thread are in flight per iteration.
 template <bool ZMASK>
-__global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, const __half* __restrict__ z,
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const __half* __restrict__ dy, const __half* __restrict__ y, const __half* __restrict__ z,
                                                               const float* __restrict__ coef, __half* __restrict__ dz, __half* __restrict__ g_out,
                                                               int64_t M, int C, const float* __restrict__ msc, const float* __restrict__ msh) {
     pdl_sync();
@@ -339,6 +402,36 @@ __global__ void __launch_bounds__(256, 3) bn_bwd_apply_kernel(const __half* __re
         store8(dz + i * 8, o);
     };
     int64_t i = i0;
+    // four units per iteration, all raw 16-byte loads (8-12 per thread) issued before the first conversion
+    auto cvt = [](const uint4& q, float (&v)[8]) {
+        const __half2* h = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float2 f = __half22float2(h[e]);
+            v[2 * e] = f.x;
+            v[2 * e + 1] = f.y;
+        }
+    };
+    const bool use_y = !ZMASK && y != nullptr;
+    for (; i + 3 * stride < total; i += 4 * stride) {
+        uint4 qg[4], qz[4], qy[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qg[u] = __ldg(reinterpret_cast<const uint4*>(dy + (i + u * stride) * 8));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qz[u] = __ldg(reinterpret_cast<const uint4*>(z + (i + u * stride) * 8));
+        if (use_y) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) qy[u] = __ldg(reinterpret_cast<const uint4*>(y + (i + u * stride) * 8));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            float g0[8], z0[8], y0[8];
+            cvt(qg[u], g0);
+            cvt(qz[u], z0);
+            if (use_y) cvt(qy[u], y0);
+            finish(i + u * stride, g0, z0, y0);
+        }
+    }
     for (; i + stride < total; i += 2 * stride) {
         float g0[8], g1[8], z0[8], z1[8], y0[8], y1[8];
         load8(dy + i * 8, g0);
@@ -771,7 +864,7 @@ static int bn_backward_impl(const void* dy, const void* y, const void* z, const 
     const __half* yh = static_cast<const __half*>(y);
     const __half* zh = static_cast<const __half*>(z);
     const float* coef = reinterpret_cast<const float*>(sums + static_cast<int64_t>(kRedSlots) * 2 * C + 2);
-    const unsigned ablocks = tr_blocks((M * (C / 8) + 1) / 2, 256);
+    const unsigned ablocks = tr_blocks((M * (C / 8) + 3) / 4, 256);
     const __half* nullh = nullptr;
     const float* nullf = nullptr;
     cudaError_t e;
