@@ -458,22 +458,46 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const __half* __re
 __global__ void relu_bwd_kernel(const __half* __restrict__ a, const __half* __restrict__ b, const __half* __restrict__ y,
                                 __half* __restrict__ out, int64_t total8) {
     pdl_sync();
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        float g[8], yy[8];
-        load8(a + i * 8, g);
-        if (b) {
-            float h[8];
-            load8(b + i * 8, h);
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    auto finish = [&](int64_t i, const uint4& qa, const uint4& qb, const uint4& qy) {
+        float g[8];
+        const __half2* ha = reinterpret_cast<const __half2*>(&qa);
+        const __half2* hb = reinterpret_cast<const __half2*>(&qb);
+        const __half2* hy = reinterpret_cast<const __half2*>(&qy);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) g[e] += h[e];
-        }
-        if (y) {
-            load8(y + i * 8, yy);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) g[e] = yy[e] > 0.f ? g[e] : 0.f;
+        for (int e = 0; e < 4; ++e) {
+            float2 f = __half22float2(ha[e]);
+            if (b) {
+                const float2 h = __half22float2(hb[e]);
+                f.x += h.x;
+                f.y += h.y;
+            }
+            if (y) {
+                const float2 m = __half22float2(hy[e]);
+                f.x = m.x > 0.f ? f.x : 0.f;
+                f.y = m.y > 0.f ? f.y : 0.f;
+            }
+            g[2 * e] = f.x;
+            g[2 * e + 1] = f.y;
         }
         store8(out + i * 8, g);
+    };
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < total8; i += 4 * stride) {  // four units (up to twelve 16-byte loads) in flight per thread
+        uint4 qa[4], qb[4], qy[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qa[u] = __ldg(reinterpret_cast<const uint4*>(a + (i + u * stride) * 8));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qb[u] = b ? __ldg(reinterpret_cast<const uint4*>(b + (i + u * stride) * 8)) : zero;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qy[u] = y ? __ldg(reinterpret_cast<const uint4*>(y + (i + u * stride) * 8)) : zero;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) finish(i + u * stride, qa[u], qb[u], qy[u]);
     }
+    for (; i < total8; i += stride)
+        finish(i, __ldg(reinterpret_cast<const uint4*>(a + i * 8)), b ? __ldg(reinterpret_cast<const uint4*>(b + i * 8)) : zero,
+               y ? __ldg(reinterpret_cast<const uint4*>(y + i * 8)) : zero);
 }
 
 // max-pool backward: dx[h][w] = sum over the windows that contain (h, w) and whose argmax is (h, w) (first max wins, like ATen)
