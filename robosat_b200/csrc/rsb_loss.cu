@@ -300,7 +300,12 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 //   state[3]  steps seen
 __global__ void grad_finite_kernel(const float* __restrict__ g, int64_t n, int32_t* __restrict__ state) {
     bool bad = false;
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t n4 = (reinterpret_cast<uintptr_t>(g) & 15) ? 0 : n / 4;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const float4 x = reinterpret_cast<const float4*>(g)[i];
+        bad |= !(fabsf(x.x) <= 3.402823466e38f) | !(fabsf(x.y) <= 3.402823466e38f) | !(fabsf(x.z) <= 3.402823466e38f) | !(fabsf(x.w) <= 3.402823466e38f);
+    }
+    for (int64_t i = 4 * n4 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
         const float x = g[i];
         bad |= !(fabsf(x) <= 3.402823466e38f);  // inf or NaN
     }
@@ -317,13 +322,30 @@ __global__ void adam_guarded_kernel(float* __restrict__ p, const float* __restri
         step_size = static_cast<float>(static_cast<double>(lr) / (1.0 - pow(static_cast<double>(beta1), eff)));
         bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), eff)));
     }
-    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        const float gi = g[i];
-        float mi = m[i], vi = v[i];
+    // four parameters per thread and iteration through 16-byte loads / stores (the arenas are 256-byte aligned torch allocations);
+    // per element the arithmetic is exactly adam_kernel's
+    auto upd = [&](float& pi, float gi, float& mi, float& vi) {
         mi = mi + one_minus_beta1 * (gi - mi);
         vi = vi * beta2 + one_minus_beta2 * (gi * gi);
         const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = p[i] - step_size * (mi / denom);
+        pi = pi - step_size * (mi / denom);
+    };
+    const int64_t n4 = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) ? 0 : n / 4;
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+        const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+        upd(p4.x, g4.x, m4.x, v4.x);
+        upd(p4.y, g4.y, m4.y, v4.y);
+        upd(p4.z, g4.z, m4.z, v4.z);
+        upd(p4.w, g4.w, m4.w, v4.w);
+        reinterpret_cast<float4*>(p)[i] = p4;
+        reinterpret_cast<float4*>(m)[i] = m4;
+        reinterpret_cast<float4*>(v)[i] = v4;
+    }
+    for (int64_t i = 4 * n4 + static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        float pi = p[i], mi = m[i], vi = v[i];
+        upd(pi, g[i], mi, vi);
+        p[i] = pi;
         m[i] = mi;
         v[i] = vi;
     }
