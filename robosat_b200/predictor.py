@@ -125,8 +125,16 @@ class TilePredictor:
         """The pinned staging buffer the next `submit` will use (fill it in place to skip one host copy)."""
         return self._slots[self._next % self.depth]["h_in"]
 
-    def collect(self):
-        """Wait for the oldest submitted batch and return its pinned host result (valid until `depth` more submits)."""
+    def collect(self, poll=False):
+        """Wait for the oldest submitted batch and return its pinned host result (valid until `depth` more submits).
+        poll=True: wait by polling the event with short sleeps instead of a blocking synchronize -- for a consumer THREAD, so that
+        the wait can never keep the interpreter away from the thread that launches the next batch."""
         slot = self._pending.pop(0)
-        slot["done"].synchronize()
+        if poll:
+            import time
+
+            while not slot["done"].query():
+                time.sleep(0.0002)
+        else:
+            slot["done"].synchronize()
         return slot["h_q"]

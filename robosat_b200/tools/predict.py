@@ -126,9 +126,9 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
         except ImportError:  # pragma: no cover
             return it
 
-    def collect(predictor):
+    def collect(predictor, poll=False):
         t0 = time.perf_counter()
-        q = predictor.collect().numpy()
+        q = predictor.collect(poll=poll).numpy()
         st["gpu_wait_s"] += time.perf_counter() - t0
         return q
 
@@ -195,7 +195,7 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
                         tiles = submitted.get()
                         if tiles is None:
                             return
-                        quantized = collect(predictor)
+                        quantized = collect(predictor, poll=os.environ.get("RSB_COLLECT_POLL", "1") == "1")
                         coords = [(int(t.x), int(t.y), int(t.z)) for t in tiles]
                         bins = quantized[:len(tiles)].copy()
                         slots_free.release()
