@@ -223,6 +223,10 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
                     marks.append((torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)))
                     marks[-1][0].record()
                 stitcher.stitch(tiles, predictor.device_input())  # upload what was decoded ahead, assemble the buffered batch on the device
+                if stats is not None:
+                    mid = torch.cuda.Event(enable_timing=True)
+                    mid.record()
+                    marks[-1] = marks[-1] + (mid,)
                 t1 = clock()
                 if ci + ahead < len(chunks):
                     stitcher.prefetch(chunks[ci + ahead])  # decode batch i+ahead on the library's threads while the GPU runs batch i
@@ -247,8 +251,9 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
             st["main_thread_s"] = tm  # launching thread: waiting for a free slot (device-bound), stitch (incl. decode wait), prefetch, launches
             if marks:
                 torch.cuda.synchronize(device)
-                st["device_busy_s"] = sum(a.elapsed_time(b) for a, b in marks) / 1e3           # uploads + stitch + net + head, per batch, summed
+                st["device_busy_s"] = sum(m[0].elapsed_time(m[1]) for m in marks) / 1e3        # uploads + stitch + net + head, per batch, summed
                 st["device_idle_s"] = sum(marks[i][1].elapsed_time(marks[i + 1][0]) for i in range(len(marks) - 1)) / 1e3  # stream empty between batches
+                st["device_stitch_s"] = sum(m[0].elapsed_time(m[2]) for m in marks) / 1e3      # of device_busy: waiting for uploads + table copy + stitch kernel
             t0 = time.perf_counter()
         st["pool_shutdown_s"] = time.perf_counter() - t0
         cache.close()
