@@ -15,8 +15,12 @@ from robosat_b200.engine import UNetEngine
 
 
 class TilePredictor:
-    def __init__(self, state_dict, num_classes, batch, size, overlap=0, device="cuda", depth=2, precision=None):
-        """size: net input extent (tile_size + 2*overlap, predict.py:75); depth: in-flight batches for copy/compute overlap"""
+    def __init__(self, state_dict, num_classes, batch, size, overlap=0, device="cuda", depth=2, precision=None, use_graph=False):
+        """size: net input extent (tile_size + 2*overlap, predict.py:75); depth: in-flight batches for copy/compute overlap.
+        use_graph=True captures the 60 launches of (network + head) once per slot into a CUDA graph and replays it: ONE driver
+        call per batch instead of 60 ctypes launches. The kernels and results are identical; it matters when the launching thread
+        shares the interpreter with decode / encode / consumer threads (`rs predict`: the 60 launches took 5 ms per batch there and
+        the device ran ahead of them). If capture fails the predictor keeps launching kernel by kernel (`graph_error` says why)."""
         self.device = torch.device(device)
         self.batch, self.size, self.overlap, self.classes = batch, size, overlap, num_classes
         self.engine = UNetEngine(state_dict, num_classes, batch, size, size, device=self.device, precision=precision)
@@ -40,6 +44,39 @@ class TilePredictor:
         self._pending = []
         self.h2d_bytes = batch * size * size * 3
         self.d2h_bytes = batch * self.out_size * self.out_size
+        self.graph_error = None
+        if use_graph and num_classes == 2:
+            self._capture_graphs()
+
+    def _compute(self, slot):
+        """network + head of one slot on the current stream: a graph replay if one was captured, else 60 launches"""
+        g = slot.get("graph")
+        if g is not None:
+            g.replay()
+        else:
+            self.quantize(self.engine.forward(slot["d_in"]), slot["d_q"])
+
+    def _capture_graphs(self):
+        # warm up on a side stream first (one-time cudaFuncSetAttribute calls must not happen while a stream is capturing)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for slot in self._slots:
+                slot["d_in"].zero_()
+                self.quantize(self.engine.forward(slot["d_in"]), slot["d_q"])
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        try:
+            for slot in self._slots:
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    self.quantize(self.engine.forward(slot["d_in"]), slot["d_q"])
+                slot["graph"] = graph
+        except Exception as exc:  # same kernels, launched one by one
+            self.graph_error = "%s: %s" % (type(exc).__name__, exc)
+            for slot in self._slots:
+                slot.pop("graph", None)
+            torch.cuda.synchronize(self.device)
 
     # ------------------------------------------------------------------ device-resident pieces
     def logits(self, x_dev):
@@ -83,9 +120,8 @@ class TilePredictor:
             slot["d_in"].copy_(src, non_blocking=True)  # pinned source: DMA straight from the caller's buffer
             slot["loaded"].record(self._copy_in)
         main.wait_event(slot["loaded"])
-        logits = self.engine.forward(slot["d_in"])
+        self._compute(slot)
         slot["consumed"].record(main)
-        self.quantize(logits, slot["d_q"])
         slot["computed"].record(main)
         with torch.cuda.stream(self._copy_out):
             self._copy_out.wait_event(slot["computed"])
@@ -110,9 +146,8 @@ class TilePredictor:
         main = torch.cuda.current_stream(self.device)
         if slot.get("busy"):
             slot["done"].synchronize()
-        logits = self.engine.forward(slot["d_in"])
+        self._compute(slot)
         slot["consumed"].record(main)
-        self.quantize(logits, slot["d_q"])
         slot["computed"].record(main)
         with torch.cuda.stream(self._copy_out):
             self._copy_out.wait_event(slot["computed"])

@@ -138,7 +138,8 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
         assert len(directory) > 0, "at least one tile in dataset"
         lo, hi = shard_range(len(directory), rank, world)
         loader = DataLoader(Subset(directory, range(lo, hi)), batch_size=args.batch_size, num_workers=args.workers)
-        predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device)
+        predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device,
+                                   use_graph=os.environ.get("RSB_PREDICT_GRAPH", "1") == "1")
         st.update(tiles=hi - lo, batches=len(loader), decode_wait_s=0.0)
         with ThreadPoolExecutor(max_workers=pool_threads) as pool:
             pending = []
@@ -171,7 +172,8 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
         decode_threads = args.workers if args.workers > 0 else default_decode_threads
         cache = DeviceTileCache(index, args.tile_size, capacity, device=device, workers=decode_threads)
         stitcher = HaloStitcher(cache, args.overlap, args.batch_size)
-        predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device)
+        predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device,
+                                   use_graph=os.environ.get("RSB_PREDICT_GRAPH", "1") == "1")
         chunks = [mine[i:i + args.batch_size] for i in range(0, len(mine), args.batch_size)]
         st.update(tiles=len(mine), batches=len(chunks), decode_threads=decode_threads)
         st["setup_s"] = time.perf_counter() - t_start  # enumerate + plan (weight folding / packing) + buffers, before the first batch

@@ -84,3 +84,26 @@ def test_rs_predict_end_to_end(tmp_path, cuda_device, monkeypatch):
         worst_ref, diff_ref = max(worst_ref, int(d.max())), diff_ref + int((d > 0).sum())
     print("rs predict vs the reference tool's own output: worst bin difference %d, pixels whose bin differs %d / %d" % (worst_ref, diff_ref, total_px))
     assert worst_ref <= 1 and diff_ref <= 0.02 * total_px
+
+
+def test_tile_predictor_graph_replay_equals_kernel_by_kernel(cuda_device):
+    """`TilePredictor(use_graph=True)` (what `rs predict` uses: network + head captured once per slot, one driver call per batch)
+    returns the same bins, bit for bit, as launching the 60 kernels one by one -- for several batches through both slots."""
+    from robosat_b200.predictor import TilePredictor
+
+    sd = synth.make_state_dict(2, seed=0)
+    tiles = [synth.make_tiles_u8(2, 128, seed=40 + i) for i in range(5)]
+    outs = {}
+    for use_graph in (False, True):
+        pred = TilePredictor(sd, 2, 2, 128, overlap=16, device=cuda_device, use_graph=use_graph)
+        if use_graph:
+            assert pred.graph_error is None, pred.graph_error
+        res = []
+        for i, t in enumerate(tiles):
+            pred.submit(t)
+            if i >= 1:
+                res.append(pred.collect().clone())
+        res.append(pred.collect().clone())
+        outs[use_graph] = res
+    for a, b in zip(outs[False], outs[True]):
+        assert torch.equal(a, b)
