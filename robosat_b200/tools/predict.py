@@ -139,7 +139,7 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
         lo, hi = shard_range(len(directory), rank, world)
         loader = DataLoader(Subset(directory, range(lo, hi)), batch_size=args.batch_size, num_workers=args.workers)
         predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device,
-                                   use_graph=os.environ.get("RSB_PREDICT_GRAPH", "1") == "1")
+                                   use_graph=os.environ.get("RSB_PREDICT_GRAPH", "1") == "1", depth=int(os.environ.get("RSB_PREDICT_DEPTH", "2")))
         st.update(tiles=hi - lo, batches=len(loader), decode_wait_s=0.0)
         with ThreadPoolExecutor(max_workers=pool_threads) as pool:
             pending = []
@@ -173,7 +173,7 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
         cache = DeviceTileCache(index, args.tile_size, capacity, device=device, workers=decode_threads)
         stitcher = HaloStitcher(cache, args.overlap, args.batch_size)
         predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device,
-                                   use_graph=os.environ.get("RSB_PREDICT_GRAPH", "1") == "1")
+                                   use_graph=os.environ.get("RSB_PREDICT_GRAPH", "1") == "1", depth=int(os.environ.get("RSB_PREDICT_DEPTH", "2")))
         chunks = [mine[i:i + args.batch_size] for i in range(0, len(mine), args.batch_size)]
         st.update(tiles=len(mine), batches=len(chunks), decode_threads=decode_threads)
         st["setup_s"] = time.perf_counter() - t_start  # enumerate + plan (weight folding / packing) + buffers, before the first batch
