@@ -108,10 +108,11 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
     # host cores of this rank, split between the PNG-encode pool and the decode pool (both run GIL-free C code)
     cores = max(2, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)) // max(world, 1))
     # The codec threads are busy C++ threads: leave the launching (main) thread and the driver's threads two cores and do not take
-    # more than the GPU can consume (2 400 tiles/s x ~7 ms of decode + encode per tile = ~18 busy threads); with every hardware
-    # thread occupied the main thread was descheduled and the device ran empty (profiles/r2_cfg4.md). Decoding a 512x512 RGB tile
+    # much more than the GPU can consume (2 400 tiles/s x ~7 ms of decode + encode per tile = ~18 threads if they were always
+    # busy; a ticket of 32-40 tiles keeps 48 threads busy for one round instead of two); with every hardware thread occupied the
+    # main thread was descheduled and the device ran empty (profiles/r2_cfg4.md). Decoding a 512x512 RGB tile
     # costs ~5.6 ms, encoding a probability mask 1-4 ms: two thirds of the budget decode, one third encodes.
-    budget = max(3, min(36, cores - 2))
+    budget = max(3, min(72, cores - 2))
     pool_threads = int(os.environ.get("RSB_PNG_THREADS", "0")) or max(1, budget // 3)
     default_decode_threads = int(os.environ.get("RSB_DECODE_THREADS", "0")) or max(2, budget - budget // 3)
     st.update(pool_threads=pool_threads, gpu_wait_s=0.0, png_cpu_s=0.0)
@@ -139,7 +140,7 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
         lo, hi = shard_range(len(directory), rank, world)
         loader = DataLoader(Subset(directory, range(lo, hi)), batch_size=args.batch_size, num_workers=args.workers)
         predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device,
-                                   use_graph=os.environ.get("RSB_PREDICT_GRAPH", "1") == "1", depth=int(os.environ.get("RSB_PREDICT_DEPTH", "2")))
+                                   use_graph=os.environ.get("RSB_PREDICT_GRAPH", "1") == "1", depth=int(os.environ.get("RSB_PREDICT_DEPTH", "3")))
         st.update(tiles=hi - lo, batches=len(loader), decode_wait_s=0.0)
         with ThreadPoolExecutor(max_workers=pool_threads) as pool:
             pending = []
@@ -173,7 +174,7 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
         cache = DeviceTileCache(index, args.tile_size, capacity, device=device, workers=decode_threads)
         stitcher = HaloStitcher(cache, args.overlap, args.batch_size)
         predictor = TilePredictor(sd, num_classes, args.batch_size, size, overlap=args.overlap, device=device,
-                                   use_graph=os.environ.get("RSB_PREDICT_GRAPH", "1") == "1", depth=int(os.environ.get("RSB_PREDICT_DEPTH", "2")))
+                                   use_graph=os.environ.get("RSB_PREDICT_GRAPH", "1") == "1", depth=int(os.environ.get("RSB_PREDICT_DEPTH", "3")))
         chunks = [mine[i:i + args.batch_size] for i in range(0, len(mine), args.batch_size)]
         st.update(tiles=len(mine), batches=len(chunks), decode_threads=decode_threads)
         st["setup_s"] = time.perf_counter() - t_start  # enumerate + plan (weight folding / packing) + buffers, before the first batch
