@@ -129,6 +129,15 @@ typedef struct rsb_conv_desc {
     int32_t kchunk;
     float* scratch;
     int64_t scratch_bytes;
+
+    /* BatchNorm batch statistics fused into the epilogue (training forward of a conv that feeds nn.BatchNorm2d: torchvision
+     * resnet.py Bottleneck.forward bn1-3, robosat/unet.py:122-130 in train mode). mode 0, split 0, no residual, phases 1.
+     * For every tile t (flat index ((n-tile * tiles_h) + h-tile) * tiles_w + w-tile) and every 32-row quarter q of it:
+     *   stats[(t*4 + q)*2*Cout + c]        = sum   of the fp16 outputs of channel c over the quarter's in-range pixels
+     *   stats[(t*4 + q)*2*Cout + Cout + c] = sum of their squares
+     * every entry is written exactly once per run (no zeroing needed); rsb_bn_partials_finalize folds them. NULL: off. */
+    float* stats;
+    int64_t stats_bytes;
 } rsb_conv_desc;
 
 typedef struct rsb_conv_plan rsb_conv_plan;
@@ -317,6 +326,12 @@ int rsb_bn_stats_finalize(const void* z, double* sums, const float* gamma, const
 int rsb_bn_stats_finalize_chained(const void* z, double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                                   int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int64_t M, int32_t C, float eps,
                                   float momentum, void* stream);
+/* Same statistics / finalize from the per-quarter-tile partial sums a convolution wrote through rsb_conv_desc.stats
+ * (partials: fp32 [rows][2][C], rows = spatial tiles * 4) instead of re-reading z: 1/8 of the bytes. `chained` as above
+ * (1: no memset, programmatic stream serialization; sums must be zero on entry and is left zeroed). */
+int rsb_bn_partials_finalize(const float* partials, int64_t rows, double* sums, const float* gamma, const float* beta, float* running_mean,
+                             float* running_var, int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int64_t M,
+                             int32_t C, float eps, float momentum, int32_t chained, void* stream);
 int rsb_bn_apply_chained(const void* z, const float* scale, const float* shift, const void* residual, void* y, int64_t M, int32_t C,
                          int32_t relu, void* stream);
 int rsb_bn_backward_chained(const void* dy, const void* y, const void* z, const float* mean, const float* invstd, const float* gamma,
@@ -350,6 +365,9 @@ int rsb_final_backward(const float* dlogits, const void* y5, const float* w, voi
                        float loss_scale, int32_t N, int32_t HW, int32_t classes, void* stream);
 /* fp32 OIHW master weights -> fp16 packed operand matrix: dst[i] = half(sum of src[map4[4i..4i+3]] (entries < 0 skipped)) */
 int rsb_pack_weights(const float* src, const int32_t* map4, void* dst, int64_t n, void* stream);
+/* the same with ONE source index per packed element (map1: int32 [n], -1 = zero; n a multiple of 8, map1 and dst 16-byte
+ * aligned): a quarter of the map bytes; used for every layout but the pre-summed nearest-x2 taps */
+int rsb_pack_weights1(const float* src, const int32_t* map1, void* dst, int64_t n, void* stream);
 /* packed fp32 gradient -> OIHW fp32 gradient: grad[map4[4i+j]] += packed_grad[i] * mul (the transpose of rsb_pack_weights) */
 int rsb_unpack_grads(const float* packed_grad, const int32_t* map4, float* grad, int64_t n, float mul, void* stream);
 

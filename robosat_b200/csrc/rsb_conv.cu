@@ -56,6 +56,9 @@ struct alignas(64) ConvKParams {
     const float* head_b;
     float* head_out;
     float acc_scale;
+    // STATS instances (training forward of a conv feeding BatchNorm): per 32-row quarter of every tile, the column sums and
+    // sums of squares of the fp16 outputs as stored: float [spatial tiles * 4][2][Cout]; every entry is written exactly once
+    float* stats;
     // K chunking (strict precision, long K loops): the tensor core truncates its fp32 accumulator after every MMA, a bias
     // that grows with the number of accumulated MMAs. A tile's K loop is therefore cut into chunks of `kchunk` K blocks; each
     // chunk accumulates in its own tensor-memory stage and the epilogue warps add the chunk results with round-to-nearest fp32
@@ -139,7 +142,7 @@ __device__ __forceinline__ int item_tile(const ConvKParams& p, int it, int rank)
     return ((it / per) * 2 + rank) * per + it % per;
 }
 
-template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, int SPLIT>
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, int SPLIT, bool STATS = false>
 __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::kThreads), 1) conv_tc_kernel(const __grid_constant__ ConvKParams p) {
     using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>;
     const int rank = TWO ? static_cast<int>(cluster_ctarank()) : 0;
@@ -363,6 +366,7 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::
             const TileCoord t = decode_tile(p, item_tile<TWO>(p, it, rank));
             const int w = t.w0 + tw, h = t.h0 + th, n = t.n0 + tn;
             const bool valid = (w < p.Wt) && (h < p.Ht) && (n < p.Nt);
+            const unsigned vmask = STATS ? __ballot_sync(0xffffffffu, valid) : 0u;
             // K chunking: every chunk but the last is added (fp32, round to nearest) into this thread's row of the CTA's scratch tile
             const int nchunks = (MODE == 0 && p.kchunk > 0) ? (p.kblocks + p.kchunk - 1) / p.kchunk : 1;
             float* srow = nullptr;
@@ -523,6 +527,39 @@ __global__ void __launch_bounds__((ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>::
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
+                    if constexpr (STATS) {
+                        // BatchNorm batch statistics of this warp's 32 rows x kChunk columns, read back column-wise from the staged
+                        // fp16 slice (the values the consumer will read): lane -> one 4-byte word (2 channels) of a row, conflict free
+                        constexpr int kWords = Cfg::kChunk / 2;   // 32 or 16 words per staged row
+                        constexpr int kGroups = 32 / kWords;      // row groups read in parallel: 1 or 2
+                        const int wd = lane % kWords, g = lane / kWords;
+                        float s0x = 0.f, s0y = 0.f, s1x = 0.f, s1y = 0.f;
+#pragma unroll 8
+                        for (int r = g; r < 32; r += kGroups) {
+                            const int u = wd >> 2;
+                            const int su = Cfg::kChunk == 64 ? (u ^ (r & 7)) : (u ^ ((r >> 1) & 3));
+                            const __half2 hv = *reinterpret_cast<const __half2*>(cbuf + r * (Cfg::kChunk * 2) + su * 16 + (wd & 3) * 4);
+                            if ((vmask >> r) & 1u) {
+                                const float2 f = __half22float2(hv);
+                                s0x += f.x;
+                                s0y += f.y;
+                                s1x = fmaf(f.x, f.x, s1x);
+                                s1y = fmaf(f.y, f.y, s1y);
+                            }
+                        }
+                        if (kGroups == 2) {
+                            s0x += __shfl_xor_sync(0xffffffffu, s0x, 16);
+                            s0y += __shfl_xor_sync(0xffffffffu, s0y, 16);
+                            s1x += __shfl_xor_sync(0xffffffffu, s1x, 16);
+                            s1y += __shfl_xor_sync(0xffffffffu, s1y, 16);
+                        }
+                        const int spatial = item_tile<TWO>(p, it, rank) / p.n_blocks;  // phases == 1
+                        if (g == 0 && spatial < p.tiles_w * p.tiles_h * p.tiles_n) {
+                            float* dst = p.stats + (static_cast<size_t>(spatial) * 4 + q) * 2 * p.Cout + t.n_blk * BLOCK_N + ck * Cfg::kChunk + 2 * wd;
+                            *reinterpret_cast<float2*>(dst) = make_float2(s0x, s0y);
+                            *reinterpret_cast<float2*>(dst + p.Cout) = make_float2(s1x, s1y);
+                        }
+                    }
                     if (lane == 0) {
                         if constexpr (SPLIT)
                             tma_store_5d(&p.tmC[t.phase], cbuf, t.n_blk * BLOCK_N + ck * Cfg::kChunk, t.w0 + qw, t.h0 + qh, t.n0 + qn, 0);
@@ -671,6 +708,7 @@ struct rsb_conv_plan {
     bool has_res;
     bool pair;   // CTA-pair (cta_group::2) schedule
     bool split;  // strict precision (hi + lo planes)
+    bool stats;  // the epilogue also writes per-quarter-tile BatchNorm partial sums
 };
 
 static int validate_desc(const rsb_conv_desc* d, int* K_out) {
@@ -720,6 +758,14 @@ static int validate_desc(const rsb_conv_desc* d, int* K_out) {
         return set_error(RSB_E_INVALID, "conv: unknown mode");
     }
     if (d->cta_pair && (d->mode != 0 || d->block_n < 128)) return set_error(RSB_E_INVALID, "conv: cta_pair needs mode 0 and block_n >= 128");
+    if (d->stats) {
+        if (d->mode != 0 || d->split || d->residual || d->phases != 1)
+            return set_error(RSB_E_INVALID, "conv: stats needs mode 0, fast precision, no residual, phases == 1");
+        const int64_t tiles = static_cast<int64_t>((d->Wt + d->TW - 1) / d->TW) * ((d->Ht + d->TH - 1) / d->TH) * ((d->Nt + d->TN - 1) / d->TN);
+        const int64_t need = tiles * 4 * 2 * d->Cout * 4;
+        if ((reinterpret_cast<uintptr_t>(d->stats) & 7) || d->stats_bytes < need)
+            return set_error(RSB_E_INVALID, "conv: stats needs an 8B-aligned buffer of >= %lld bytes (tiles x 4 x 2 x Cout fp32)", (long long)need);
+    }
     *K_out = kblocks * kBlockK;
     return RSB_OK;
 }
@@ -731,7 +777,7 @@ static int current_device() {
     return dev;
 }
 
-template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, int SPLIT>
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, int SPLIT, bool STATS = false>
 struct ConvInst {
     using Cfg = ConvCfg<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>;
     static constexpr int kSmem = Cfg::kSmemBytes;
@@ -741,7 +787,7 @@ struct ConvInst {
         static bool attr_set[kMaxDevices] = {};
         const int dev = current_device();
         if (!attr_set[dev]) {
-            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+            cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, MODE, HAS_RES, TWO, SPLIT, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
             if (e != cudaSuccess) return set_cuda_error(e, "cudaFuncSetAttribute(conv)");
             attr_set[dev] = true;
         }
@@ -768,7 +814,7 @@ struct ConvInst {
             attr[1].val.clusterDim.z = 1;
             cfg.numAttrs = 2;
         }
-        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>, plan->kp);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, MODE, HAS_RES, TWO, SPLIT, STATS>, plan->kp);
         if (e != cudaSuccess) return set_cuda_error(e, "conv_tc_kernel launch");
         return RSB_OK;
     }
@@ -792,7 +838,7 @@ struct ConvInst {
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>, &cfg) != cudaSuccess) {
+        if (cudaOccupancyMaxActiveClusters(&n, conv_tc_kernel<BLOCK_N, MODE, HAS_RES, TWO, SPLIT, STATS>, &cfg) != cudaSuccess) {
             cudaGetLastError();
             n = 0;
         }
@@ -806,9 +852,9 @@ struct ConvInst {
 // what to do with the instantiation a plan selects
 enum ConvAction { kLaunch, kSmemOf, kPairClusters };
 
-template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, int SPLIT>
+template <int BLOCK_N, int MODE, bool HAS_RES, bool TWO, int SPLIT, bool STATS = false>
 static int conv_act(ConvAction a, const rsb_conv_plan* plan, cudaStream_t stream) {
-    using I = ConvInst<BLOCK_N, MODE, HAS_RES, TWO, SPLIT>;
+    using I = ConvInst<BLOCK_N, MODE, HAS_RES, TWO, SPLIT, STATS>;
     switch (a) {
         case kLaunch: return I::launch(plan, stream);
         case kSmemOf: return I::kSmem;
@@ -845,7 +891,22 @@ static int conv_dispatch(ConvAction a, const rsb_conv_plan* plan, cudaStream_t s
     return a == kLaunch ? set_error(RSB_E_INVALID, "conv: unsupported block_n / residual / split combination") : 0;
 }
 
+// training forward of a conv that feeds BatchNorm: fast precision, no residual, mode 0 (validate_desc)
+static int conv_dispatch_stats(ConvAction a, const rsb_conv_plan* plan, cudaStream_t stream) {
+    if (plan->pair) {
+        if (plan->block_n == 128) return conv_act<128, 0, false, true, 0, true>(a, plan, stream);
+        return conv_act<256, 0, false, true, 0, true>(a, plan, stream);
+    }
+    switch (plan->block_n) {
+        case 32: return conv_act<32, 0, false, false, 0, true>(a, plan, stream);
+        case 64: return conv_act<64, 0, false, false, 0, true>(a, plan, stream);
+        case 128: return conv_act<128, 0, false, false, 0, true>(a, plan, stream);
+        default: return conv_act<256, 0, false, false, 0, true>(a, plan, stream);
+    }
+}
+
 static int conv_select(ConvAction a, const rsb_conv_plan* plan, cudaStream_t stream) {
+    if (plan->stats) return conv_dispatch_stats(a, plan, stream);
     return plan->split ? conv_dispatch<1>(a, plan, stream) : conv_dispatch<0>(a, plan, stream);
 }
 
@@ -972,10 +1033,12 @@ extern "C" int rsb_conv_plan_create(const rsb_conv_desc* d, rsb_conv_plan** out_
     kp.acc_scale = d->acc_scale != 0.f ? d->acc_scale : 1.f;
     kp.kchunk = (d->kchunk > 0 && d->kchunk < kp.kblocks) ? d->kchunk : 0;
     kp.scratch = d->scratch;
+    kp.stats = d->stats;
 
     plan->block_n = d->block_n;
     plan->mode = d->mode;
     plan->split = split;
+    plan->stats = d->stats != nullptr;
     const int sms = num_sms();
     plan->grid = kp.total_tiles < sms ? kp.total_tiles : sms;
     plan->has_res = d->mode == 0 && d->residual != nullptr;

@@ -287,6 +287,94 @@ __global__ void __launch_bounds__(256, 2) channel_reduce_kernel(const __half* __
     if (tail.self_clean && threadIdx.x == 0) *reinterpret_cast<unsigned*>(sums + static_cast<int64_t>(kRedSlots) * 2 * C) = 0u;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Batch statistics from the per-quarter-tile partial sums a STATS convolution wrote (rsb_conv_desc.stats): P is an fp32
+// matrix [R][L], L = 2*C (row = one 32-pixel quarter of a tile: C sums, then C sums of squares). Column sums go to the same
+// replicated fp64 accumulators as channel_reduce_kernel<0> ([slot][2][C] == [slot][L]) and the last block runs the same
+// BatchNorm finalize, so the op reads 1/8 of the bytes of z instead of all of z.
+__global__ void __launch_bounds__(256) partial_reduce_kernel(const float* __restrict__ P, double* __restrict__ sums, int64_t R, int L, int C, int64_t M,
+                                                            const RedTail tail) {
+    __shared__ float4 sh[256];
+    pdl_sync();
+    const int tpr = L / 4 < 256 ? L / 4 : 256;  // threads per row, one float4 each
+    const int rows_per_iter = 256 / tpr;
+    const int col = blockIdx.y * tpr * 4 + (threadIdx.x % tpr) * 4;
+    const int rsub = threadIdx.x / tpr;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t step = static_cast<int64_t>(gridDim.x) * rows_per_iter;
+    int64_t r = static_cast<int64_t>(blockIdx.x) * rows_per_iter + rsub;
+    auto ld = [&](int64_t row) { return __ldg(reinterpret_cast<const float4*>(P + row * L + col)); };
+    auto add = [&](const float4& v) {
+        acc.x += v.x;
+        acc.y += v.y;
+        acc.z += v.z;
+        acc.w += v.w;
+    };
+    for (; r + 3 * step < R; r += 4 * step) {
+        const float4 a = ld(r), b = ld(r + step), c = ld(r + 2 * step), d = ld(r + 3 * step);
+        add(a);
+        add(b);
+        add(c);
+        add(d);
+    }
+    for (; r < R; r += step) add(ld(r));
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.x < tpr) {
+        float4 t = sh[threadIdx.x];
+        for (int g = 1; g < rows_per_iter; ++g) {
+            const float4 v = sh[g * tpr + threadIdx.x];
+            t.x += v.x;
+            t.y += v.y;
+            t.z += v.z;
+            t.w += v.w;
+        }
+        double* s = sums + static_cast<int64_t>(blockIdx.x % kRedSlots) * L + col;
+        atomicAdd(&s[0], static_cast<double>(t.x));
+        atomicAdd(&s[1], static_cast<double>(t.y));
+        atomicAdd(&s[2], static_cast<double>(t.z));
+        atomicAdd(&s[3], static_cast<double>(t.w));
+    }
+    // ---- last block (of the whole 2-D grid): BatchNorm finalize, as in channel_reduce_kernel<0>
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned* counter = reinterpret_cast<unsigned*>(sums + static_cast<int64_t>(kRedSlots) * 2 * C);
+        is_last = atomicAdd(counter, 1u) == gridDim.x * gridDim.y - 1;
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const double dM = static_cast<double>(M);
+    if (threadIdx.x == 0 && tail.num_batches) *tail.num_batches += 1;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const double t0 = red_slots(sums, 0, c, C), t1 = red_slots(sums, 1, c, C);
+        const double mean = t0 / dM;
+        double var = t1 / dM - mean * mean;
+        if (var < 0) var = 0;
+        const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(tail.eps)));
+        const float sc = tail.gamma[c] * invstd;
+        tail.mean[c] = static_cast<float>(mean);
+        tail.invstd[c] = invstd;
+        tail.scale[c] = sc;
+        tail.shift[c] = tail.beta[c] - static_cast<float>(mean) * sc;
+        if (tail.running_mean) {
+            const double unbiased = dM > 1 ? var * dM / (dM - 1.0) : var;
+            tail.running_mean[c] = (1.f - tail.momentum) * tail.running_mean[c] + tail.momentum * static_cast<float>(mean);
+            tail.running_var[c] = (1.f - tail.momentum) * tail.running_var[c] + tail.momentum * static_cast<float>(unbiased);
+        }
+        if (tail.self_clean) {
+#pragma unroll
+            for (int sl = 0; sl < kRedSlots; ++sl) {
+                sums[(static_cast<int64_t>(sl) * 2 + 0) * C + c] = 0.0;
+                sums[(static_cast<int64_t>(sl) * 2 + 1) * C + c] = 0.0;
+            }
+        }
+    }
+    if (tail.self_clean && threadIdx.x == 0) *reinterpret_cast<unsigned*>(sums + static_cast<int64_t>(kRedSlots) * 2 * C) = 0u;
+}
+
 // mean / invstd / folded scale+shift from the batch sums, running-stat update (momentum, unbiased variance)
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
@@ -728,6 +816,20 @@ __global__ void pack_gather_kernel(const float* __restrict__ src, const int32_t*
     }
 }
 
+// the common case of the same re-pack: every packed element has ONE source (all layouts but the pre-summed nearest-x2 taps).
+// 8 elements per thread: 32 bytes of map, 8 gathers, one 16-byte store (the 4-index map costs 16 bytes per element).
+__global__ void pack_gather1_kernel(const float* __restrict__ src, const int32_t* __restrict__ map, __half* __restrict__ dst, int64_t n8) {
+    for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int4 m0 = __ldg(reinterpret_cast<const int4*>(map) + 2 * i);
+        const int4 m1 = __ldg(reinterpret_cast<const int4*>(map) + 2 * i + 1);
+        const int idx[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = idx[j] >= 0 ? __ldg(src + idx[j]) : 0.f;
+        store8(dst + 8 * i, v);
+    }
+}
+
 __global__ void unpack_scatter_kernel(const float* __restrict__ packed_grad, const int32_t* __restrict__ map, float* __restrict__ grad,
                                       int64_t n, float mul) {
     for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -831,6 +933,52 @@ extern "C" int rsb_bn_stats_finalize_chained(const void* z, double* sums, const 
                                              int64_t M, int32_t C, float eps, float momentum, void* stream) {
     return bn_stats_finalize_impl(z, sums, gamma, beta, running_mean, running_var, num_batches, mean, invstd, scale, shift, M, C, eps, momentum, stream,
                                   true);
+}
+
+extern "C" int rsb_bn_partials_finalize(const float* partials, int64_t rows, double* sums, const float* gamma, const float* beta, float* running_mean,
+                                        float* running_var, int64_t* num_batches, float* mean, float* invstd, float* scale, float* shift, int64_t M,
+                                        int32_t C, float eps, float momentum, int32_t chained, void* stream) {
+    if (!partials || rows <= 0 || !sums || !gamma || !beta || !mean || !invstd || !scale || !shift || M <= 0 || bad_c(C) || C < 32 ||
+        (reinterpret_cast<uintptr_t>(partials) & 15))
+        return set_error(RSB_E_INVALID, "bn_partials_finalize: bad arguments (C in 32..2048, power of two; partials 16B aligned)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!chained) {
+        cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * (2 * C * kRedSlots + 2), st);
+        if (e != cudaSuccess) return set_cuda_error(e, "bn_partials_finalize memset");
+    }
+    RedTail tail = {};
+    tail.gamma = gamma;
+    tail.beta = beta;
+    tail.running_mean = running_mean;
+    tail.running_var = running_var;
+    tail.num_batches = num_batches;
+    tail.mean = mean;
+    tail.invstd = invstd;
+    tail.scale = scale;
+    tail.shift = shift;
+    tail.eps = eps;
+    tail.momentum = momentum;
+    tail.self_clean = chained ? 1 : 0;
+    const int L = 2 * C;
+    const int tpr = L / 4 < 256 ? L / 4 : 256;
+    const int colblocks = L / (tpr * 4);
+    const int rows_per_iter = 256 / tpr;
+    int64_t bx = (rows + rows_per_iter * 4 - 1) / (rows_per_iter * 4);
+    const int64_t cap = (2 * num_sms() + colblocks - 1) / colblocks;
+    if (bx > cap) bx = cap;
+    if (bx < 1) bx = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(bx), static_cast<unsigned>(colblocks));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = chained ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, partial_reduce_kernel, partials, sums, rows, L, static_cast<int>(C), M, tail);
+    if (e != cudaSuccess) return set_cuda_error(e, "bn_partials_finalize launch");
+    return RSB_OK;
 }
 
 extern "C" int rsb_bn_finalize(const double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
@@ -980,6 +1128,14 @@ extern "C" int rsb_pack_weights(const float* src, const int32_t* map4, void* dst
     if (!src || !map4 || !dst || n <= 0) return set_error(RSB_E_INVALID, "pack_weights: bad arguments");
     pack_gather_kernel<<<tr_blocks(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, map4, static_cast<__half*>(dst), n);
     RSB_LAUNCH_CHECK("pack_weights launch");
+    return RSB_OK;
+}
+
+extern "C" int rsb_pack_weights1(const float* src, const int32_t* map1, void* dst, int64_t n, void* stream) {
+    if (!src || !map1 || !dst || n <= 0 || (n % 8) || (reinterpret_cast<uintptr_t>(dst) & 15) || (reinterpret_cast<uintptr_t>(map1) & 15))
+        return set_error(RSB_E_INVALID, "pack_weights1: bad arguments (n a multiple of 8, map and dst 16B aligned)");
+    pack_gather1_kernel<<<tr_blocks(n / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(src, map1, static_cast<__half*>(dst), n / 8);
+    RSB_LAUNCH_CHECK("pack_weights1 launch");
     return RSB_OK;
 }
 

@@ -27,6 +27,7 @@ from robosat_b200 import _lib
 from robosat_b200._lib import ConvSrc
 
 # BatchNorm kernels chained by programmatic dependent launch, accumulators cleaned by the kernels themselves (no memset launches)
+CONV_STATS = os.environ.get("RSB_CONV_STATS", "1") == "1"  # BatchNorm batch sums from the conv epilogue (profiles/r2_train.md)
 BN_CHAINED = os.environ.get("RSB_BN_CHAINED", "1") == "1"  # measured: 17.77 vs 18.03 ms per cfg-3 step (profiles/r2_train.md)
 from robosat_b200.engine import ConvOp, _src_dense, _src_parity, make_conv_desc
 
@@ -169,6 +170,7 @@ class UNetTrainEngine:
         self.fwd_ops, self.bwd_ops = [], []
         self.pack_list, self.unpack_list = [], []  # (wname, map, packed fp16) / (packed fp32 grad, map, wname)
         self._pack_all = None
+        self._stats_buf = {}
         self._pack_chunks = []  # [fp16 arena tensor, elements used]
         self._dw_chunks = []    # [fp32 arena tensor, elements used] packed weight gradients
         self._grads_flat, self._grad_offset, self._unpack_all = None, {}, None
@@ -231,8 +233,10 @@ class UNetTrainEngine:
 
     # ---------------------------------------------------------------- unit construction
     def _add_unit(self, name, wname, fwd_map, srcs, segs, cout, phases, tile_space, out, out_pitches, out_scale=(1, 1), relu=False,
-                  out_offset=0, residual=None):
-        """forward conv (raw output unless relu=True) + its weight-gradient plan"""
+                  out_offset=0, residual=None, stats=False, stats_slot=0):
+        """forward conv (raw output unless relu=True) + its weight-gradient plan. stats=True (a conv feeding BatchNorm): the
+        epilogue also writes the per-quarter-tile column sums / sums of squares that rsb_bn_partials_finalize folds, so the
+        batch statistics do not re-read z (RSB_CONV_STATS=0 keeps the separate reduction over z)."""
         u = Unit(name)
         u.wname = wname
         w = self.params[wname]
@@ -242,6 +246,18 @@ class UNetTrainEngine:
         wp = u.w_packed.view(phases * cout, K)
         u.desc = make_conv_desc(srcs, segs, wp, None, cout, phases, tile_space, out, out_pitches, out_scale=out_scale, relu=relu,
                                 out_offset_elems=out_offset, residual=residual)
+        u.stats, u.stats_rows = None, 0
+        if stats and CONV_STATS:
+            d = u.desc
+            rows = 4 * (-(-d.Wt // d.TW)) * (-(-d.Ht // d.TH)) * (-(-d.Nt // d.TN))
+            need = rows * 2 * cout
+            # one buffer per slot for every layer (stream ordered: written by the conv, folded before the next conv of the same slot
+            # runs), grown if a later layer is larger. Slot 1: the downsample conv, which runs between conv3 and bn3's statistics.
+            if self._stats_buf.get(stats_slot) is None or self._stats_buf[stats_slot].numel() < need:
+                self._stats_buf[stats_slot] = self._buf(need, dtype=torch.float32)
+            u.stats, u.stats_rows = self._stats_buf[stats_slot], rows
+            d.stats = u.stats.data_ptr()
+            d.stats_bytes = u.stats.numel() * 4
         u.fwd = self._conv_op(name, u.desc)
         nd = phases * cout * K
         if not self._dw_chunks or self._dw_chunks[-1][1] + nd > self._dw_chunks[-1][0].numel():
@@ -289,9 +305,10 @@ class UNetTrainEngine:
         op = self._conv_op(name, desc)
         return [("conv", op)]
 
-    def _bn(self, prefix, z, M, C):
+    def _bn(self, prefix, z, M, C, conv=None):
         b = Unit(prefix)
         b.prefix, b.z, b.M, b.C = prefix, z, M, C
+        b.partials, b.partial_rows = (conv.stats, conv.stats_rows) if conv is not None and conv.stats is not None else (None, 0)
         b.sums = self._buf(20 * C, dtype=torch.float64)  # 8 accumulator slots x {sum0, sum1} x C, arrival counter, backward coefficients
         b.mean, b.invstd, b.scale, b.shift = (self._buf(C, dtype=torch.float32) for _ in range(4))
         return b
@@ -322,8 +339,8 @@ class UNetTrainEngine:
         y0 = self._buf(N, H2, W2, 64)
         src = ConvSrc(self.s2d.data_ptr(), 16, Wp * 16, H2 * Wp * 16, 64, W2, H2, N)
         stem = self._add_unit("stem", "resnet.conv1.weight", map_stem_fwd(tuple(P["resnet.conv1.weight"].shape)), [src],
-                              [(0, t - 2, 0, 1) for t in range(4)], 64, 1, (W2, H2, N), z0, dense(H2, W2, 64))
-        bn0 = self._bn("resnet.bn1", z0, N * H2 * W2, 64)
+                              [(0, t - 2, 0, 1) for t in range(4)], 64, 1, (W2, H2, N), z0, dense(H2, W2, 64), stats=True)
+        bn0 = self._bn("resnet.bn1", z0, N * H2 * W2, 64, conv=stem)
         self._bn_fwd_ops(bn0, y0, None, True)
         p0 = self._buf(N, H4, W4, 64)
         self.fwd_ops.append(("maxpool", y0, p0, N, H2, W2, 64, 3, 2, 1))
@@ -351,8 +368,8 @@ class UNetTrainEngine:
                 z1, y1 = self._buf(N, curH, curW, planes), self._buf(N, curH, curW, planes)
                 u1 = self._add_unit(p + ".conv1", p + ".conv1.weight", map_conv_fwd(tuple(P[p + ".conv1.weight"].shape)),
                                     [_src_dense(cur, N, curH, curW, curC)], [(0, 0, 0, curC // 64)], planes, 1, (curW, curH, N), z1,
-                                    dense(curH, curW, planes))
-                b1 = self._bn(p + ".bn1", z1, M_in, planes)
+                                    dense(curH, curW, planes), stats=True)
+                b1 = self._bn(p + ".bn1", z1, M_in, planes, conv=u1)
                 self._bn_fwd_ops(b1, y1, None, True)
                 z2, y2 = self._buf(N, oH, oW, planes), self._buf(N, oH, oW, planes)
                 if stride == 1:
@@ -362,19 +379,21 @@ class UNetTrainEngine:
                     srcs2 = [_src_parity(y1, N, curH, curW, planes, ph, pw) for ph in range(2) for pw in range(2)]
                     segs2 = [(((kh - 1) % 2) * 2 + (kw - 1) % 2, (kh - 1) // 2, (kw - 1) // 2, planes // 64) for kh in range(3) for kw in range(3)]
                 u2 = self._add_unit(p + ".conv2", p + ".conv2.weight", map_conv_fwd(tuple(P[p + ".conv2.weight"].shape)), srcs2, segs2,
-                                    planes, 1, (oW, oH, N), z2, dense(oH, oW, planes))
-                b2 = self._bn(p + ".bn2", z2, M_out, planes)
+                                    planes, 1, (oW, oH, N), z2, dense(oH, oW, planes), stats=True)
+                b2 = self._bn(p + ".bn2", z2, M_out, planes, conv=u2)
                 self._bn_fwd_ops(b2, y2, None, True)
                 z3 = self._buf(N, oH, oW, outC)
                 u3 = self._add_unit(p + ".conv3", p + ".conv3.weight", map_conv_fwd(tuple(P[p + ".conv3.weight"].shape)),
-                                    [_src_dense(y2, N, oH, oW, planes)], [(0, 0, 0, planes // 64)], outC, 1, (oW, oH, N), z3, dense(oH, oW, outC))
-                b3 = self._bn(p + ".bn3", z3, M_out, outC)
+                                    [_src_dense(y2, N, oH, oW, planes)], [(0, 0, 0, planes // 64)], outC, 1, (oW, oH, N), z3, dense(oH, oW, outC),
+                                    stats=True)
+                b3 = self._bn(p + ".bn3", z3, M_out, outC, conv=u3)
                 if has_ds:
                     zd, idt = self._buf(N, oH, oW, outC), self._buf(N, oH, oW, outC)
                     sd_ = _src_dense(cur, N, curH, curW, curC) if stride == 1 else _src_parity(cur, N, curH, curW, curC, 0, 0)
                     ud = self._add_unit(p + ".downsample", p + ".downsample.0.weight", map_conv_fwd(tuple(P[p + ".downsample.0.weight"].shape)),
-                                        [sd_], [(0, 0, 0, curC // 64)], outC, 1, (oW, oH, N), zd, dense(oH, oW, outC))
-                    bd = self._bn(p + ".downsample.1", zd, M_out, outC)
+                                        [sd_], [(0, 0, 0, curC // 64)], outC, 1, (oW, oH, N), zd, dense(oH, oW, outC),
+                                        stats=True, stats_slot=1)
+                    bd = self._bn(p + ".downsample.1", zd, M_out, outC, conv=ud)
                     self._bn_fwd_ops(bd, idt, None, False)
                 else:
                     idt = cur
@@ -574,6 +593,13 @@ class UNetTrainEngine:
                 # batch sums + (in the reduction's last block) statistics, folded scale/shift and the running-stat update
                 b = op[1]
                 pf = b.prefix
+                if b.partials is not None:
+                    _lib.check(lib.rsb_bn_partials_finalize(b.partials.data_ptr(), b.partial_rows, b.sums.data_ptr(), P[pf + ".weight"].data_ptr(),
+                                                            P[pf + ".bias"].data_ptr(), P[pf + ".running_mean"].data_ptr(),
+                                                            P[pf + ".running_var"].data_ptr(), P[pf + ".num_batches_tracked"].data_ptr(),
+                                                            b.mean.data_ptr(), b.invstd.data_ptr(), b.scale.data_ptr(), b.shift.data_ptr(), b.M, b.C,
+                                                            BN_EPS, BN_MOMENTUM, 1 if BN_CHAINED else 0, st), "rsb_bn_partials_finalize")
+                    continue
                 _lib.check((lib.rsb_bn_stats_finalize_chained if BN_CHAINED else lib.rsb_bn_stats_finalize)(b.z.data_ptr(), b.sums.data_ptr(), P[pf + ".weight"].data_ptr(), P[pf + ".bias"].data_ptr(),
                                                      P[pf + ".running_mean"].data_ptr(), P[pf + ".running_var"].data_ptr(),
                                                      P[pf + ".num_batches_tracked"].data_ptr(), b.mean.data_ptr(), b.invstd.data_ptr(),
@@ -649,17 +675,32 @@ class UNetTrainEngine:
                 combined = []
                 for ci, (chunk, used) in enumerate(self._pack_chunks):
                     gmap = torch.full((used, 4), -1, dtype=torch.int32, device=self.device)
+                    kinds = []  # (offset, one source per element?) per layout of this chunk, in address order
                     for p, (w, m, d, c, off) in zip(ptrs, self.pack_list):
                         if c == ci:
                             gmap[off:off + m.shape[0]] = torch.where(m >= 0, m + int((p - base) // 4), m)
-                    combined.append((gmap, chunk, used))
+                            kinds.append((off, bool((m[:, 1:] < 0).all())))
+                    # runs of layouts with a single source per element (everything but the pre-summed nearest-x2 taps) go through
+                    # the 1-index kernel: 4 instead of 16 map bytes per element (layout offsets are multiples of 8 elements)
+                    kinds.sort()
+                    runs = []
+                    for off, single in kinds:
+                        if runs and runs[-1][2] == single:
+                            continue
+                        if runs:
+                            runs[-1][1] = off
+                        runs.append([off, used, single])
+                    for start, end, single in runs:
+                        m = gmap[start:end, 0].contiguous() if single else gmap[start:end].contiguous()
+                        combined.append((m, chunk[start:end], end - start, single))
             self._pack_all = {"ptrs": ptrs, "combined": combined, "base": base}
         if self._pack_all["combined"] is None:
             for w, m, d, _, _ in self.pack_list:
                 _lib.check(lib.rsb_pack_weights(P[w].data_ptr(), m.data_ptr(), d.data_ptr(), d.numel(), st), "rsb_pack_weights")
             return
-        for gmap, chunk, used in self._pack_all["combined"]:
-            _lib.check(lib.rsb_pack_weights(self._pack_all["base"], gmap.data_ptr(), chunk.data_ptr(), used, st), "rsb_pack_weights")
+        for gmap, chunk, used, single in self._pack_all["combined"]:
+            _lib.check((lib.rsb_pack_weights1 if single else lib.rsb_pack_weights)(self._pack_all["base"], gmap.data_ptr(), chunk.data_ptr(), used, st),
+                       "rsb_pack_weights")
 
     def forward(self, x):
         if self.plan_only:

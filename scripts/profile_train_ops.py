@@ -20,7 +20,16 @@ for _ in range(2):
     eng.forward(x)
     eng.backward(dl)
 torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(10):
+    eng.forward(x)
+    eng.backward(dl)
+b.record()
+torch.cuda.synchronize()
+step_ms = a.elapsed_time(b) / 10
 agg = collections.defaultdict(float)
+agg["fwd+bwd step (10 back to back, no optimizer)"] = step_ms
 rows = []
 for phase, ops, kw in (("fwd", eng.fwd_ops, {"x": x}), ("bwd", eng.bwd_ops, {"dlogits": dl})):
     for op in ops:

@@ -218,3 +218,82 @@ def test_row_split_case_matches_fp64_reference(i, cuda_device):
         err = (case.result() - ref).abs().max().item()
         print("%s: max|err| %.3e (%.2e of range)" % (case.name, err, err / scale))
         assert err <= 1e-5 * scale, case.name
+
+
+@pytest.mark.parametrize("kind,N,H,W,cin,cout,block_n,pair", [
+    ("1x1", 2, 24, 40, 64, 64, 32, 0),      # ragged tiles (W, H not multiples of the tile box), 32-column chunks
+    ("1x1", 3, 16, 16, 64, 256, 64, 0),
+    ("3x3", 2, 20, 36, 64, 128, 128, 0),    # 8 epilogue warps (two per lane quarter)
+    ("3x3s2", 2, 32, 32, 128, 256, 256, 0),
+    ("3x3", 4, 16, 16, 128, 256, 128, 1),   # CTA pair
+    ("1x1", 3, 24, 16, 256, 512, 256, 1),   # CTA pair, odd number of spatial tiles (last pair half empty)
+])
+def test_conv_stats_epilogue_and_partials_finalize(kind, N, H, W, cin, cout, block_n, pair, cuda_device):
+    """rsb_conv_desc.stats: the per-quarter-tile column sums of the fp16 outputs, written by the conv epilogue, fold to exactly
+    the BatchNorm batch statistics a reduction over the stored z gives (rsb_bn_stats_finalize): same mean / invstd / scale /
+    shift / running statistics to fp32 rounding; the conv output itself is bit-identical to the plain instance."""
+    lib = _lib.load()
+    stream = _lib.current_stream_ptr()
+    case = conv_cases.conv_case(kind, N, H, W, cin, cout, cuda_device, seed=11, relu=False, bias=False, block_n=block_n, cta_pair=bool(pair))
+    d = case.desc
+    plan = ctypes.c_void_p()
+    _lib.check(lib.rsb_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)), "plan_create")
+    _lib.check(lib.rsb_conv_run(plan, stream), "conv_run")
+    torch.cuda.synchronize()
+    plain = case.out.clone()
+    lib.rsb_conv_plan_destroy(plan)
+
+    rows = 4 * (-(-d.Wt // d.TW)) * (-(-d.Ht // d.TH)) * (-(-d.Nt // d.TN))
+    partials = torch.full((rows, 2, cout), float("nan"), dtype=torch.float32, device=cuda_device)
+    d.stats, d.stats_bytes = partials.data_ptr(), partials.numel() * 4
+    _lib.check(lib.rsb_conv_plan_create(ctypes.byref(d), ctypes.byref(plan)), "plan_create(stats)")
+    try:
+        case.out.zero_()
+        _lib.check(lib.rsb_conv_run(plan, stream), "conv_run(stats)")
+        torch.cuda.synchronize()
+        assert torch.equal(case.out, plain)
+        assert torch.isfinite(partials).all(), "a partial entry was not written"
+        z = case.out.reshape(-1, cout).double()
+        M = z.shape[0]
+        tot = partials.double().sum(0)
+        assert torch.allclose(tot[0], z.sum(0), rtol=1e-5, atol=1e-3)
+        assert torch.allclose(tot[1], (z * z).sum(0), rtol=1e-5, atol=1e-3)
+
+        def bn_buffers():
+            g = torch.Generator().manual_seed(3)
+            gamma = (torch.rand(cout, generator=g) + 0.5).to(cuda_device)
+            beta = torch.randn(cout, generator=g).to(cuda_device)
+            rm, rv = torch.zeros(cout, device=cuda_device), torch.ones(cout, device=cuda_device)
+            nb = torch.zeros(1, dtype=torch.int64, device=cuda_device)
+            outs = [torch.empty(cout, device=cuda_device) for _ in range(4)]
+            sums = torch.zeros(20 * cout, dtype=torch.float64, device=cuda_device)
+            return gamma, beta, rm, rv, nb, outs, sums
+
+        ga, be, rm, rv, nb, o1, sums = bn_buffers()
+        for chained in (1, 1, 0):  # chained twice: the accumulators are left clean for the next call
+            _lib.check(lib.rsb_bn_partials_finalize(partials.data_ptr(), rows, sums.data_ptr(), ga.data_ptr(), be.data_ptr(), rm.data_ptr(),
+                                                    rv.data_ptr(), nb.data_ptr(), *[t.data_ptr() for t in o1], M, cout, 1e-5, 0.1, chained,
+                                                    stream), "partials_finalize")
+        ga2, be2, rm2, rv2, nb2, o2, sums2 = bn_buffers()
+        for _ in range(3):
+            _lib.check(lib.rsb_bn_stats_finalize(case.out.data_ptr(), sums2.data_ptr(), ga2.data_ptr(), be2.data_ptr(), rm2.data_ptr(),
+                                                 rv2.data_ptr(), nb2.data_ptr(), *[t.data_ptr() for t in o2], M, cout, 1e-5, 0.1, stream),
+                       "stats_finalize")
+        torch.cuda.synchronize()
+        assert int(nb) == 3 and int(nb2) == 3
+        for a, b in zip(o1 + [rm, rv], o2 + [rm2, rv2]):
+            assert torch.allclose(a, b, rtol=2e-5, atol=2e-6), (a - b).abs().max()
+    finally:
+        lib.rsb_conv_plan_destroy(plan)
+
+
+def test_conv_stats_rejects_unsupported_descriptors(cuda_device):
+    lib = _lib.load()
+    case = conv_cases.conv_case("1x1", 1, 16, 16, 64, 64, cuda_device, relu=False, bias=False, residual=True)
+    buf = torch.zeros(1 << 16, dtype=torch.float32, device=cuda_device)
+    case.desc.stats, case.desc.stats_bytes = buf.data_ptr(), buf.numel() * 4
+    plan = ctypes.c_void_p()
+    assert lib.rsb_conv_plan_create(ctypes.byref(case.desc), ctypes.byref(plan)) == -1      # residual
+    case = conv_cases.conv_case("1x1", 1, 16, 16, 64, 64, cuda_device, relu=False, bias=False)
+    case.desc.stats, case.desc.stats_bytes = buf.data_ptr(), 64
+    assert lib.rsb_conv_plan_create(ctypes.byref(case.desc), ctypes.byref(plan)) == -1      # buffer too small

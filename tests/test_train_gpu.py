@@ -162,6 +162,20 @@ def test_relu_maxpool_final_pack_kernels(cuda_device):
     wref = wt.clone().requires_grad_(True)
     (pack_upsample_phases(wref).reshape(-1) * gp * 0.5).sum().backward()
     assert torch.allclose(grad.cpu(), wref.grad, atol=1e-5)
+    # single-source layouts: the 1-index kernel equals the 4-index one (and the whole-engine re-pack equals the per-layout one)
+    from robosat_b200.train_engine import map_conv_fwd
+
+    wc = torch.randn((64, 128, 3, 3), generator=g).to(d)
+    m4 = torch.from_numpy(map_conv_fwd(tuple(wc.shape))).to(d)
+    assert bool((m4[:, 1:] < 0).all()) and m4.shape[0] % 8 == 0
+    m1 = m4[:, 0].contiguous()
+    m1[5], m4[5, 0] = -1, -1  # a hole packs as zero
+    d4, d1 = (torch.full((m4.shape[0],), 7.0, dtype=torch.float16, device=d) for _ in range(2))
+    _lib.check(lib.rsb_pack_weights(wc.data_ptr(), m4.data_ptr(), d4.data_ptr(), m4.shape[0], st), "pack")
+    _lib.check(lib.rsb_pack_weights1(wc.data_ptr(), m1.data_ptr(), d1.data_ptr(), m1.shape[0], st), "pack1")
+    torch.cuda.synchronize()
+    assert torch.equal(d1, d4) and float(d1[5]) == 0.0
+    assert lib.rsb_pack_weights1(wc.data_ptr(), m1.data_ptr(), d1.data_ptr(), 12, st) == -1  # not a multiple of 8
 
 
 @pytest.mark.parametrize("i", range(len(conv_cases.default_cases(None)) - 2))  # head cases have no packed fp16 output
