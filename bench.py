@@ -103,7 +103,10 @@ class ClockSampler:
 # reference arm: the unmodified reference on the host cores
 # ----------------------------------------------------------------------------------------------------------------------
 def host_threads():
-    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    """cores this process can really use: min(affinity mask, cgroup CPU quota)"""
+    from robosat_b200.hostinfo import usable_cores
+
+    return usable_cores()
 
 
 def cpu_reference_leg(steps, warmup, tiles_per_step, threads=None):

@@ -249,7 +249,9 @@ int rsb_head_argmax(const float* logits, uint8_t* mask, int32_t N, int32_t C, in
 int rsb_png_decode_rgb(const uint8_t* file_bytes_host, int64_t n, uint8_t* out_rgb_host, int32_t w_expected, int32_t h_expected);
 int rsb_png_read_rgb(const char* path, uint8_t* out_rgb_host, int32_t w_expected, int32_t h_expected);
 /* `Image.fromarray(q, mode="P"); putpalette(palette); save(path)` (robosat/tools/predict.py:105-113): 8-bit palette PNG,
- * palette_rgb_host uint8 [entries][3]; level = zlib level (0-9, <0 default). encode returns the byte count or a negative code. */
+ * palette_rgb_host uint8 [entries][3]; level = zlib level (0-9, <0 default). Noise-like rasters (a level-1 probe of 16 rows does not
+ * shrink below 90 %) are coded with zlib's Z_RLE strategy: same size, a third of the time. encode returns the byte count or a
+ * negative code. */
 int64_t rsb_png_encode_p8(const uint8_t* pixels_host, int32_t w, int32_t h, const uint8_t* palette_rgb_host, int32_t entries, int32_t level,
                           uint8_t* out_host, int64_t capacity);
 int rsb_png_write_p8(const char* path, const uint8_t* pixels_host, int32_t w, int32_t h, const uint8_t* palette_rgb_host, int32_t entries,

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 from PIL import Image
 
+from robosat_b200.hostinfo import usable_cores
 from robosat_b200 import _lib
 from robosat_b200.colors import make_palette
 from robosat_b200.tiles import tiles_from_slippy_map
@@ -60,7 +61,7 @@ def main(args, batch=64):
     assert all(set(ix) == set(indices[0]) for ix in indices), "tilesets in sync"  # masks.py:38
     palette = make_palette("denim", "orange")
     K = len(indices)
-    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 8)) as pool:
+    with ThreadPoolExecutor(max_workers=min(32, usable_cores())) as pool:
         pending = []
         for i in range(0, len(keys), batch):
             part = keys[i:i + batch]

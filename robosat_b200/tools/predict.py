@@ -105,16 +105,19 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
     st = stats if stats is not None else {}
     size = args.tile_size + 2 * args.overlap
     palette = continuous_palette_for_color("pink", 256)
-    # host cores of this rank, split between the PNG-encode pool and the decode pool (both run GIL-free C code)
-    cores = max(2, (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 8)) // max(world, 1))
-    # The codec threads are busy C++ threads: leave the launching (main) thread and the driver's threads two cores and do not take
-    # much more than the GPU can consume (2 400 tiles/s x ~7 ms of decode + encode per tile = ~18 threads if they were always
-    # busy; a ticket of 32-40 tiles keeps 48 threads busy for one round instead of two); with every hardware thread occupied the
-    # main thread was descheduled and the device ran empty (profiles/r2_cfg4.md). Decoding a 512x512 RGB tile
-    # costs ~5.6 ms, encoding a probability mask 1-4 ms: two thirds of the budget decode, one third encodes.
-    budget = max(3, min(72, cores - 2))
-    pool_threads = int(os.environ.get("RSB_PNG_THREADS", "0")) or max(1, budget // 3)
-    default_decode_threads = int(os.environ.get("RSB_DECODE_THREADS", "0")) or max(2, budget - budget // 3)
+    # host cores of this rank -- min(affinity, cgroup CPU quota): the GPU boxes report 128 hardware threads under a quota of 16
+    # cores -- split between the PNG-decode and PNG-encode pools (both run GIL-free C++ threads of the library).
+    # More busy threads than the quota allows get the WHOLE process throttled for the rest of each scheduler period, the launching
+    # thread included: the device then runs empty however deep the pipeline is (profiles/r2_cfg4.md). So: leave two cores to the
+    # main / consumer threads and the driver, and split the rest by measured cost: ~4.4 ms to decode a 512x512 RGB tile, ~1.3 ms
+    # to encode a probability mask (on one of those cores).
+    from robosat_b200.hostinfo import usable_cores
+
+    cores = max(2, usable_cores() // max(world, 1))
+    budget = max(2, min(72, cores - 2))
+    pool_threads = int(os.environ.get("RSB_PNG_THREADS", "0")) or max(1, budget // 4)
+    default_decode_threads = int(os.environ.get("RSB_DECODE_THREADS", "0")) or max(1, budget - max(1, budget // 4))
+    st.update(host_cores=cores)
     st.update(pool_threads=pool_threads, gpu_wait_s=0.0, png_cpu_s=0.0)
 
     def progress(it, total):

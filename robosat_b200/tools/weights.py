@@ -12,6 +12,7 @@ import numpy as np
 import torch
 from PIL import Image
 
+from robosat_b200.hostinfo import usable_cores
 from robosat_b200 import _lib
 from robosat_b200.config import load_config
 from robosat_b200.tiles import tiles_from_slippy_map
@@ -56,7 +57,7 @@ def main(args, batch=64):
     paths = [p for _, p in sorted(tiles_from_slippy_map(os.path.join(path, "training", "labels")), key=lambda tp: tuple(int(v) for v in (tp[0].z, tp[0].x, tp[0].y)))]
     n = 0
     counts = torch.zeros(num_classes, dtype=torch.int64, device=device)
-    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 8)) as pool:
+    with ThreadPoolExecutor(max_workers=min(32, usable_cores())) as pool:
         for i in range(0, len(paths), batch):
             arrays = list(pool.map(_load, paths[i:i + batch]))
             flat = torch.from_numpy(np.concatenate([a.ravel() for a in arrays]))

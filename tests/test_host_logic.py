@@ -179,3 +179,29 @@ def test_cta_pair_policy_respects_kernel_constraints():
     for name in ("dec0", "dec1", "dec3", "resnet.layer2.1.conv2", "resnet.layer3.2.conv2", "resnet.layer4.1.conv2"):
         assert name in paired, name
     assert "dec2" not in paired and "stem" not in paired  # Cout = 64: narrow tiles stay on one CTA
+
+
+def test_usable_cores_honours_the_cgroup_quota(monkeypatch, tmp_path):
+    """A container's CPU quota (cgroup cpu.max), not the hardware-thread count, sizes the codec pools"""
+    import builtins
+
+    from robosat_b200 import hostinfo
+
+    real_open = builtins.open
+
+    def fake(content):
+        def _open(path, *a, **k):
+            if path == "/sys/fs/cgroup/cpu.max":
+                f = tmp_path / "cpu.max"
+                f.write_text(content)
+                return real_open(f, *a, **k)
+            return real_open(path, *a, **k)
+        return _open
+
+    monkeypatch.setattr(hostinfo.os, "sched_getaffinity", lambda pid: set(range(128)), raising=False)
+    monkeypatch.setattr(builtins, "open", fake("1600000 100000\n"))
+    assert hostinfo.usable_cores() == 16
+    monkeypatch.setattr(builtins, "open", fake("max 100000\n"))
+    assert hostinfo.usable_cores() == 128
+    monkeypatch.setattr(builtins, "open", fake("50000 100000\n"))
+    assert hostinfo.usable_cores() == 1

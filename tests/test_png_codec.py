@@ -68,6 +68,29 @@ def test_encode_p8_round_trips_through_pil(level, tmp_path):
         assert im.getpalette()[:768] == pal  # what `rs masks` / a viewer reads back is what predict.py:105-108 would have written
 
 
+def test_encode_strategy_follows_the_content(tmp_path):
+    """noise-like masks skip deflate's string matcher (Z_RLE) without growing; compressible masks keep the default strategy"""
+    import os
+    import zlib
+
+    pal = colors.continuous_palette_for_color("pink", 256)
+    rs = np.random.RandomState(1)
+    noisy = rs.randint(0, 256, (256, 256)).astype(np.uint8)
+    yy, xx = np.mgrid[0:256, 0:256]
+    soft = np.clip((np.sin(xx / 31.0) + np.cos(yy / 23.0)) * 400 + 128, 0, 255).astype(np.uint8)
+    for name, arr, same_as_default in (("noisy", noisy, False), ("soft", soft, True)):
+        path = str(tmp_path / (name + ".png"))
+        _lib.check(_lib.load().rsb_png_write_p8(path.encode(), arr.ctypes.data, 256, 256, bytes(pal), 256, 6), "write")
+        assert np.array_equal(np.asarray(Image.open(path)), arr)
+        raw = np.concatenate([np.zeros((256, 1), np.uint8), arr], 1).tobytes()
+        default = len(zlib.compress(raw, 6))
+        overhead = 8 + 3 * 12 + 13 + 768 + 12  # signature, IHDR / PLTE / IDAT / IEND framing
+        if same_as_default:
+            assert os.path.getsize(path) == default + overhead
+        else:
+            assert os.path.getsize(path) <= 1.01 * default + overhead
+
+
 def test_tools_use_the_native_codec_and_agree_with_pil(tmp_path, monkeypatch):
     from robosat_b200 import stitch
     from robosat_b200.tools import predict
