@@ -27,6 +27,7 @@ from robosat_b200 import _lib
 from robosat_b200._lib import ConvSrc
 
 # BatchNorm kernels chained by programmatic dependent launch, accumulators cleaned by the kernels themselves (no memset launches)
+TRAIN_GRAPH = os.environ.get("RSB_TRAIN_GRAPH", "1") == "1"  # forward / backward op lists replayed from CUDA graphs
 CONV_STATS = os.environ.get("RSB_CONV_STATS", "1") == "1"  # BatchNorm batch sums from the conv epilogue (profiles/r2_train.md)
 BN_CHAINED = os.environ.get("RSB_BN_CHAINED", "1") == "1"  # measured: 17.77 vs 18.03 ms per cfg-3 step (profiles/r2_train.md)
 from robosat_b200.engine import ConvOp, _src_dense, _src_parity, make_conv_desc
@@ -171,6 +172,8 @@ class UNetTrainEngine:
         self.pack_list, self.unpack_list = [], []  # (wname, map, packed fp16) / (packed fp32 grad, map, wname)
         self._pack_all = None
         self._stats_buf = {}
+        self._graphs = {}
+        self.use_graph = TRAIN_GRAPH and not plan_only
         self._pack_chunks = []  # [fp16 arena tensor, elements used]
         self._dw_chunks = []    # [fp32 arena tensor, elements used] packed weight gradients
         self._grads_flat, self._grad_offset, self._unpack_all = None, {}, None
@@ -702,11 +705,52 @@ class UNetTrainEngine:
             _lib.check((lib.rsb_pack_weights1 if single else lib.rsb_pack_weights)(self._pack_all["base"], gmap.data_ptr(), chunk.data_ptr(), used, st),
                        "rsb_pack_weights")
 
+    # ---------------------------------------------------------------- CUDA-graph replay of the two op lists
+    # A step is ~520 launches of mostly 10-40 us kernels; replaying each op list from one CUDA graph removes the launch gaps
+    # between them (16.2 -> 15.5 ms for forward + backward at 16 x 512^2, profiles/r2_train.md). The lists only touch static
+    # buffers; what varies per call (the input tensor, dlogits) is copied into a static buffer first, and everything baked into
+    # kernel arguments at capture time (parameter addresses, the loss scale) is part of the graph's key: a change re-captures.
+    def _graph_key(self, static):
+        return (static.data_ptr(), float(self.loss_scale), tuple(v.data_ptr() for v in self.params.values()))
+
+    def _replay(self, which, ops, src, **kw):
+        """run `ops` with the per-call tensor `src` through the graph of list `which` ("fwd" / "bwd"); the first two calls of a
+        key run eagerly (lazy tables are built there), the third captures."""
+        slot = self._graphs.setdefault((which, src.dtype, tuple(src.shape)), {"static": torch.empty_like(src), "calls": 0, "graph": None, "key": None})
+        static = slot["static"]
+        static.copy_(src)
+        key = self._graph_key(static)
+        if slot["key"] != key:
+            slot.update(key=key, calls=0, graph=None)
+        name = "x" if which == "fwd" else "dlogits"
+        if slot["graph"] is None:
+            slot["calls"] += 1
+            if slot["calls"] <= 2 or torch.cuda.is_current_stream_capturing():
+                self._run(ops, **{name: static}, **kw)
+                return
+            graph = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                    self._run(ops, **{name: static}, **kw)
+            except Exception as exc:  # noqa: BLE001 -- a failed capture leaves the eager path, loudly
+                import warnings
+
+                warnings.warn("robosat_b200: CUDA-graph capture of the training %s plan failed (%r); running it kernel by kernel" % (which, exc))
+                self.use_graph = False
+                torch.cuda.synchronize()
+                self._run(ops, **{name: static}, **kw)
+                return
+            slot["graph"] = graph
+        slot["graph"].replay()
+
     def forward(self, x):
         if self.plan_only:
             raise _lib.RsbError("UNetTrainEngine was built with plan_only=True; there is no CPU execution path")
         assert x.is_cuda and x.is_contiguous()
-        self._run(self.fwd_ops, x=x)
+        if self.use_graph:
+            self._replay("fwd", self.fwd_ops, x)
+        else:
+            self._run(self.fwd_ops, x=x)
         return self.logits
 
     def accumulate_into(self, targets):
@@ -735,5 +779,8 @@ class UNetTrainEngine:
             raise _lib.RsbError("UNetTrainEngine was built with plan_only=True; there is no CPU execution path")
         assert dlogits.is_cuda and dlogits.is_contiguous() and dlogits.dtype == torch.float32
         self._grad("final.bias")
-        self._run(self.bwd_ops, dlogits=dlogits)
+        if self.use_graph:
+            self._replay("bwd", self.bwd_ops, dlogits)
+        else:
+            self._run(self.bwd_ops, dlogits=dlogits)
         return self.grads

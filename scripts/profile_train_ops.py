@@ -21,38 +21,21 @@ for _ in range(2):
     eng.backward(dl)
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-a.record()
-for _ in range(10):
-    eng.forward(x)
-    eng.backward(dl)
-b.record()
-torch.cuda.synchronize()
-step_ms = a.elapsed_time(b) / 10
 agg = collections.defaultdict(float)
-agg["fwd+bwd step (10 back to back, no optimizer)"] = step_ms
-if os.environ.get("RSB_PROFILE_GRAPH", "1") == "1":
-    # the same two op lists replayed from ONE CUDA graph: what do ~520 launches cost in launch gaps?
-    try:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            eng.forward(x)
-            eng.backward(dl)
-        torch.cuda.current_stream().wait_stream(side)
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            eng.forward(x)
-            eng.backward(dl)
-        graph.replay()
-        torch.cuda.synchronize()
-        a.record()
-        for _ in range(10):
-            graph.replay()
-        b.record()
-        torch.cuda.synchronize()
-        agg["fwd+bwd step replayed from one CUDA graph"] = a.elapsed_time(b) / 10
-    except Exception as exc:  # noqa: BLE001
-        agg["graph capture failed: %r" % (exc,)] = 0.0
+for label, use_graph in (("fwd+bwd step, kernel by kernel (10 back to back, no optimizer)", False),
+                         ("fwd+bwd step, op lists replayed from CUDA graphs (default)", True)):
+    eng.use_graph = use_graph
+    for _ in range(4):  # a graph is captured on the third call
+        eng.forward(x)
+        eng.backward(dl)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(10):
+        eng.forward(x)
+        eng.backward(dl)
+    b.record()
+    torch.cuda.synchronize()
+    agg[label] = a.elapsed_time(b) / 10
 rows = []
 for phase, ops, kw in (("fwd", eng.fwd_ops, {"x": x}), ("bwd", eng.bwd_ops, {"dlogits": dl})):
     for op in ops:

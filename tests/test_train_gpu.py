@@ -483,3 +483,32 @@ def test_backward_is_deterministic(cuda_device):
     assert getattr(eng, "_wgrad_scratch", None) is not None, "no wgrad plan needed a scratch: the test would be vacuous"
     for k in runs[0]:
         assert torch.equal(runs[0][k], runs[1][k]), k
+
+
+def test_graph_replay_equals_kernel_by_kernel(cuda_device):
+    """The forward / backward op lists replayed from CUDA graphs (default, RSB_TRAIN_GRAPH=1: captured on the third call of a
+    key) give bit-identical logits, gradients and running statistics to launching the same lists kernel by kernel, also after
+    the loss scale changes (re-capture) and with a fresh input tensor at every call (static input copy)."""
+    sd0, x, params_a, eng_a = _engine_pair(2, 2, 128, cuda_device)
+    _, _, params_b, eng_b = _engine_pair(2, 2, 128, cuda_device)
+    assert eng_a.use_graph and eng_b.use_graph
+    eng_b.use_graph = False
+    g = torch.Generator().manual_seed(5)
+    for step in range(7):
+        if step == 5:
+            eng_a.loss_scale = eng_b.loss_scale = 1024.0
+        xs = (x + 0.01 * step).to(cuda_device)  # a new tensor (new address) per step
+        dl = (torch.randn((2, 2, 128, 128), generator=g) * 1e-3).to(cuda_device)
+        la = eng_a.forward(xs).clone()
+        lb = eng_b.forward(xs.clone()).clone()
+        ga = {k: v.clone() for k, v in eng_a.backward(dl).items()}
+        gb = {k: v.clone() for k, v in eng_b.backward(dl.clone()).items()}
+        torch.cuda.synchronize()
+        assert torch.equal(la, lb), step
+        for k in ga:
+            assert torch.equal(ga[k], gb[k]), (step, k)
+    assert any(s["graph"] is not None for s in eng_a._graphs.values()), "no graph was captured: the test would be vacuous"
+    assert not eng_b._graphs
+    for k in params_a:
+        if k.endswith("running_mean") or k.endswith("running_var") or k.endswith("num_batches_tracked"):
+            assert torch.equal(params_a[k], params_b[k]), k
