@@ -698,7 +698,19 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to STDOUT when the communicator is created if NCCL_DEBUG is VERSION / WARN (the GPU boxes
+        # export it): stdout must carry the one JSON line only, so the communicator is created here with fd 1 pointed at stderr.
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.all_reduce(torch.zeros(1, device=dev))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     # weights: rank 0 materialises the checkpoint; ONE NCCL broadcast of the flat fp32 state_dict (the predict path's only collective)
     sd = synth.make_state_dict(CLASSES, seed=0)
