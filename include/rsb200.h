@@ -246,6 +246,9 @@ int rsb_head_argmax(const float* logits, uint8_t* mask, int32_t N, int32_t C, in
  */
 /* `Image.open(path).convert("RGB")` (robosat/tiles.py:150-159,181) for 8-bit non-interlaced PNGs (gray, RGB, palette, +alpha):
  * out_rgb_host uint8 [h][w][3]. RSB_E_UNSUPPORTED for other PNG flavours / non-PNG files (the caller then uses PIL). */
+/* zlib-wrapped DEFLATE stream (RFC 1950 / 1951; what PNG IDAT chunks carry) -> exactly out_len bytes, Adler-32 verified, with the
+ * library's own decoder (csrc/rsb_inflate.cpp); RSB_E_INVALID for anything it rejects (the PNG reader then asks zlib). */
+int rsb_zlib_inflate(const uint8_t* stream_host, int64_t n, uint8_t* out_host, int64_t out_len);
 int rsb_png_decode_rgb(const uint8_t* file_bytes_host, int64_t n, uint8_t* out_rgb_host, int32_t w_expected, int32_t h_expected);
 int rsb_png_read_rgb(const char* path, uint8_t* out_rgb_host, int32_t w_expected, int32_t h_expected);
 /* `Image.fromarray(q, mode="P"); putpalette(palette); save(path)` (robosat/tools/predict.py:105-113): 8-bit palette PNG,

@@ -11,7 +11,8 @@ for f in rsb_host rsb_conv rsb_conv_row rsb_elementwise rsb_loss rsb_train rsb_w
 done
 # host-side PNG codec (plain C++ over zlib)
 ${CXX:-g++} -O3 -std=c++17 -fPIC -I/usr/local/cuda/include -c rsb_png.cpp -o rsb_png.o
-$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../librsb200.so $OBJS rsb_png.o -cudart static -lz -lpthread
+${CXX:-g++} -O3 -std=c++17 -fPIC -c rsb_inflate.cpp -o rsb_inflate.o
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../librsb200.so $OBJS rsb_png.o rsb_inflate.o -cudart static -lz -lpthread
 # bring-up probes: their own library, not part of the product (include/rsb200_debug.h)
 $NVCC $FLAGS -c rsb_debug.cu -o rsb_debug.o 2> rsb_debug.ptxas.log || { cat rsb_debug.ptxas.log; exit 1; }
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o ../librsb200_debug.so rsb_debug.o rsb_host.o -cudart static

@@ -109,3 +109,73 @@ def test_tools_use_the_native_codec_and_agree_with_pil(tmp_path, monkeypatch):
     predict._save_png(str(tmp_path / "b"), pal, 1, 2, 3, q)
     a, b = Image.open(tmp_path / "a" / "3" / "1" / "2.png"), Image.open(tmp_path / "b" / "3" / "1" / "2.png")
     assert a.mode == b.mode == "P" and np.array_equal(np.asarray(a), np.asarray(b)) and a.getpalette()[:768] == b.getpalette()[:768]
+
+
+def _own_inflate(stream, n):
+    out = np.empty(max(n, 1), dtype=np.uint8)
+    rc = _lib.load().rsb_zlib_inflate(stream, len(stream), out.ctypes.data, n)
+    return rc, out[:n].tobytes()
+
+
+def test_own_inflate_matches_zlib_on_every_block_type_and_strategy():
+    """csrc/rsb_inflate.cpp (the PNG reader's DEFLATE decoder) against zlib: stored / fixed / dynamic blocks, literal-only and
+    match-heavy data, long runs (distance 1), maximum distances, multi-block streams"""
+    import os
+    import zlib
+
+    rs = np.random.RandomState(0)
+    text = open(__file__, "rb").read()
+    cases = [b"", b"a", b"hello hello hello hello hello", bytes(70000), os.urandom(70000), bytes(rs.randint(0, 4, 200000).astype(np.uint8)),
+             (b"abcdefgh" * 5000) + os.urandom(1000) + (b"xy" * 40000), text * 20,
+             bytes(rs.randint(0, 256, 40000).astype(np.uint8)) * 3]  # repeats at distance 40 000 > 32 K: literals again
+    for i, c in enumerate(cases):
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED):
+                co = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strategy)
+                stream = co.compress(c) + co.flush()
+                rc, got = _own_inflate(stream, len(c))
+                assert rc == 0 and got == c, (i, level, strategy, _lib.last_error())
+
+
+def test_own_inflate_rejects_damaged_streams_and_the_reader_falls_back():
+    """A flipped bit, a truncated stream or a wrong expected size is an error, never a silent wrong answer (Adler-32 is verified) and
+    never an out-of-bounds access; window sizes / dictionaries the decoder does not take are left to zlib by the PNG reader."""
+    import zlib
+
+    rs = np.random.RandomState(1)
+    text = open(__file__, "rb").read() * 4
+    stream = zlib.compress(text, 6)
+    for _ in range(400):
+        b = bytearray(stream)
+        b[rs.randint(2, len(b))] ^= 1 << rs.randint(0, 8)
+        rc, got = _own_inflate(bytes(b), len(text))
+        assert rc != 0 or got == text
+    for cut in (6, 10, 100, len(stream) // 2, len(stream) - 1):
+        assert _own_inflate(stream[:cut], len(text))[0] != 0
+    assert _own_inflate(stream, len(text) - 1)[0] != 0 and _own_inflate(stream, len(text) + 1)[0] != 0
+
+
+def test_png_reader_is_identical_with_either_inflate(monkeypatch):
+    """the same tiles through the library inflate (default) and through zlib (RSB_INFLATE=zlib, read once per process: checked in
+    a child) decode to the same pixels as PIL"""
+    import subprocess
+    import sys
+
+    code = ("import io, sys, numpy as np\n"
+            "from PIL import Image\n"
+            "from robosat_b200 import _lib, synth\n"
+            "u8 = synth.make_tiles_u8(3, 256, seed=5).numpy()\n"
+            "for arr in u8:\n"
+            "    for level in (1, 6, 9):\n"
+            "        b = io.BytesIO(); Image.fromarray(arr).save(b, format='PNG', compress_level=level); raw = b.getvalue()\n"
+            "        out = np.zeros((256, 256, 3), np.uint8)\n"
+            "        assert _lib.load().rsb_png_decode_rgb(raw, len(raw), out.ctypes.data, 256, 256) == 0\n"
+            "        assert np.array_equal(out, arr)\n"
+            "print('ok')\n")
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for mode in ("own", "zlib"):
+        env = dict(os.environ, RSB_INFLATE=mode, PYTHONPATH=root)
+        res = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0 and res.stdout.strip().endswith("ok"), (mode, res.stderr[-800:])
