@@ -344,6 +344,41 @@ def default_precision():
     return p
 
 
+_PLAN_TABLE = None
+
+
+def plan_table():
+    """Measured tile choices per (precision, batch, height, width): `robosat_b200/plans_b200.json`, written by
+    scripts/tune_plans.py on a B200 (every layer timed alone for each (block_n, CTA pair) candidate; an entry exists only where
+    a candidate beat the modelled choice by >= 3 %). RSB_PLAN_TABLE=<path> reads another file, RSB_PLAN_TABLE=0 disables it."""
+    global _PLAN_TABLE
+    if _PLAN_TABLE is None:
+        path = os.environ.get("RSB_PLAN_TABLE", os.path.join(os.path.dirname(os.path.abspath(__file__)), "plans_b200.json"))
+        table = {}
+        if path not in ("0", "") and os.path.exists(path):
+            import json
+
+            with open(path) as fp:
+                table = json.load(fp).get("plans", {})
+        _PLAN_TABLE = table
+    return _PLAN_TABLE
+
+
+def _override_valid(ov, cout, tile_space, split, has_res):
+    """what rsb_conv_plan_create would accept (include/rsb200.h), checked here so that the GPU-less plan_only mode agrees"""
+    bn, pair = int(ov.get("block_n", 0)), bool(ov.get("cta_pair", 0))
+    if bn not in (32, 64, 128, 256) or cout % bn:
+        return False
+    Wt, Ht, Nt = tile_space
+    TW, TH, TN = choose_tile(Wt, Ht, Nt)
+    m_tiles = -(-Wt // TW) * -(-Ht // TH) * -(-Nt // TN)
+    if pair and (bn < 128 or m_tiles < 2 or not CTA_PAIR):
+        return False
+    if split and has_res and bn == 256 and not pair:
+        return False
+    return True
+
+
 class UNetEngine:
     """Static-shape inference plan for `UNet(num_classes)` on one GPU.
 
@@ -351,9 +386,12 @@ class UNetEngine:
     (hi*lo + lo*hi + hi*hi, fp32 accumulate) -- logits agree with the fp32 reference to ~1e-5 relative, argmax up to
     the fp32 noise floor. precision="fast": single fp16 operands (one MMA per K step, ~3x the throughput, logits ~2e-3)."""
 
-    def __init__(self, state_dict, num_classes, batch, height, width, device="cuda", plan_only=False, use_row=True, precision=None):
+    def __init__(self, state_dict, num_classes, batch, height, width, device="cuda", plan_only=False, use_row=True, precision=None,
+                 plan_overrides=None):
         """plan_only=True builds buffers and descriptors on `device` without touching the GPU library
-        (used by the CPU tests, which execute the descriptors with tests/emulate.py)."""
+        (used by the CPU tests, which execute the descriptors with tests/emulate.py).
+        plan_overrides: {layer name: {"block_n": int, "cta_pair": 0|1}} replacing the modelled tile choice of those layers
+        (None: the measured table `plan_table()` has for this precision and shape, if any; {}: the model only)."""
         assert height % 32 == 0 and width % 32 == 0, "image resolution has to be divisible by 32 for resnet"
         # the reference's torch.cat([enc4, center]) (unet.py:134) only works when enc4's extent is even
         assert height % 64 == 0 and width % 64 == 0, "enc4 must have even extents (input divisible by 64), as in the reference"
@@ -361,6 +399,8 @@ class UNetEngine:
         self.precision = precision or default_precision()
         assert self.precision in PRECISIONS, self.precision
         self.strict = self.precision == "strict"
+        self._overrides = plan_overrides if plan_overrides is not None else plan_table().get(
+            "%s:%dx%dx%d" % (self.precision, batch, height, width), {})
         # line-buffer kernel for the >= 128-pixel-wide, small-Cout layers (layer1 3x3, dec4, dec5 + final). In strict precision
         # only dec5 + final has one (resident weights + a 2-plane row ring must fit in shared memory)
         self.use_row_head = use_row
@@ -420,11 +460,23 @@ class UNetEngine:
     def _conv(self, name, srcs, segs, w, b, cout, phases, tile_space, out, out_pitches, residual=None, **kw):
         wd, scale = self._wts(w)
         bd = self._dev(b, torch.float32) if b is not None else None
-        desc = make_conv_desc(srcs, segs, wd, bd, cout, phases, tile_space, out, out_pitches, residual=residual,
-                              split=self.strict, acc_scale=scale, out_plane=self._plane(out) if out is not None else 0,
-                              res_plane=self._plane(residual) if residual is not None else 0,
-                              scratch=self._scratch() if self.strict else None, **kw)
-        op = ConvOp(name, desc, (wd, bd), create_plan=not self.plan_only)
+
+        def build(extra):
+            desc = make_conv_desc(srcs, segs, wd, bd, cout, phases, tile_space, out, out_pitches, residual=residual,
+                                  split=self.strict, acc_scale=scale, out_plane=self._plane(out) if out is not None else 0,
+                                  res_plane=self._plane(residual) if residual is not None else 0,
+                                  scratch=self._scratch() if self.strict else None, **dict(kw, **extra))
+            return ConvOp(name, desc, (wd, bd), create_plan=not self.plan_only)
+
+        op = None
+        ov = self._overrides.get(name)
+        if ov and "block_n" not in kw and "cta_pair" not in kw and "head" not in kw and _override_valid(ov, cout, tile_space, self.strict, residual is not None):
+            try:
+                op = build({"block_n": int(ov["block_n"]), "cta_pair": bool(ov["cta_pair"])})
+            except _lib.RsbError:  # e.g. no shared memory for this tile on this device: the modelled choice always fits
+                op = None
+        if op is None:
+            op = build({})
         self.ops.append(("conv", op))
         return op
 

@@ -164,7 +164,7 @@ def test_cta_pair_policy_respects_kernel_constraints():
     from robosat_b200 import synth
     from robosat_b200.engine import UNetEngine
 
-    eng = UNetEngine(synth.make_state_dict(2, seed=0), 2, 32, 512, 512, device="cpu", plan_only=True, precision="fast")
+    eng = UNetEngine(synth.make_state_dict(2, seed=0), 2, 32, 512, 512, device="cpu", plan_only=True, precision="fast", plan_overrides={})
     paired = {}
     for op in eng.ops:
         if op[0] != "conv" or not hasattr(op[1].desc, "nseg"):
@@ -205,3 +205,26 @@ def test_usable_cores_honours_the_cgroup_quota(monkeypatch, tmp_path):
     assert hostinfo.usable_cores() == 128
     monkeypatch.setattr(builtins, "open", fake("50000 100000\n"))
     assert hostinfo.usable_cores() == 1
+
+
+def test_plan_overrides_change_the_tiles_not_the_result():
+    """engine.plan_table() / plan_overrides: a measured (block_n, CTA pair) choice replaces the modelled one where it is valid for
+    the layer, is ignored where it is not, and the emulated plan computes the same logits either way"""
+    from robosat_b200 import synth
+    from robosat_b200.engine import UNetEngine
+
+    sd = synth.make_state_dict(2, seed=0)
+    x = synth.normalize_tiles(synth.make_tiles_u8(1, 64, seed=1))
+    ov = {"resnet.layer1.0.conv1": {"block_n": 32, "cta_pair": 0},        # Cout 64: narrower tile
+          "resnet.layer2.0.conv2": {"block_n": 64, "cta_pair": 0},
+          "resnet.layer3.0.conv1": {"block_n": 96, "cta_pair": 0},        # not a tile width: ignored
+          "resnet.layer4.1.conv2": {"block_n": 256, "cta_pair": 1},       # 1 x 2 x 2 pixels = one spatial tile: no pair possible, ignored
+          "dec2": {"block_n": 128, "cta_pair": 0}}                        # Cout 64 is not a multiple of 128: ignored
+    base = UNetEngine(sd, 2, 1, 64, 64, device="cpu", plan_only=True, precision="fast", plan_overrides={})
+    tuned = UNetEngine(sd, 2, 1, 64, 64, device="cpu", plan_only=True, precision="fast", plan_overrides=ov)
+    db = {op[1].name: op[1].desc for op in base.ops if op[0] == "conv"}
+    dt = {op[1].name: op[1].desc for op in tuned.ops if op[0] == "conv"}
+    assert dt["resnet.layer1.0.conv1"].block_n == 32 and dt["resnet.layer2.0.conv2"].block_n == 64
+    for name in ("resnet.layer3.0.conv1", "resnet.layer4.1.conv2", "dec2"):
+        assert (dt[name].block_n, dt[name].cta_pair) == (db[name].block_n, db[name].cta_pair), name
+    assert torch.equal(emulate.run_engine(base, x), emulate.run_engine(tuned, x))
