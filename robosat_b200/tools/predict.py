@@ -109,14 +109,15 @@ def run_shard(rank, world, args, device, sd, num_classes, stats=None):
     # cores -- split between the PNG-decode and PNG-encode pools (both run GIL-free C++ threads of the library).
     # More busy threads than the quota allows get the WHOLE process throttled for the rest of each scheduler period, the launching
     # thread included: the device then runs empty however deep the pipeline is (profiles/r2_cfg4.md). So: leave two cores to the
-    # main / consumer threads and the driver, and split the rest by measured cost: ~4.4 ms to decode a 512x512 RGB tile, ~1.3 ms
-    # to encode a probability mask (on one of those cores).
+    # main / consumer threads and the driver, and split the rest by measured cost: ~2.4 ms to decode a 512x512 RGB tile with the
+    # library's inflate, 1.1 - 1.4 ms to encode a probability mask (on one of those cores): two thirds decode, one third encodes.
     from robosat_b200.hostinfo import usable_cores
 
     cores = max(2, usable_cores() // max(world, 1))
     budget = max(2, min(72, cores - 2))
-    pool_threads = int(os.environ.get("RSB_PNG_THREADS", "0")) or max(1, budget // 4)
-    default_decode_threads = int(os.environ.get("RSB_DECODE_THREADS", "0")) or max(1, budget - max(1, budget // 4))
+    enc_default = max(1, (budget + 1) // 3)
+    pool_threads = int(os.environ.get("RSB_PNG_THREADS", "0")) or enc_default
+    default_decode_threads = int(os.environ.get("RSB_DECODE_THREADS", "0")) or max(1, budget - enc_default)
     st.update(host_cores=cores)
     st.update(pool_threads=pool_threads, gpu_wait_s=0.0, png_cpu_s=0.0)
 
