@@ -26,7 +26,7 @@ int main(int argc,char**argv){
       if(variant==2 && cn>1){ in_len=rand()%cn; in.resize(in_len); }
       if(variant==3){ out_len = n? (rand()%(2*n+1)) : 1; }
       // exact padding, allocated on the heap so ASAN sees any access beyond it
-      uint8_t* ib=(uint8_t*)malloc(in_len+kInflateInPad); memcpy(ib,in.data(),in_len); memset(ib+in_len,0,kInflateInPad);
+      uint8_t* ib=(uint8_t*)malloc(in_len+kInflateInPad); if (in_len) memcpy(ib, in.data(), in_len); memset(ib+in_len,0,kInflateInPad);
       uint8_t* ob=(uint8_t*)malloc(out_len+kInflateOutPad);
       int rc = in_len>=6 ? rsb_inflate_zlib_padded(ib,in_len,ob,out_len) : -2;
       if(rc==0){ if(out_len==n && memcmp(ob,src.data(),n)==0) ok++; else { // a successful decode must be THE data (adler verified) unless sizes differ legitimately
