@@ -130,6 +130,10 @@ def get_dataset_loaders(model, dataset, workers, rank=0, world=1):
     assert len(train_dataset) > 0, "at least one tile in training dataset"
     assert len(val_dataset) > 0, "at least one tile in validation dataset"
     if world > 1:
+        # Validation sees exactly the tiles the reference's single loader (train.py:265-268: batch_size, drop_last=True) sees:
+        # with the TOML batch split over the ranks (batch_size = B / world here) rank r takes tiles r, r + world, ... of the
+        # first floor(n / world) * world, and its loader keeps floor(floor(n / world) / (B / world)) = floor(n / B) batches --
+        # together the first floor(n / B) * B tiles, each once (tests/test_host_logic.py).
         ts = DistributedSampler(train_dataset, num_replicas=world, rank=rank, shuffle=True, drop_last=True)
         vs = DistributedSampler(val_dataset, num_replicas=world, rank=rank, shuffle=False, drop_last=True)
         train_loader = DataLoader(train_dataset, batch_size=batch_size, sampler=ts, drop_last=True, num_workers=workers)

@@ -228,3 +228,19 @@ def test_plan_overrides_change_the_tiles_not_the_result():
     for name in ("resnet.layer3.0.conv1", "resnet.layer4.1.conv2", "dec2"):
         assert (dt[name].block_n, dt[name].cta_pair) == (db[name].block_n, db[name].cta_pair), name
     assert torch.equal(emulate.run_engine(base, x), emulate.run_engine(tuned, x))
+
+
+def test_multi_rank_validation_covers_the_reference_tile_set():
+    """rs train on N ranks (TOML batch split over the ranks, DistributedSampler + loader, both drop_last) evaluates exactly the
+    validation tiles the reference's one DataLoader(batch_size=B, shuffle=False, drop_last=True) does, each once"""
+    from torch.utils.data import DataLoader
+    from torch.utils.data.distributed import DistributedSampler
+
+    for n, world, B in ((103, 2, 16), (37, 4, 8), (64, 8, 16), (15, 2, 16), (1000, 8, 32)):
+        data = list(range(n))
+        ref = [int(i) for batch in DataLoader(data, batch_size=B, shuffle=False, drop_last=True) for i in batch]
+        seen = []
+        for rank in range(world):
+            sampler = DistributedSampler(data, num_replicas=world, rank=rank, shuffle=False, drop_last=True)
+            seen += [int(i) for batch in DataLoader(data, batch_size=B // world, sampler=sampler, drop_last=True) for i in batch]
+        assert sorted(seen) == ref, (n, world, B)
