@@ -39,6 +39,7 @@ def add_parser(subparser):
 
 
 NATIVE_PNG = os.environ.get("RSB_PNG_ENCODER", "native") != "pil"
+PNG_LEVEL = min(9, max(0, int(os.environ.get("RSB_PNG_LEVEL", "6"))))  # zlib level of the library encoder (3: ~40 % less encode time, files 4 - 16 % larger)
 _PALETTE_BYTES = {}
 
 
@@ -57,7 +58,7 @@ def _save_png(root, palette, x, y, z, quantized, stats=None):
         if pal is None:
             pal = _PALETTE_BYTES.setdefault(id(palette), bytes(palette[:768]))
         q = quantized if quantized.flags["C_CONTIGUOUS"] else quantized.copy()
-        _lib.check(_lib.load().rsb_png_write_p8(os.fsencode(path), q.ctypes.data, q.shape[1], q.shape[0], pal, len(pal) // 3, 6), "rsb_png_write_p8")
+        _lib.check(_lib.load().rsb_png_write_p8(os.fsencode(path), q.ctypes.data, q.shape[1], q.shape[0], pal, len(pal) // 3, PNG_LEVEL), "rsb_png_write_p8")
     else:
         out = Image.fromarray(quantized, mode="P")
         out.putpalette(palette)
@@ -84,7 +85,7 @@ def _save_batch(root, palette, tiles, quantized, threads, stats=None):
         pal = _PALETTE_BYTES.setdefault(id(palette), bytes(palette[:768]))
     paths = (ctypes.c_char_p * n)(*[os.fsencode(os.path.join(root, str(z), str(x), str(y) + ".png")) for x, y, z in tiles])
     q = quantized if quantized.flags["C_CONTIGUOUS"] else quantized.copy()
-    _lib.check(_lib.load().rsb_png_write_p8_batch(paths, n, q.ctypes.data, q.shape[1] * q.shape[2], q.shape[2], q.shape[1], pal, len(pal) // 3, 6,
+    _lib.check(_lib.load().rsb_png_write_p8_batch(paths, n, q.ctypes.data, q.shape[1] * q.shape[2], q.shape[2], q.shape[1], pal, len(pal) // 3, PNG_LEVEL,
                                                   threads, 1), "rsb_png_write_p8_batch")
     if stats is not None:
         stats["png_cpu_s"] = stats.get("png_cpu_s", 0.0) + (time.perf_counter() - t0)  # wall time of the batch calls
