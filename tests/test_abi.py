@@ -58,3 +58,38 @@ def test_no_cpu_fallback_without_device():
 
     with pytest.raises(_lib.RsbError):
         UNetEngine(synth.make_state_dict(2), 2, 1, 64, 64, device="cpu")
+
+
+def test_descriptor_validation_runs_before_the_device_check():
+    """Argument errors are reported as RSB_E_INVALID on any host (validation never touches the device or dereferences the
+    pointers); a VALID descriptor then fails with RSB_E_NODEVICE here -- there is no CPU execution path behind a plan."""
+    import ctypes
+    import sys
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import conv_cases
+
+    lib = _lib.load()
+    plan = ctypes.c_void_p()
+    case = conv_cases.conv_case("1x1", 1, 16, 16, 64, 64, "cpu", relu=False, bias=False)
+    assert lib.rsb_conv_plan_create(ctypes.byref(case.desc), ctypes.byref(plan)) == -3          # valid, but no sm_100 device
+    buf = torch.zeros(1 << 16, dtype=torch.float32)
+    case.desc.stats, case.desc.stats_bytes = buf.data_ptr(), 64
+    assert lib.rsb_conv_plan_create(ctypes.byref(case.desc), ctypes.byref(plan)) == -1          # stats buffer too small
+    assert "stats" in _lib.last_error()
+    case.desc.stats_bytes = buf.numel() * 4
+    assert lib.rsb_conv_plan_create(ctypes.byref(case.desc), ctypes.byref(plan)) == -3
+    res = conv_cases.conv_case("1x1", 1, 16, 16, 64, 64, "cpu", relu=False, bias=False, residual=True)
+    res.desc.stats, res.desc.stats_bytes = buf.data_ptr(), buf.numel() * 4
+    assert lib.rsb_conv_plan_create(ctypes.byref(res.desc), ctypes.byref(plan)) == -1           # stats + residual
+    case.desc.stats = None
+    case.desc.block_n = 48
+    assert lib.rsb_conv_plan_create(ctypes.byref(case.desc), ctypes.byref(plan)) == -1           # not a tile width
+    # host codec entry points work without a device; the stream inflate rejects garbage
+    out = (ctypes.c_uint8 * 16)()
+    assert lib.rsb_zlib_inflate(b"\x78\x9c" + b"\xff" * 20, 22, out, 16) == -1
+    assert lib.rsb_pack_weights1(None, None, None, 8, None) == -1
